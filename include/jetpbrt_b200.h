@@ -1,0 +1,155 @@
+/* jetpbrt_b200.h -- the drop-in boundary: C ABI of libjetpbrt_b200.so.
+ *
+ * The reference has no FFI; its seam for the hot path is the C++ call
+ *     void FIntegrator::Render(const FScene*, FSampler*, FFilm*, int numthreads) const
+ * (reference src/integrator.h:32, sole call site main.cc:156) on a scene prepared by
+ * FScene::Preprocess (scene.cc:11-23), followed by FFilm::SaveAsImage (main.cc:160).
+ * This header is what a maintainer of the reference would bind instead (INTEGRATION.md shows the
+ * FIntegrator subclass that does it).  Plain pointers and sizes only; no C++ or torch types; every
+ * function returns 0 on success or a negative jpbrt_status, never throws, and records a message
+ * retrievable with jpbrt_last_error().  One host thread per context.
+ *
+ * There is NO CPU fallback: every compute entry point fails with JPBRT_ERR_CUDA when no sm_100
+ * device (or no CUDA driver) is present.
+ */
+#ifndef JETPBRT_B200_H
+#define JETPBRT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "jetpbrt_scene.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum jpbrt_status {
+    JPBRT_OK = 0,
+    JPBRT_ERR_INVALID = -1,     /* bad argument / malformed scene description */
+    JPBRT_ERR_CUDA = -2,        /* CUDA runtime error or no usable device */
+    JPBRT_ERR_UNSUPPORTED = -3, /* scene uses a feature outside the hot-path scope */
+    JPBRT_ERR_IO = -4
+} jpbrt_status;
+
+typedef struct jpbrt_ctx jpbrt_ctx;
+
+/* ------------------------------------------------------------------------------------------
+ * The render trio (BASELINE.json north_star: upload_scene / render_pass / read_film).
+ * ---------------------------------------------------------------------------------------- */
+
+/* Replaces FScene::Preprocess (scene.cc:11-23) + the scene graph the integrator reads
+ * (scene.h:139-149): computes shape normals/bounds, the world bound and the environment-light
+ * radius, builds and flattens the BVH on the host, and copies everything to `device`.
+ * The description is copied; the caller may free it afterwards. */
+int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out_ctx);
+
+/* Replaces FIntegrator::DoRender (integrator.cc:82-111) for sample indices
+ * [sample_begin, sample_begin + sample_count) of EVERY pixel: adds the raw radiance of each
+ * sample (FPathIntegratorIteration::Li, integrator.cc:316-403) into the device film.
+ * Asynchronous: work is queued on the context's stream.  The sampler is counter based: the
+ * result depends only on (seed, pixel, sample index), not on how samples are split into passes
+ * or across GPUs. */
+int jpbrt_render_pass(jpbrt_ctx* ctx, int sample_begin, int sample_count, uint64_t seed);
+
+/* Replaces FFilmView::AddColor(x, y, Clamp01(L)) (integrator.cc:108, film.h:64-68) and the film
+ * readback.  If `finalize` != 0 writes clamp01(sum / spp_total), else the raw sums.  `rgb` is
+ * host memory, width*height*3 floats, row 0 = top of the image (the reference's FFilm layout).
+ * Synchronises the stream. */
+int jpbrt_read_film(jpbrt_ctx* ctx, float* rgb, int spp_total, int finalize);
+
+/* Zero the device film (FFilm::Clear, film.h:75-82) and the work counters. */
+int jpbrt_clear_film(jpbrt_ctx* ctx);
+
+void        jpbrt_destroy(jpbrt_ctx* ctx);
+const char* jpbrt_last_error(const jpbrt_ctx* ctx); /* ctx may be NULL: last error of this thread */
+
+/* One call = FIntegrator::Render (integrator.cc:35-80): upload + all passes + finalize + readback
+ * into host memory.  `seconds_out` (optional) receives the wall time of the render part, the
+ * interval the reference prints (integrator.cc:77-79). */
+int jpbrt_render(const jpbrt_scene_desc* desc, int spp, uint64_t seed, int device, float* rgb, double* seconds_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Plumbing for multi-GPU (one process per GPU; the film sum is reduced by the caller with NCCL,
+ * e.g. torch.distributed.reduce on a tensor aliasing this buffer) and for timing.
+ * ---------------------------------------------------------------------------------------- */
+void*  jpbrt_film_device_ptr(jpbrt_ctx* ctx);             /* float32[width*height*3] raw sums, device memory */
+size_t jpbrt_film_num_floats(const jpbrt_ctx* ctx);
+void*  jpbrt_stream(jpbrt_ctx* ctx);                      /* cudaStream_t all work is queued on */
+int    jpbrt_synchronize(jpbrt_ctx* ctx);
+/* Finalise on the device: out[i] = clamp01(film[i] / spp_total); out may alias the film. */
+int    jpbrt_finalize_film_device(jpbrt_ctx* ctx, void* out_device, int spp_total);
+/* Re-upload the flattened scene arrays from the host copy kept in the context (what a per-frame
+ * caller pays for a changed scene); returns bytes copied through *bytes. */
+int    jpbrt_reupload_scene(jpbrt_ctx* ctx, size_t* bytes);
+
+/* Tunables: paths in flight per wavefront (0 = default), per-stage CUDA-event timing on/off,
+ * counting build of the traversal kernels on/off (node/primitive test counters). */
+int jpbrt_set_option(jpbrt_ctx* ctx, const char* name, long long value);
+
+typedef struct jpbrt_stats {
+    uint64_t samples;          /* camera paths started */
+    uint64_t extension_rays;   /* FScene::Intersect calls from Li (integrator.cc:327) */
+    uint64_t shadow_rays;      /* FScene::Occluded calls (integrator.cc:367) */
+    uint64_t shaded_vertices;
+    uint64_t box_tests;        /* only with option "count_traversal" = 1 */
+    uint64_t prim_tests;       /* only with option "count_traversal" = 1 */
+    uint64_t shadow_box_tests;
+    uint64_t shadow_prim_tests;
+    uint64_t invalid_contributions; /* NaN/inf radiance dropped instead of being stored */
+    uint64_t kernel_launches;  /* kernels of this library launched since the last clear */
+    double   ms_generate, ms_extend, ms_shade, ms_connect, ms_finalize; /* with option "stage_timing" = 1 */
+    uint64_t n_nodes, n_prim_slots, scene_bytes;
+    double   bvh_build_seconds;
+} jpbrt_stats;
+int jpbrt_get_stats(jpbrt_ctx* ctx, jpbrt_stats* out);
+
+/* ------------------------------------------------------------------------------------------
+ * Unit kernels: the device functions of the wavefront stages run on caller-supplied arrays, for
+ * parity tests against the reference's CPU functions on identical inputs.
+ * All pointers are HOST memory; arrays are copied in and out.  Layouts match oracle/oracle_api.h.
+ * ---------------------------------------------------------------------------------------- */
+/* FShape::Intersect on one shape (shape.h:291-327 / 399-435 / 487-526 / 199-221). rays8 = o,d,tmin,tmax */
+int jpbrt_unit_intersect_shape(const jpbrt_shape* shape, int device, int n, const float* rays8,
+                               int* hit, float* t, float* pos3, float* nrm3);
+/* FScene::Intersect (scene.cc:25-33) through the flattened BVH: the `extend` stage's traversal. */
+int jpbrt_unit_scene_intersect(jpbrt_ctx* ctx, int n, const float* rays8, int* prim, float* t, float* pos3, float* nrm3);
+/* FScene::Occluded (scene.h:36-47): the `connect` stage's any-hit traversal. */
+int jpbrt_unit_scene_occluded(jpbrt_ctx* ctx, int n, const float* pos3, const float* target3, int* occluded);
+/* material->Scattering + FBSDF::Evalf/Pdf/Sample (material.cc, bsdf.h:285-302): the `shade` stage's BSDF code. */
+int jpbrt_unit_bsdf(const jpbrt_material* mat, int device, int n,
+                    const float* nrm3, const float* wo3, const float* wi3, const float* u2, const float* ulobe,
+                    float* f_eval3, float* pdf_eval, float* s_wi3, float* s_f3, float* s_pdf, int* s_flags, int* is_delta);
+/* FLight::Sample_Li (light.h): the `shade` stage's next-event sampling. */
+int jpbrt_unit_light_sample(jpbrt_ctx* ctx, int light, int n, const float* pos3, const float* nrm3, const float* u2,
+                            float* lpos3, float* wi3, float* pdf, float* Li3);
+/* FPrimitive::GetLe (primitive.h:60-63). */
+int jpbrt_unit_emitted(jpbrt_ctx* ctx, int n, const int* prim, const float* nrm3, const float* wo3, float* Le3);
+/* FCamera::GenerateRay (camera.h:52-58): the `generate` stage. */
+int jpbrt_unit_generate_rays(jpbrt_ctx* ctx, int n, const float* posfilm2, float* o3, float* d3);
+/* The counter-based sampler's block (pixel, sample, block) -> 4 floats in [0,1). */
+int jpbrt_unit_rng_block(int device, int n, const uint32_t* pixel, const uint32_t* sample, const uint32_t* block,
+                         uint64_t seed, float* out4);
+/* Scene facts computed at upload: out[0..2] world min, [3..5] world max, [6] environment radius. */
+int jpbrt_scene_info(jpbrt_ctx* ctx, float* out7);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-side scene construction (C++ class jetpbrt::Scene, host/scene.h) behind C handles:
+ * the five BASELINE.json configurations and OBJ ingestion.  No GPU needed.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct jpbrt_scene jpbrt_scene;
+/* name: "cornell" (C1/C5), "bunny" (C2), "large" (C3), "glossy" (C4). scale: mesh-resolution
+ * multiplier for bunny/large (1 = the configuration's full size). */
+jpbrt_scene*            jpbrt_scene_builtin(const char* name, int width, int height, float scale);
+const jpbrt_scene_desc* jpbrt_scene_get_desc(jpbrt_scene* s);
+void                    jpbrt_scene_free(jpbrt_scene* s);
+
+/* FFilm::SaveAsImage (film.cc:13-43): kind 0 = PPM, 1 = BMP, 2 = HDR; `basename` without extension. */
+int jpbrt_save_image(const char* basename, int kind, int width, int height, const float* rgb);
+
+const char* jpbrt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JETPBRT_B200_H */

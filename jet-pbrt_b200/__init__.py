@@ -1,0 +1,383 @@
+"""jet-pbrt_b200 -- thin ctypes binding of libjetpbrt_b200.so (include/jetpbrt_b200.h).
+
+This package is plumbing for tests, bench.py and multi-GPU launches (torch.distributed); the
+product is the shared library: host C++ (scene description, BVH build) + hand-written sm_100a
+CUDA (wavefront path tracer).  Nothing here computes: if the library is missing the import
+fails loudly, and every compute call fails with an exception when no B200 is present.
+
+The directory name has a hyphen (the reference's name); import it through
+``__graft_entry__.load_package()`` which registers it as ``jet_pbrt_b200``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libjetpbrt_b200.so"
+
+
+# ---- include/jetpbrt_scene.h --------------------------------------------------------------------
+class Camera(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("front", C.c_float * 3), ("up", C.c_float * 3),
+                ("vfov_deg", C.c_float), ("width", C.c_int), ("height", C.c_int)]
+
+
+class Shape(C.Structure):
+    _fields_ = [("type", C.c_int), ("flip_normal", C.c_int), ("p", (C.c_float * 3) * 4)]
+
+
+class Material(C.Structure):
+    _fields_ = [("type", C.c_int), ("remap_roughness", C.c_int), ("a", C.c_float * 3), ("b", C.c_float * 3),
+                ("f0", C.c_float), ("f1", C.c_float)]
+
+
+class Light(C.Structure):
+    _fields_ = [("type", C.c_int), ("shape", C.c_int), ("color", C.c_float * 3), ("pos", C.c_float * 3),
+                ("dir", C.c_float * 3)]
+
+
+class Primitive(C.Structure):
+    _fields_ = [("shape", C.c_int), ("material", C.c_int), ("light", C.c_int)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("camera", Camera), ("max_depth", C.c_int), ("n_shapes", C.c_int), ("n_materials", C.c_int),
+                ("n_lights", C.c_int), ("n_primitives", C.c_int),
+                ("shapes", C.POINTER(Shape)), ("materials", C.POINTER(Material)), ("lights", C.POINTER(Light)),
+                ("primitives", C.POINTER(Primitive)), ("name", C.c_char_p)]
+
+
+SHAPE_TRIANGLE, SHAPE_RECTANGLE, SHAPE_SPHERE, SHAPE_DISK = 0, 1, 2, 3
+MAT_MATTE, MAT_MIRROR, MAT_GLASS, MAT_PLASTIC, MAT_METAL = 0, 1, 2, 3, 4
+LIGHT_ENVIRONMENT, LIGHT_AREA, LIGHT_POINT, LIGHT_DIRECTION = 0, 1, 2, 3
+
+
+class Stats(C.Structure):
+    _fields_ = [("samples", C.c_uint64), ("extension_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("shaded_vertices", C.c_uint64), ("box_tests", C.c_uint64), ("prim_tests", C.c_uint64),
+                ("shadow_box_tests", C.c_uint64), ("shadow_prim_tests", C.c_uint64),
+                ("invalid_contributions", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("ms_generate", C.c_double), ("ms_extend", C.c_double), ("ms_shade", C.c_double),
+                ("ms_connect", C.c_double), ("ms_finalize", C.c_double),
+                ("n_nodes", C.c_uint64), ("n_prim_slots", C.c_uint64), ("scene_bytes", C.c_uint64),
+                ("bvh_build_seconds", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# Every symbol include/jetpbrt_b200.h declares (tests check the library exports them all).
+EXPORTS = [
+    "jpbrt_upload_scene", "jpbrt_render_pass", "jpbrt_read_film", "jpbrt_clear_film", "jpbrt_destroy",
+    "jpbrt_last_error", "jpbrt_render", "jpbrt_film_device_ptr", "jpbrt_film_num_floats", "jpbrt_stream",
+    "jpbrt_synchronize", "jpbrt_finalize_film_device", "jpbrt_reupload_scene", "jpbrt_set_option",
+    "jpbrt_get_stats", "jpbrt_unit_intersect_shape", "jpbrt_unit_scene_intersect", "jpbrt_unit_scene_occluded",
+    "jpbrt_unit_bsdf", "jpbrt_unit_light_sample", "jpbrt_unit_emitted", "jpbrt_unit_generate_rays",
+    "jpbrt_unit_rng_block", "jpbrt_scene_info", "jpbrt_scene_builtin", "jpbrt_scene_get_desc",
+    "jpbrt_scene_free", "jpbrt_save_image", "jpbrt_version",
+]
+
+
+class JpbrtError(RuntimeError):
+    pass
+
+
+def _load():
+    if not LIB_PATH.exists():
+        raise ImportError(f"{LIB_PATH} is missing: build it with `make -C {_HERE}` "
+                          "(or __graft_entry__.build()); there is no Python/CPU fallback")
+    lib = C.CDLL(str(LIB_PATH))
+    P, I, F = C.c_void_p, C.c_int, C.POINTER(C.c_float)
+    IP = C.POINTER(C.c_int)
+    lib.jpbrt_version.restype = C.c_char_p
+    lib.jpbrt_last_error.restype = C.c_char_p
+    lib.jpbrt_last_error.argtypes = [P]
+    lib.jpbrt_upload_scene.argtypes = [C.POINTER(SceneDesc), I, C.POINTER(P)]
+    lib.jpbrt_render_pass.argtypes = [P, I, I, C.c_uint64]
+    lib.jpbrt_read_film.argtypes = [P, F, I, I]
+    lib.jpbrt_clear_film.argtypes = [P]
+    lib.jpbrt_destroy.argtypes = [P]
+    lib.jpbrt_destroy.restype = None
+    lib.jpbrt_render.argtypes = [C.POINTER(SceneDesc), I, C.c_uint64, I, F, C.POINTER(C.c_double)]
+    lib.jpbrt_film_device_ptr.argtypes = [P]
+    lib.jpbrt_film_device_ptr.restype = P
+    lib.jpbrt_film_num_floats.argtypes = [P]
+    lib.jpbrt_film_num_floats.restype = C.c_size_t
+    lib.jpbrt_stream.argtypes = [P]
+    lib.jpbrt_stream.restype = P
+    lib.jpbrt_synchronize.argtypes = [P]
+    lib.jpbrt_finalize_film_device.argtypes = [P, P, I]
+    lib.jpbrt_reupload_scene.argtypes = [P, C.POINTER(C.c_size_t)]
+    lib.jpbrt_set_option.argtypes = [P, C.c_char_p, C.c_longlong]
+    lib.jpbrt_get_stats.argtypes = [P, C.POINTER(Stats)]
+    lib.jpbrt_unit_intersect_shape.argtypes = [C.POINTER(Shape), I, I, F, IP, F, F, F]
+    lib.jpbrt_unit_scene_intersect.argtypes = [P, I, F, IP, F, F, F]
+    lib.jpbrt_unit_scene_occluded.argtypes = [P, I, F, F, IP]
+    lib.jpbrt_unit_bsdf.argtypes = [C.POINTER(Material), I, I, F, F, F, F, F, F, F, F, F, F, IP, IP]
+    lib.jpbrt_unit_light_sample.argtypes = [P, I, I, F, F, F, F, F, F, F]
+    lib.jpbrt_unit_emitted.argtypes = [P, I, IP, F, F, F]
+    lib.jpbrt_unit_generate_rays.argtypes = [P, I, F, F, F]
+    lib.jpbrt_unit_rng_block.argtypes = [I, I, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                         C.c_uint64, F]
+    lib.jpbrt_scene_info.argtypes = [P, F]
+    lib.jpbrt_scene_builtin.argtypes = [C.c_char_p, I, I, C.c_float]
+    lib.jpbrt_scene_builtin.restype = P
+    lib.jpbrt_scene_get_desc.argtypes = [P]
+    lib.jpbrt_scene_get_desc.restype = C.POINTER(SceneDesc)
+    lib.jpbrt_scene_free.argtypes = [P]
+    lib.jpbrt_scene_free.restype = None
+    lib.jpbrt_save_image.argtypes = [C.c_char_p, I, I, I, F]
+    return lib
+
+
+lib = _load()
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _i(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _check(rc, ctx=None):
+    if rc != 0:
+        msg = lib.jpbrt_last_error(ctx)
+        raise JpbrtError(f"jetpbrt_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+# ---- scenes --------------------------------------------------------------------------------------
+class HostScene:
+    """A scene description owned by the host library (jetpbrt::Scene) or built in Python."""
+
+    def __init__(self, handle=None, desc=None, keepalive=None):
+        self._handle = handle
+        self._desc = desc
+        self._keepalive = keepalive
+
+    @classmethod
+    def builtin(cls, name: str, width: int, height: int, scale: float = 1.0) -> "HostScene":
+        h = lib.jpbrt_scene_builtin(name.encode(), width, height, scale)
+        if not h:
+            raise JpbrtError(f"unknown built-in scene {name!r}")
+        return cls(handle=h, desc=lib.jpbrt_scene_get_desc(h))
+
+    @classmethod
+    def from_arrays(cls, camera: Camera, shapes, materials, lights, primitives, max_depth=5, name="scene"):
+        """Build a description from Python lists of Shape/Material/Light/Primitive structs."""
+        sa = (Shape * max(1, len(shapes)))(*shapes)
+        ma = (Material * max(1, len(materials)))(*materials)
+        la = (Light * max(1, len(lights)))(*lights)
+        pa = (Primitive * max(1, len(primitives)))(*primitives)
+        nm = name.encode()
+        d = SceneDesc(camera, max_depth, len(shapes), len(materials), len(lights), len(primitives),
+                      C.cast(sa, C.POINTER(Shape)), C.cast(ma, C.POINTER(Material)), C.cast(la, C.POINTER(Light)),
+                      C.cast(pa, C.POINTER(Primitive)), nm)
+        return cls(desc=C.pointer(d), keepalive=(sa, ma, la, pa, nm, d))
+
+    @property
+    def desc(self):
+        return self._desc
+
+    @property
+    def d(self) -> SceneDesc:
+        return self._desc.contents
+
+    def set_max_depth(self, depth: int):
+        self._desc.contents.max_depth = depth
+
+    def set_resolution(self, w: int, h: int):
+        self._desc.contents.camera.width = w
+        self._desc.contents.camera.height = h
+
+    def close(self):
+        if self._handle:
+            lib.jpbrt_scene_free(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- device context --------------------------------------------------------------------------------
+class Context:
+    """jpbrt_ctx: a scene uploaded to one GPU plus its film and wavefront buffers."""
+
+    def __init__(self, scene: HostScene, device: int = 0):
+        self._ctx = C.c_void_p()
+        self.scene = scene
+        rc = lib.jpbrt_upload_scene(scene.desc, device, C.byref(self._ctx))
+        _check(rc, None)
+        self.width = scene.d.camera.width
+        self.height = scene.d.camera.height
+        self.device = device
+
+    # the render trio
+    def render_pass(self, sample_begin: int, sample_count: int, seed: int = 1234):
+        _check(lib.jpbrt_render_pass(self._ctx, sample_begin, sample_count, seed), self._ctx)
+
+    def read_film(self, spp_total: int = 1, finalize: bool = True, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.height, self.width, 3), dtype=np.float32)
+        _check(lib.jpbrt_read_film(self._ctx, _f(out), spp_total, 1 if finalize else 0), self._ctx)
+        return out
+
+    def clear_film(self):
+        _check(lib.jpbrt_clear_film(self._ctx), self._ctx)
+
+    def synchronize(self):
+        _check(lib.jpbrt_synchronize(self._ctx), self._ctx)
+
+    def set_option(self, name: str, value: int):
+        _check(lib.jpbrt_set_option(self._ctx, name.encode(), value), self._ctx)
+
+    def stats(self) -> dict:
+        s = Stats()
+        _check(lib.jpbrt_get_stats(self._ctx, C.byref(s)), self._ctx)
+        return s.as_dict()
+
+    def reupload_scene(self) -> int:
+        n = C.c_size_t(0)
+        _check(lib.jpbrt_reupload_scene(self._ctx, C.byref(n)), self._ctx)
+        return n.value
+
+    def film_device_ptr(self) -> int:
+        return lib.jpbrt_film_device_ptr(self._ctx)
+
+    def film_num_floats(self) -> int:
+        return lib.jpbrt_film_num_floats(self._ctx)
+
+    def stream(self) -> int:
+        return lib.jpbrt_stream(self._ctx) or 0
+
+    def finalize_film_device(self, out_ptr: int, spp_total: int):
+        _check(lib.jpbrt_finalize_film_device(self._ctx, out_ptr, spp_total), self._ctx)
+
+    def film_tensor(self):
+        """The raw-sum device film as a torch tensor aliasing the context's buffer (for NCCL)."""
+        import torch
+
+        n = self.film_num_floats()
+        ptr = self.film_device_ptr()
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+        return torch.as_tensor(_Arr(), device=f"cuda:{self.device}")
+
+    def scene_info(self) -> np.ndarray:
+        o = np.zeros(7, dtype=np.float32)
+        _check(lib.jpbrt_scene_info(self._ctx, _f(o)), self._ctx)
+        return o
+
+    # unit kernels
+    def unit_scene_intersect(self, rays8):
+        rays8 = _f32(rays8, (-1, 8))
+        n = len(rays8)
+        prim = np.empty(n, np.int32); t = np.empty(n, np.float32)
+        pos = np.empty((n, 3), np.float32); nrm = np.empty((n, 3), np.float32)
+        _check(lib.jpbrt_unit_scene_intersect(self._ctx, n, _f(rays8), _i(prim), _f(t), _f(pos), _f(nrm)), self._ctx)
+        return prim, t, pos, nrm
+
+    def unit_scene_occluded(self, pos3, target3):
+        pos3 = _f32(pos3, (-1, 3)); target3 = _f32(target3, (-1, 3))
+        n = len(pos3)
+        occ = np.empty(n, np.int32)
+        _check(lib.jpbrt_unit_scene_occluded(self._ctx, n, _f(pos3), _f(target3), _i(occ)), self._ctx)
+        return occ
+
+    def unit_light_sample(self, light, pos3, nrm3, u2):
+        pos3 = _f32(pos3, (-1, 3)); nrm3 = _f32(nrm3, (-1, 3)); u2 = _f32(u2, (-1, 2))
+        n = len(pos3)
+        lpos = np.empty((n, 3), np.float32); wi = np.empty((n, 3), np.float32)
+        pdf = np.empty(n, np.float32); Li = np.empty((n, 3), np.float32)
+        _check(lib.jpbrt_unit_light_sample(self._ctx, light, n, _f(pos3), _f(nrm3), _f(u2), _f(lpos), _f(wi), _f(pdf), _f(Li)), self._ctx)
+        return lpos, wi, pdf, Li
+
+    def unit_emitted(self, prim, nrm3, wo3):
+        prim = np.ascontiguousarray(prim, np.int32); nrm3 = _f32(nrm3, (-1, 3)); wo3 = _f32(wo3, (-1, 3))
+        n = len(prim)
+        Le = np.empty((n, 3), np.float32)
+        _check(lib.jpbrt_unit_emitted(self._ctx, n, _i(prim), _f(nrm3), _f(wo3), _f(Le)), self._ctx)
+        return Le
+
+    def unit_generate_rays(self, posfilm2):
+        posfilm2 = _f32(posfilm2, (-1, 2))
+        n = len(posfilm2)
+        o = np.empty((n, 3), np.float32); d = np.empty((n, 3), np.float32)
+        _check(lib.jpbrt_unit_generate_rays(self._ctx, n, _f(posfilm2), _f(o), _f(d)), self._ctx)
+        return o, d
+
+    def close(self):
+        if self._ctx:
+            lib.jpbrt_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def unit_intersect_shape(shape: Shape, rays8, device: int = 0):
+    rays8 = _f32(rays8, (-1, 8))
+    n = len(rays8)
+    hit = np.empty(n, np.int32); t = np.empty(n, np.float32)
+    pos = np.empty((n, 3), np.float32); nrm = np.empty((n, 3), np.float32)
+    _check(lib.jpbrt_unit_intersect_shape(C.byref(shape), device, n, _f(rays8), _i(hit), _f(t), _f(pos), _f(nrm)))
+    return hit, t, pos, nrm
+
+
+def unit_bsdf(mat: Material, nrm3, wo3, wi3, u2, ulobe, device: int = 0):
+    nrm3 = _f32(nrm3, (-1, 3)); wo3 = _f32(wo3, (-1, 3)); wi3 = _f32(wi3, (-1, 3)); u2 = _f32(u2, (-1, 2)); ulobe = _f32(ulobe, (-1,))
+    n = len(nrm3)
+    fe = np.empty((n, 3), np.float32); pe = np.empty(n, np.float32); swi = np.empty((n, 3), np.float32)
+    sf = np.empty((n, 3), np.float32); sp = np.empty(n, np.float32); fl = np.empty(n, np.int32); dl = np.empty(n, np.int32)
+    _check(lib.jpbrt_unit_bsdf(C.byref(mat), device, n, _f(nrm3), _f(wo3), _f(wi3), _f(u2), _f(ulobe), _f(fe), _f(pe),
+                               _f(swi), _f(sf), _f(sp), _i(fl), _i(dl)))
+    return dict(f_eval=fe, pdf_eval=pe, s_wi=swi, s_f=sf, s_pdf=sp, s_flags=fl, is_delta=dl)
+
+
+def unit_rng_block(pixel, sample, block, seed: int, device: int = 0):
+    pixel = np.ascontiguousarray(pixel, np.uint32); sample = np.ascontiguousarray(sample, np.uint32)
+    block = np.ascontiguousarray(block, np.uint32)
+    n = len(pixel)
+    out = np.empty((n, 4), np.float32)
+    u32p = C.POINTER(C.c_uint32)
+    _check(lib.jpbrt_unit_rng_block(device, n, pixel.ctypes.data_as(u32p), sample.ctypes.data_as(u32p),
+                                    block.ctypes.data_as(u32p), seed, _f(out)))
+    return out
+
+
+def render(scene: HostScene, spp: int, seed: int = 1234, device: int = 0):
+    """FIntegrator::Render equivalent: returns (film[h,w,3] = clamp01(mean), seconds)."""
+    out = np.empty((scene.d.camera.height, scene.d.camera.width, 3), dtype=np.float32)
+    sec = C.c_double(0)
+    _check(lib.jpbrt_render(scene.desc, spp, seed, device, _f(out), C.byref(sec)))
+    return out, sec.value
+
+
+def save_image(basename: str, kind: int, film: np.ndarray):
+    film = _f32(film)
+    h, w = film.shape[0], film.shape[1]
+    _check(lib.jpbrt_save_image(basename.encode(), kind, w, h, _f(film)))
+
+
+def version() -> str:
+    return lib.jpbrt_version().decode()

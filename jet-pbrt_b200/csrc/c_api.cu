@@ -1,0 +1,759 @@
+// c_api.cu -- implementation of the C ABI in include/jetpbrt_b200.h (device side).
+//
+// jpbrt_upload_scene / jpbrt_render_pass / jpbrt_read_film replace, for the hot path, the
+// reference's FScene::Preprocess + FIntegrator::Render/DoRender + FFilmView::AddColor
+// (scene.cc:11-23, integrator.cc:35-111, film.h:64-68).  There is no CPU fallback in this file:
+// every entry point that computes launches CUDA kernels and reports JPBRT_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/jetpbrt_b200.h"
+#include "scene_flatten.h"
+#include "wavefront.cuh"
+
+using namespace jpbrt;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int set_error(jpbrt_ctx* ctx, int code, const char* fmt, ...);
+
+#define CU_CHECK(ctx, call)                                                                             \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return set_error(ctx, JPBRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* ptr = nullptr;
+    size_t count = 0;
+    cudaError_t Alloc(size_t n) {
+        Free();
+        if (n == 0) n = 1;
+        cudaError_t e = cudaMalloc(&ptr, n * sizeof(T));
+        if (e == cudaSuccess) count = n; else ptr = nullptr;
+        return e;
+    }
+    cudaError_t Upload(const T* host, size_t n, cudaStream_t s) {
+        if (n == 0) return cudaSuccess;
+        return cudaMemcpyAsync(ptr, host, n * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    void Free() { if (ptr) cudaFree(ptr); ptr = nullptr; count = 0; }
+    ~DevBuf() { Free(); }
+};
+
+struct StageEvent {
+    cudaEvent_t a, b;
+    int stage;
+};
+
+}  // namespace
+
+struct jpbrt_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    HostScene hs;
+    // scene on the device
+    DevBuf<Float4> nodes, slots, slot_nrm, materials, lights;
+    DevBuf<Int2> slot_ml;
+    DevBuf<int> inf_lights, prim_slot;
+    DevScene dsc{};
+    // wavefront state
+    long long paths_in_flight = 0;  // capacity of the path pool
+    DevBuf<float4> ray_o[2], ray_d[2], ray_b[2], sh_o, sh_d, sh_c;
+    DevBuf<float2> hit;
+    DevBuf<int> counters;
+    int counter_stride = 0;
+    int n_iters = 0;
+    DevBuf<float> film;
+    DevBuf<unsigned long long> dstats;
+    // options
+    long long opt_paths_in_flight = 0;
+    bool opt_stage_timing = false;
+    bool opt_count_traversal = false;
+    // launch geometry
+    int grid_generate = 0, grid_extend = 0, grid_extend_c = 0, grid_shade = 0, grid_connect = 0, grid_connect_c = 0, grid_finalize = 0;
+    // host-side accounting
+    unsigned long long kernel_launches = 0;
+    double ms_stage[5] = {0, 0, 0, 0, 0};
+    std::vector<StageEvent> pending_events;
+    std::vector<cudaEvent_t> free_events;
+};
+
+namespace {
+
+int set_error(jpbrt_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (ctx) ctx->error = buf;
+    return code;
+}
+
+int select_device(jpbrt_ctx* ctx, int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return set_error(ctx, JPBRT_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return set_error(ctx, JPBRT_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+    CU_CHECK(ctx, cudaSetDevice(device));
+    return 0;
+}
+
+cudaEvent_t get_event(jpbrt_ctx* c) {
+    if (!c->free_events.empty()) { cudaEvent_t e = c->free_events.back(); c->free_events.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct StageTimer {
+    jpbrt_ctx* c;
+    int stage;
+    cudaEvent_t a = nullptr, b = nullptr;
+    StageTimer(jpbrt_ctx* ctx, int st) : c(ctx), stage(st) {
+        if (c->opt_stage_timing) { a = get_event(c); b = get_event(c); cudaEventRecord(a, c->stream); }
+    }
+    ~StageTimer() {
+        if (c->opt_stage_timing) { cudaEventRecord(b, c->stream); c->pending_events.push_back(StageEvent{a, b, stage}); }
+    }
+};
+
+void drain_events(jpbrt_ctx* c) {
+    for (auto& ev : c->pending_events) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) c->ms_stage[ev.stage] += ms;
+        c->free_events.push_back(ev.a);
+        c->free_events.push_back(ev.b);
+    }
+    c->pending_events.clear();
+}
+
+template <typename K>
+int occupancy_grid(jpbrt_ctx* c, K kernel) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0) != cudaSuccess || per_sm <= 0) per_sm = 1;
+    return c->sm_count * per_sm;
+}
+
+int upload_arrays(jpbrt_ctx* c, size_t* bytes) {
+    HostScene& hs = c->hs;
+    CU_CHECK(c, c->nodes.Upload(hs.nodes.data(), hs.nodes.size(), c->stream));
+    CU_CHECK(c, c->slots.Upload(hs.slots.data(), hs.slots.size(), c->stream));
+    CU_CHECK(c, c->slot_nrm.Upload(hs.slot_nrm.data(), hs.slot_nrm.size(), c->stream));
+    CU_CHECK(c, c->slot_ml.Upload(hs.slot_ml.data(), hs.slot_ml.size(), c->stream));
+    CU_CHECK(c, c->materials.Upload(hs.materials.data(), hs.materials.size(), c->stream));
+    CU_CHECK(c, c->lights.Upload(hs.lights.data(), hs.lights.size(), c->stream));
+    CU_CHECK(c, c->inf_lights.Upload(hs.inf_lights.data(), hs.inf_lights.size(), c->stream));
+    CU_CHECK(c, c->prim_slot.Upload(hs.prim_slot.data(), hs.prim_slot.size(), c->stream));
+    if (bytes) *bytes = hs.Bytes();
+    return 0;
+}
+
+int ensure_pool(jpbrt_ctx* c) {
+    const long long npix = (long long)c->hs.width * c->hs.height;
+    long long want = c->opt_paths_in_flight > 0 ? c->opt_paths_in_flight : (1ll << 23);
+    // whole samples only: the pool holds k full-frame samples
+    long long k = std::max(1ll, want / npix);
+    long long cap = k * npix;
+    if (cap > 0x7fff0000ll) return set_error(c, JPBRT_ERR_UNSUPPORTED, "film too large for one wavefront (%lld pixels)", npix);
+    int n_lights = std::max(1, (int)(c->hs.lights.size() / kLightStride));
+    long long shadow_cap = cap * n_lights;
+    if (shadow_cap > 0x7fff0000ll) {  // keep queue indices in int range
+        k = std::max(1ll, 0x7fff0000ll / (npix * n_lights));
+        cap = k * npix;
+        shadow_cap = cap * n_lights;
+        if (shadow_cap > 0x7fff0000ll) return set_error(c, JPBRT_ERR_UNSUPPORTED, "pixels x lights too large for one wavefront");
+    }
+    if (cap == c->paths_in_flight) return 0;
+    for (int b = 0; b < 2; ++b) {
+        CU_CHECK(c, c->ray_o[b].Alloc(cap));
+        CU_CHECK(c, c->ray_d[b].Alloc(cap));
+        CU_CHECK(c, c->ray_b[b].Alloc(cap));
+    }
+    CU_CHECK(c, c->hit.Alloc(cap));
+    CU_CHECK(c, c->sh_o.Alloc(shadow_cap));
+    CU_CHECK(c, c->sh_d.Alloc(shadow_cap));
+    CU_CHECK(c, c->sh_c.Alloc(shadow_cap));
+    c->paths_in_flight = cap;
+    return 0;
+}
+
+WfParams make_params(jpbrt_ctx* c, int sample_begin, uint64_t seed) {
+    WfParams p{};
+    p.sc = c->dsc;
+    for (int b = 0; b < 2; ++b) { p.ray_o[b] = c->ray_o[b].ptr; p.ray_d[b] = c->ray_d[b].ptr; p.ray_b[b] = c->ray_b[b].ptr; }
+    p.hit = c->hit.ptr;
+    p.sh_o = c->sh_o.ptr;
+    p.sh_d = c->sh_d.ptr;
+    p.sh_c = c->sh_c.ptr;
+    p.counters = c->counters.ptr;
+    p.counter_stride = c->counter_stride;
+    p.film = c->film.ptr;
+    p.stats = c->dstats.ptr;
+    p.key.k0 = (uint32_t)seed;
+    p.key.k1 = (uint32_t)(seed >> 32);
+    p.sample_begin = sample_begin;
+    p.npix = c->hs.width * c->hs.height;
+    p.blocks_per_bounce = rng_blocks_per_bounce(c->dsc.n_lights);
+    p.shadow_capacity = (int)std::min<size_t>(c->sh_o.count, 0x7fffffff);
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* jpbrt_version(void) { return "jet-pbrt_b200 0.1 (sm_100a wavefront path tracer)"; }
+
+const char* jpbrt_last_error(const jpbrt_ctx* ctx) { return ctx ? ctx->error.c_str() : g_last_error.c_str(); }
+
+int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out_ctx) {
+    if (!out_ctx) return set_error(nullptr, JPBRT_ERR_INVALID, "out_ctx is null");
+    *out_ctx = nullptr;
+    jpbrt_ctx* c = new jpbrt_ctx();
+    std::string err;
+    int rc = FlattenScene(desc, &c->hs, &err);
+    if (rc != 0) { set_error(nullptr, rc, "%s", err.c_str()); delete c; return rc; }
+    rc = select_device(nullptr, device);
+    if (rc != 0) { delete c; return rc; }
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    auto fail = [&](int code) { jpbrt_destroy(c); return code; };
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError())));
+    HostScene& hs = c->hs;
+    cudaError_t e = cudaSuccess;
+    if ((e = c->nodes.Alloc(hs.nodes.size())) != cudaSuccess || (e = c->slots.Alloc(hs.slots.size())) != cudaSuccess ||
+        (e = c->slot_nrm.Alloc(hs.slot_nrm.size())) != cudaSuccess || (e = c->slot_ml.Alloc(hs.slot_ml.size())) != cudaSuccess ||
+        (e = c->materials.Alloc(hs.materials.size())) != cudaSuccess || (e = c->lights.Alloc(hs.lights.size())) != cudaSuccess ||
+        (e = c->inf_lights.Alloc(hs.inf_lights.size())) != cudaSuccess || (e = c->prim_slot.Alloc(hs.prim_slot.size())) != cudaSuccess ||
+        (e = c->film.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess || (e = c->dstats.Alloc(ST_COUNT)) != cudaSuccess)
+        return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)));
+    rc = upload_arrays(c, nullptr);
+    if (rc != 0) { g_last_error = c->error; return fail(rc); }
+    DevScene& d = c->dsc;
+    d.nodes = c->nodes.ptr; d.slots = c->slots.ptr; d.slot_nrm = c->slot_nrm.ptr; d.slot_ml = c->slot_ml.ptr;
+    d.materials = c->materials.ptr; d.lights = c->lights.ptr; d.inf_lights = c->inf_lights.ptr; d.prim_slot = c->prim_slot.ptr;
+    d.n_nodes = (int)(hs.nodes.size() / kNodeStride);
+    d.n_slots = (int)hs.slot_nrm.size();
+    d.n_materials = (int)(hs.materials.size() / kMaterialStride);
+    d.n_lights = (int)(hs.lights.size() / kLightStride);
+    d.n_inf_lights = (int)hs.inf_lights.size();
+    d.n_prims = hs.n_prims;
+    d.max_depth = hs.max_depth;
+    d.width = hs.width;
+    d.height = hs.height;
+    d.world_radius = hs.world_radius;
+    d.cam = hs.cam;
+    // iterations: bounces 0..max_depth, plus slack for null-material pass-through vertices
+    c->n_iters = hs.max_depth + 1 + (hs.has_null_material ? 16 : 0);
+    c->counter_stride = c->n_iters + 2;
+    if ((e = c->counters.Alloc((size_t)CNT_KINDS * c->counter_stride)) != cudaSuccess)
+        return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)));
+    c->grid_generate = occupancy_grid(c, k_generate);
+    c->grid_extend = occupancy_grid(c, k_extend<false>);
+    c->grid_extend_c = occupancy_grid(c, k_extend<true>);
+    c->grid_shade = occupancy_grid(c, k_shade);
+    c->grid_connect = occupancy_grid(c, k_connect<false>);
+    c->grid_connect_c = occupancy_grid(c, k_connect<true>);
+    c->grid_finalize = occupancy_grid(c, k_finalize);
+    rc = jpbrt_clear_film(c);
+    if (rc != 0) { g_last_error = c->error; return fail(rc); }
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess)
+        return fail(set_error(nullptr, JPBRT_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e)));
+    *out_ctx = c;
+    return 0;
+}
+
+int jpbrt_reupload_scene(jpbrt_ctx* c, size_t* bytes) {
+    if (!c) return set_error(nullptr, JPBRT_ERR_INVALID, "ctx is null");
+    CU_CHECK(c, cudaSetDevice(c->device));
+    return upload_arrays(c, bytes);
+}
+
+int jpbrt_clear_film(jpbrt_ctx* c) {
+    if (!c) return set_error(nullptr, JPBRT_ERR_INVALID, "ctx is null");
+    CU_CHECK(c, cudaSetDevice(c->device));
+    CU_CHECK(c, cudaMemsetAsync(c->film.ptr, 0, c->film.count * sizeof(float), c->stream));
+    CU_CHECK(c, cudaMemsetAsync(c->dstats.ptr, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
+    c->kernel_launches = 0;
+    for (double& m : c->ms_stage) m = 0;
+    return 0;
+}
+
+int jpbrt_set_option(jpbrt_ctx* c, const char* name, long long value) {
+    if (!c || !name) return set_error(c, JPBRT_ERR_INVALID, "null argument");
+    if (!strcmp(name, "paths_in_flight")) { c->opt_paths_in_flight = value; return 0; }
+    if (!strcmp(name, "stage_timing")) { c->opt_stage_timing = value != 0; return 0; }
+    if (!strcmp(name, "count_traversal")) { c->opt_count_traversal = value != 0; return 0; }
+    return set_error(c, JPBRT_ERR_INVALID, "unknown option '%s'", name);
+}
+
+int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t seed) {
+    if (!c) return set_error(nullptr, JPBRT_ERR_INVALID, "ctx is null");
+    if (sample_begin < 0 || sample_count < 0 || (long long)sample_begin + sample_count > 0xffffff)
+        return set_error(c, JPBRT_ERR_INVALID, "sample range [%d, %d) outside [0, 2^24)", sample_begin, sample_begin + sample_count);
+    CU_CHECK(c, cudaSetDevice(c->device));
+    int rc = ensure_pool(c);
+    if (rc != 0) return rc;
+    const long long npix = (long long)c->hs.width * c->hs.height;
+    const int chunk = (int)(c->paths_in_flight / npix);
+    const bool count = c->opt_count_traversal;
+    for (int done = 0; done < sample_count;) {
+        const int spp = std::min(chunk, sample_count - done);
+        const int n_paths = (int)(npix * spp);
+        WfParams p = make_params(c, sample_begin + done, seed);
+        CU_CHECK(c, cudaMemsetAsync(c->counters.ptr, 0, c->counters.count * sizeof(int), c->stream));
+        {
+            StageTimer t(c, 0);
+            k_generate<<<c->grid_generate, kBlock, 0, c->stream>>>(p, n_paths);
+            c->kernel_launches++;
+        }
+        for (int it = 0; it < c->n_iters; ++it) {
+            {
+                StageTimer t(c, 1);
+                if (count) k_extend<true><<<c->grid_extend_c, kBlock, 0, c->stream>>>(p, it);
+                else k_extend<false><<<c->grid_extend, kBlock, 0, c->stream>>>(p, it);
+                c->kernel_launches++;
+            }
+            {
+                StageTimer t(c, 2);
+                k_shade<<<c->grid_shade, kBlock, 0, c->stream>>>(p, it);
+                c->kernel_launches++;
+            }
+            if (it < c->n_iters - 1 || c->hs.has_null_material) {  // no NEE at bounce == maxDepth (integrator.cc:340)
+                StageTimer t(c, 3);
+                if (count) k_connect<true><<<c->grid_connect_c, kBlock, 0, c->stream>>>(p, it);
+                else k_connect<false><<<c->grid_connect, kBlock, 0, c->stream>>>(p, it);
+                c->kernel_launches++;
+            }
+        }
+        if (c->hs.has_null_material) {
+            k_count_dropped<<<1, 32, 0, c->stream>>>(p, c->n_iters);
+            c->kernel_launches++;
+        }
+        CU_CHECK(c, cudaGetLastError());
+        done += spp;
+    }
+    return 0;
+}
+
+int jpbrt_finalize_film_device(jpbrt_ctx* c, void* out_device, int spp_total) {
+    if (!c || !out_device || spp_total <= 0) return set_error(c, JPBRT_ERR_INVALID, "bad argument to finalize");
+    CU_CHECK(c, cudaSetDevice(c->device));
+    StageTimer t(c, 4);
+    const float ratio = 1.0f / (float)spp_total;  // integrator.cc:89
+    k_finalize<<<c->grid_finalize, kBlock, 0, c->stream>>>(c->film.ptr, (float*)out_device, c->film.count, ratio);
+    c->kernel_launches++;
+    CU_CHECK(c, cudaGetLastError());
+    return 0;
+}
+
+int jpbrt_read_film(jpbrt_ctx* c, float* rgb, int spp_total, int finalize) {
+    if (!c || !rgb) return set_error(c, JPBRT_ERR_INVALID, "null argument");
+    CU_CHECK(c, cudaSetDevice(c->device));
+    const size_t n = c->film.count;
+    if (finalize) {
+        if (spp_total <= 0) return set_error(c, JPBRT_ERR_INVALID, "spp_total must be positive");
+        DevBuf<float> tmp;
+        CU_CHECK(c, tmp.Alloc(n));
+        int rc = jpbrt_finalize_film_device(c, tmp.ptr, spp_total);
+        if (rc != 0) return rc;
+        CU_CHECK(c, cudaMemcpyAsync(rgb, tmp.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    } else {
+        CU_CHECK(c, cudaMemcpyAsync(rgb, c->film.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    }
+    drain_events(c);
+    return 0;
+}
+
+void* jpbrt_film_device_ptr(jpbrt_ctx* c) { return c ? (void*)c->film.ptr : nullptr; }
+size_t jpbrt_film_num_floats(const jpbrt_ctx* c) { return c ? c->film.count : 0; }
+void* jpbrt_stream(jpbrt_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int jpbrt_synchronize(jpbrt_ctx* c) {
+    if (!c) return set_error(nullptr, JPBRT_ERR_INVALID, "ctx is null");
+    CU_CHECK(c, cudaSetDevice(c->device));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    drain_events(c);
+    return 0;
+}
+
+int jpbrt_get_stats(jpbrt_ctx* c, jpbrt_stats* out) {
+    if (!c || !out) return set_error(c, JPBRT_ERR_INVALID, "null argument");
+    CU_CHECK(c, cudaSetDevice(c->device));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    drain_events(c);
+    unsigned long long h[ST_COUNT];
+    CU_CHECK(c, cudaMemcpy(h, c->dstats.ptr, sizeof(h), cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof(*out));
+    out->samples = h[ST_SAMPLES];
+    out->extension_rays = h[ST_EXT_RAYS];
+    out->shadow_rays = h[ST_SHADOW_RAYS];
+    out->shaded_vertices = h[ST_VERTICES];
+    out->box_tests = h[ST_BOX];
+    out->prim_tests = h[ST_PRIM];
+    out->shadow_box_tests = h[ST_SH_BOX];
+    out->shadow_prim_tests = h[ST_SH_PRIM];
+    out->invalid_contributions = h[ST_INVALID] + h[ST_DROPPED];
+    out->kernel_launches = c->kernel_launches;
+    out->ms_generate = c->ms_stage[0];
+    out->ms_extend = c->ms_stage[1];
+    out->ms_shade = c->ms_stage[2];
+    out->ms_connect = c->ms_stage[3];
+    out->ms_finalize = c->ms_stage[4];
+    out->n_nodes = c->dsc.n_nodes;
+    out->n_prim_slots = c->dsc.n_slots;
+    out->scene_bytes = c->hs.Bytes();
+    out->bvh_build_seconds = c->hs.bvh_build_seconds;
+    return 0;
+}
+
+void jpbrt_destroy(jpbrt_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& ev : c->pending_events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    for (auto& ev : c->free_events) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int jpbrt_render(const jpbrt_scene_desc* desc, int spp, uint64_t seed, int device, float* rgb, double* seconds_out) {
+    if (spp <= 0 || !rgb) return set_error(nullptr, JPBRT_ERR_INVALID, "spp must be positive and rgb non-null");
+    jpbrt_ctx* c = nullptr;
+    int rc = jpbrt_upload_scene(desc, device, &c);
+    if (rc != 0) return rc;
+    auto t0 = std::chrono::steady_clock::now();
+    rc = jpbrt_render_pass(c, 0, spp, seed);
+    if (rc == 0) rc = jpbrt_read_film(c, rgb, spp, 1);
+    auto t1 = std::chrono::steady_clock::now();
+    if (rc != 0) g_last_error = c->error;
+    if (seconds_out) *seconds_out = std::chrono::duration<double>(t1 - t0).count();
+    jpbrt_destroy(c);
+    return rc;
+}
+
+int jpbrt_scene_info(jpbrt_ctx* c, float* out7) {
+    if (!c || !out7) return set_error(c, JPBRT_ERR_INVALID, "null argument");
+    for (int a = 0; a < 3; ++a) { out7[a] = c->hs.world_min[a]; out7[3 + a] = c->hs.world_max[a]; }
+    out7[6] = c->hs.world_radius;
+    return 0;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// Unit kernels: the stage device functions on caller-supplied arrays (parity tests).
+// =================================================================================================
+namespace {
+
+__device__ __forceinline__ f3 ld3(const float* p, int i) { return mk3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); }
+__device__ __forceinline__ void st3(float* p, int i, const f3& v) { p[3 * i] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z; }
+
+__global__ void k_unit_intersect_shape(DevScene sc, int n, const float* rays8, int* hit, float* t, float* pos3, float* nrm3) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float* q = rays8 + 8 * i;
+        const f3 o = mk3(q[0], q[1], q[2]), d = mk3(q[3], q[4], q[5]);
+        float tmax = q[7];
+        bool h = intersect_slot(sc.slots, sc.slot_nrm, o, d, q[6], tmax);
+        hit[i] = h ? 1 : 0;
+        t[i] = h ? tmax : 0.f;
+        f3 P = mk3(0, 0, 0), N = mk3(0, 0, 0);
+        if (h) { P = o + tmax * d; N = hit_normal(sc, 0, P, d); }
+        st3(pos3, i, P);
+        st3(nrm3, i, N);
+    }
+}
+
+__global__ void k_unit_scene_intersect(DevScene sc, int n, const float* rays8, int* prim, float* t, float* pos3, float* nrm3) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float* q = rays8 + 8 * i;
+        const f3 o = mk3(q[0], q[1], q[2]), d = mk3(q[3], q[4], q[5]);
+        float tmax = q[7];
+        unsigned a = 0, b = 0;
+        int slot = traverse<false, false>(sc, o, d, q[6], tmax, a, b);
+        f3 P = mk3(0, 0, 0), N = mk3(0, 0, 0);
+        int pi = -1;
+        if (slot >= 0) {
+            P = o + tmax * d;
+            N = hit_normal(sc, slot, P, d);
+            pi = __float_as_int(ldg4(sc.slot_nrm + slot).w) >> kTypeBits;
+        }
+        prim[i] = pi;
+        t[i] = slot >= 0 ? tmax : 0.f;
+        if (pos3) st3(pos3, i, P);
+        if (nrm3) st3(nrm3, i, N);
+    }
+}
+
+__global__ void k_unit_scene_occluded(DevScene sc, int n, const float* pos3, const float* target3, int* occ) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const f3 P = ld3(pos3, i), T = ld3(target3, i);
+        const f3 v = T - P;  // scene.h:44-47: Normalize(target - pos), Distance(pos, target)
+        const float dist = length(v);
+        const f3 d = v / dist;
+        float tmax = dist - 0.001f;
+        unsigned a = 0, b = 0;
+        int slot = traverse<true, false>(sc, P, d, JPBRT_RAY_TMIN, tmax, a, b);
+        occ[i] = slot >= 0 ? 1 : 0;
+    }
+}
+
+__global__ void k_unit_bsdf(const Float4* mat, int n, const float* nrm3, const float* wo3, const float* wi3, const float* u2,
+                            const float* ulobe, float* f_eval3, float* pdf_eval, float* s_wi3, float* s_f3, float* s_pdf,
+                            int* s_flags, int* is_delta) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Bsdf b = make_bsdf(mat, ulobe ? ulobe[i] : 0.f);
+        const Frame fr = make_frame(ld3(nrm3, i));
+        const f3 wo = to_local(fr, ld3(wo3, i)), wi = to_local(fr, ld3(wi3, i));
+        st3(f_eval3, i, bsdf_eval_local(b, wo, wi));
+        pdf_eval[i] = bsdf_pdf_local(b, wo, wi);
+        BsdfSample s = bsdf_sample_local(b, wo, u2[2 * i], u2[2 * i + 1]);
+        st3(s_wi3, i, to_world(fr, s.wi));
+        st3(s_f3, i, s.f);
+        s_pdf[i] = s.pdf;
+        s_flags[i] = s.flags;
+        is_delta[i] = bsdf_is_delta(b) ? 1 : 0;
+    }
+}
+
+__global__ void k_unit_light_sample(DevScene sc, int light, int n, const float* pos3, const float* nrm3, const float* u2,
+                                    float* lpos3, float* wi3, float* pdf, float* Li3) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        LightSample s = sample_light(sc, light, ld3(pos3, i), ld3(nrm3, i), u2[2 * i], u2[2 * i + 1]);
+        st3(lpos3, i, s.pos);
+        st3(wi3, i, s.wi);
+        pdf[i] = s.pdf;
+        st3(Li3, i, s.Li);
+    }
+}
+
+__global__ void k_unit_emitted(DevScene sc, int n, const int* prim, const float* nrm3, const float* wo3, float* Le3) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        f3 Le = mk3(0, 0, 0);
+        int pi = prim[i];
+        if (pi >= 0 && pi < sc.n_prims) {
+            int slot = sc.prim_slot[pi];
+            Le = emitted(sc, sc.slot_ml[slot].y, ld3(nrm3, i), ld3(wo3, i));
+        }
+        st3(Le3, i, Le);
+    }
+}
+
+__global__ void k_unit_generate_rays(DevScene sc, int n, const float* posfilm2, float* o3, float* d3) {
+    const DevCamera& cam = sc.cam;
+    const f3 pos = mk3(cam.pos[0], cam.pos[1], cam.pos[2]);
+    const f3 front = mk3(cam.front[0], cam.front[1], cam.front[2]);
+    const f3 right = mk3(cam.right[0], cam.right[1], cam.right[2]);
+    const f3 up = mk3(cam.up[0], cam.up[1], cam.up[2]);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float fx = posfilm2[2 * i], fy = posfilm2[2 * i + 1];
+        const f3 dir = front + right * (fx / cam.res_x - 0.5f) + up * (0.5f - fy / cam.res_y);
+        st3(o3, i, pos);
+        st3(d3, i, normalize(dir));
+    }
+}
+
+__global__ void k_unit_rng_block(int n, const uint32_t* pixel, const uint32_t* sample, const uint32_t* block, RngKey key, float* out4) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 r = rng_block(key, pixel[i], sample[i], block[i]);
+        out4[4 * i] = r.x; out4[4 * i + 1] = r.y; out4[4 * i + 2] = r.z; out4[4 * i + 3] = r.w;
+    }
+}
+
+// host <-> device marshalling for the unit entry points
+struct Arena {
+    std::vector<void*> ptrs;
+    cudaError_t err = cudaSuccess;
+    template <typename T>
+    T* In(const T* host, size_t n) {
+        if (!host || n == 0) return nullptr;
+        T* d = Out<T>(n);
+        if (d && err == cudaSuccess) err = cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice);
+        return d;
+    }
+    template <typename T>
+    T* Out(size_t n) {
+        T* d = nullptr;
+        if (err != cudaSuccess) return nullptr;
+        err = cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T));
+        if (err == cudaSuccess) ptrs.push_back(d); else d = nullptr;
+        return d;
+    }
+    template <typename T>
+    void Back(T* host, const T* dev, size_t n) {
+        if (host && dev && err == cudaSuccess) err = cudaMemcpy(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost);
+    }
+    ~Arena() { for (void* p : ptrs) cudaFree(p); }
+};
+
+int unit_grid(int n) { return std::max(1, std::min((n + kBlock - 1) / kBlock, 148 * 8)); }
+
+int finish_unit(jpbrt_ctx* c, Arena& a) {
+    if (a.err == cudaSuccess) a.err = cudaGetLastError();
+    if (a.err == cudaSuccess) a.err = cudaDeviceSynchronize();
+    if (a.err != cudaSuccess) return set_error(c, JPBRT_ERR_CUDA, "unit kernel failed: %s", cudaGetErrorString(a.err));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jpbrt_unit_intersect_shape(const jpbrt_shape* shape, int device, int n, const float* rays8, int* hit, float* t, float* pos3, float* nrm3) {
+    if (!shape || n < 0 || !rays8 || !hit || !t || !pos3 || !nrm3) return set_error(nullptr, JPBRT_ERR_INVALID, "null argument");
+    Float4 q[4], nr;
+    float bmn[3], bmx[3];
+    if (!MakeSlot(*shape, 0, q, &nr, bmn, bmx)) return set_error(nullptr, JPBRT_ERR_INVALID, "unknown shape type");
+    int rc = select_device(nullptr, device);
+    if (rc != 0) return rc;
+    Arena a;
+    DevScene sc{};
+    sc.slots = a.In(q, 4);
+    sc.slot_nrm = a.In(&nr, 1);
+    sc.n_slots = 1;
+    const float* d_rays = a.In(rays8, (size_t)n * 8);
+    int* d_hit = a.Out<int>(n);
+    float* d_t = a.Out<float>(n);
+    float* d_pos = a.Out<float>((size_t)n * 3);
+    float* d_nrm = a.Out<float>((size_t)n * 3);
+    if (a.err == cudaSuccess && n > 0) k_unit_intersect_shape<<<unit_grid(n), kBlock>>>(sc, n, d_rays, d_hit, d_t, d_pos, d_nrm);
+    rc = finish_unit(nullptr, a);
+    if (rc != 0) return rc;
+    a.Back(hit, d_hit, n); a.Back(t, d_t, n); a.Back(pos3, d_pos, (size_t)n * 3); a.Back(nrm3, d_nrm, (size_t)n * 3);
+    return a.err == cudaSuccess ? 0 : set_error(nullptr, JPBRT_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(a.err));
+}
+
+int jpbrt_unit_scene_intersect(jpbrt_ctx* c, int n, const float* rays8, int* prim, float* t, float* pos3, float* nrm3) {
+    if (!c || n < 0 || !rays8 || !prim || !t) return set_error(c, JPBRT_ERR_INVALID, "null argument");
+    CU_CHECK(c, cudaSetDevice(c->device));
+    Arena a;
+    const float* d_rays = a.In(rays8, (size_t)n * 8);
+    int* d_prim = a.Out<int>(n);
+    float* d_t = a.Out<float>(n);
+    float* d_pos = pos3 ? a.Out<float>((size_t)n * 3) : nullptr;
+    float* d_nrm = nrm3 ? a.Out<float>((size_t)n * 3) : nullptr;
+    if (a.err == cudaSuccess && n > 0) k_unit_scene_intersect<<<unit_grid(n), kBlock>>>(c->dsc, n, d_rays, d_prim, d_t, d_pos, d_nrm);
+    int rc = finish_unit(c, a);
+    if (rc != 0) return rc;
+    a.Back(prim, d_prim, n); a.Back(t, d_t, n); a.Back(pos3, d_pos, (size_t)n * 3); a.Back(nrm3, d_nrm, (size_t)n * 3);
+    return a.err == cudaSuccess ? 0 : set_error(c, JPBRT_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(a.err));
+}
+
+int jpbrt_unit_scene_occluded(jpbrt_ctx* c, int n, const float* pos3, const float* target3, int* occluded) {
+    if (!c || n < 0 || !pos3 || !target3 || !occluded) return set_error(c, JPBRT_ERR_INVALID, "null argument");
+    CU_CHECK(c, cudaSetDevice(c->device));
+    Arena a;
+    const float* d_pos = a.In(pos3, (size_t)n * 3);
+    const float* d_tgt = a.In(target3, (size_t)n * 3);
+    int* d_occ = a.Out<int>(n);
+    if (a.err == cudaSuccess && n > 0) k_unit_scene_occluded<<<unit_grid(n), kBlock>>>(c->dsc, n, d_pos, d_tgt, d_occ);
+    int rc = finish_unit(c, a);
+    if (rc != 0) return rc;
+    a.Back(occluded, d_occ, n);
+    return a.err == cudaSuccess ? 0 : set_error(c, JPBRT_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(a.err));
+}
+
+int jpbrt_unit_bsdf(const jpbrt_material* mat, int device, int n, const float* nrm3, const float* wo3, const float* wi3,
+                    const float* u2, const float* ulobe, float* f_eval3, float* pdf_eval, float* s_wi3, float* s_f3,
+                    float* s_pdf, int* s_flags, int* is_delta) {
+    if (!mat || n < 0 || !nrm3 || !wo3 || !wi3 || !u2) return set_error(nullptr, JPBRT_ERR_INVALID, "null argument");
+    Float4 m[3];
+    if (!MakeMaterial(*mat, m)) return set_error(nullptr, JPBRT_ERR_INVALID, "unknown material type");
+    int rc = select_device(nullptr, device);
+    if (rc != 0) return rc;
+    Arena a;
+    const Float4* d_m = a.In(m, 3);
+    const float *d_n = a.In(nrm3, (size_t)n * 3), *d_wo = a.In(wo3, (size_t)n * 3), *d_wi = a.In(wi3, (size_t)n * 3);
+    const float *d_u = a.In(u2, (size_t)n * 2), *d_ul = a.In(ulobe, (size_t)n);
+    float *d_fe = a.Out<float>((size_t)n * 3), *d_pe = a.Out<float>(n), *d_swi = a.Out<float>((size_t)n * 3);
+    float *d_sf = a.Out<float>((size_t)n * 3), *d_sp = a.Out<float>(n);
+    int *d_fl = a.Out<int>(n), *d_dl = a.Out<int>(n);
+    if (a.err == cudaSuccess && n > 0)
+        k_unit_bsdf<<<unit_grid(n), kBlock>>>(d_m, n, d_n, d_wo, d_wi, d_u, d_ul, d_fe, d_pe, d_swi, d_sf, d_sp, d_fl, d_dl);
+    rc = finish_unit(nullptr, a);
+    if (rc != 0) return rc;
+    a.Back(f_eval3, d_fe, (size_t)n * 3); a.Back(pdf_eval, d_pe, n); a.Back(s_wi3, d_swi, (size_t)n * 3);
+    a.Back(s_f3, d_sf, (size_t)n * 3); a.Back(s_pdf, d_sp, n); a.Back(s_flags, d_fl, n); a.Back(is_delta, d_dl, n);
+    return a.err == cudaSuccess ? 0 : set_error(nullptr, JPBRT_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(a.err));
+}
+
+int jpbrt_unit_light_sample(jpbrt_ctx* c, int light, int n, const float* pos3, const float* nrm3, const float* u2,
+                            float* lpos3, float* wi3, float* pdf, float* Li3) {
+    if (!c || n < 0 || !pos3 || !nrm3 || !u2) return set_error(c, JPBRT_ERR_INVALID, "null argument");
+    if (light < 0 || light >= c->dsc.n_lights) return set_error(c, JPBRT_ERR_INVALID, "light index out of range");
+    CU_CHECK(c, cudaSetDevice(c->device));
+    Arena a;
+    const float *d_p = a.In(pos3, (size_t)n * 3), *d_n = a.In(nrm3, (size_t)n * 3), *d_u = a.In(u2, (size_t)n * 2);
+    float *d_lp = a.Out<float>((size_t)n * 3), *d_wi = a.Out<float>((size_t)n * 3), *d_pdf = a.Out<float>(n), *d_li = a.Out<float>((size_t)n * 3);
+    if (a.err == cudaSuccess && n > 0) k_unit_light_sample<<<unit_grid(n), kBlock>>>(c->dsc, light, n, d_p, d_n, d_u, d_lp, d_wi, d_pdf, d_li);
+    int rc = finish_unit(c, a);
+    if (rc != 0) return rc;
+    a.Back(lpos3, d_lp, (size_t)n * 3); a.Back(wi3, d_wi, (size_t)n * 3); a.Back(pdf, d_pdf, n); a.Back(Li3, d_li, (size_t)n * 3);
+    return a.err == cudaSuccess ? 0 : set_error(c, JPBRT_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(a.err));
+}
+
+int jpbrt_unit_emitted(jpbrt_ctx* c, int n, const int* prim, const float* nrm3, const float* wo3, float* Le3) {
+    if (!c || n < 0 || !prim || !nrm3 || !wo3 || !Le3) return set_error(c, JPBRT_ERR_INVALID, "null argument");
+    CU_CHECK(c, cudaSetDevice(c->device));
+    Arena a;
+    const int* d_prim = a.In(prim, n);
+    const float *d_n = a.In(nrm3, (size_t)n * 3), *d_wo = a.In(wo3, (size_t)n * 3);
+    float* d_le = a.Out<float>((size_t)n * 3);
+    if (a.err == cudaSuccess && n > 0) k_unit_emitted<<<unit_grid(n), kBlock>>>(c->dsc, n, d_prim, d_n, d_wo, d_le);
+    int rc = finish_unit(c, a);
+    if (rc != 0) return rc;
+    a.Back(Le3, d_le, (size_t)n * 3);
+    return a.err == cudaSuccess ? 0 : set_error(c, JPBRT_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(a.err));
+}
+
+int jpbrt_unit_generate_rays(jpbrt_ctx* c, int n, const float* posfilm2, float* o3, float* d3) {
+    if (!c || n < 0 || !posfilm2 || !o3 || !d3) return set_error(c, JPBRT_ERR_INVALID, "null argument");
+    CU_CHECK(c, cudaSetDevice(c->device));
+    Arena a;
+    const float* d_pf = a.In(posfilm2, (size_t)n * 2);
+    float *d_o = a.Out<float>((size_t)n * 3), *d_d = a.Out<float>((size_t)n * 3);
+    if (a.err == cudaSuccess && n > 0) k_unit_generate_rays<<<unit_grid(n), kBlock>>>(c->dsc, n, d_pf, d_o, d_d);
+    int rc = finish_unit(c, a);
+    if (rc != 0) return rc;
+    a.Back(o3, d_o, (size_t)n * 3); a.Back(d3, d_d, (size_t)n * 3);
+    return a.err == cudaSuccess ? 0 : set_error(c, JPBRT_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(a.err));
+}
+
+int jpbrt_unit_rng_block(int device, int n, const uint32_t* pixel, const uint32_t* sample, const uint32_t* block, uint64_t seed, float* out4) {
+    if (n < 0 || !pixel || !sample || !block || !out4) return set_error(nullptr, JPBRT_ERR_INVALID, "null argument");
+    int rc = select_device(nullptr, device);
+    if (rc != 0) return rc;
+    Arena a;
+    const uint32_t *d_p = a.In(pixel, n), *d_s = a.In(sample, n), *d_b = a.In(block, n);
+    float* d_o = a.Out<float>((size_t)n * 4);
+    RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    if (a.err == cudaSuccess && n > 0) k_unit_rng_block<<<unit_grid(n), kBlock>>>(n, d_p, d_s, d_b, key, d_o);
+    rc = finish_unit(nullptr, a);
+    if (rc != 0) return rc;
+    a.Back(out4, d_o, (size_t)n * 4);
+    return a.err == cudaSuccess ? 0 : set_error(nullptr, JPBRT_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(a.err));
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// dev_scene.h -- the flattened scene layout shared by the host uploader and the CUDA kernels.
+//
+// Everything the wavefront kernels read is a 16-byte-aligned array of float4 (SoA by role), so
+// every fetch is one LDG.128 (DESIGN.md "Data layout in HBM"):
+//
+//   nodes     4 x float4 / node  (64 B)  two child boxes + two child references
+//   slots     4 x float4 / slot  (64 B)  primitive geometry in BVH leaf order
+//   slot_nrm  1 x float4 / slot          stored normal + tag, read on accepted hits and by shade
+//   slot_ml   1 x int2   / slot          (material, light) of the primitive
+//   materials 3 x float4 / material
+//   lights    6 x float4 / light
+#pragma once
+
+#include <stdint.h>
+
+namespace jpbrt {
+
+// ---- node: n0 = (Lmin.x Lmin.y Lmin.z Lmax.x) n1 = (Lmax.y Lmax.z Rmin.x Rmin.y)
+//            n2 = (Rmin.z Rmax.x Rmax.y Rmax.z) n3 = (int left, int right, -, -)
+// child reference >= 0: inner node index;  < 0: leaf, ~ref = (first_slot << 4) | count
+constexpr int kNodeStride = 4;
+constexpr int kLeafCountBits = 4;
+constexpr int kMaxLeafPrims = 4;
+
+// ---- slot: q0.w carries the tag = type | (primitive_index << 2)
+//   triangle : q0 = p0, q1 = p1, q2 = p2
+//   rectangle: q0 = p0, q1 = p1, q2 = p2, q3 = p3
+//   sphere   : q0 = centre, q1.x = radius
+//   disk     : q0 = position, q1 = normal(xyz) radius(w)
+constexpr int kSlotStride = 4;
+constexpr int kTypeBits = 2;
+
+// ---- material: m0 = (a.rgb, type)  m1 = (b.rgb, f0)  m2 = (f1, Qd, -, -)
+//   matte   a = albedo                      mirror  a = reflectance
+//   glass   a = Kr, b = Kt, f0 = eta
+//   plastic a = Kd/Qd, b = Ks/(1-Qd), f0 = alpha (clamped, remapped), m2.y = Qd
+//   metal   a = eta, b = k, f0 = alpha_x, m2.x = alpha_y
+constexpr int kMaterialStride = 3;
+
+// ---- light: l0 = (color.rgb, type | shape_type << 8)  l1 = (p0 | centre | position | dir, 1/area)
+//             l2 = (p1, radius)  l3 = (p2, -)  l4 = (stored normal, -)  l5 = spare
+constexpr int kLightStride = 6;
+
+struct DevCamera {
+    float pos[3];
+    float front[3];
+    float right[3];
+    float up[3];
+    float res_x, res_y;
+};
+
+struct Float4 { float x, y, z, w; };
+struct Int2 { int x, y; };
+
+// Passed to kernels by value (pointers are device pointers).
+struct DevScene {
+    const Float4* nodes;
+    const Float4* slots;
+    const Float4* slot_nrm;
+    const Int2*   slot_ml;
+    const Float4* materials;
+    const Float4* lights;
+    const int*    inf_lights;
+    const int*    prim_slot;  // primitive index -> slot
+    int n_nodes, n_slots, n_materials, n_lights, n_inf_lights, n_prims;
+    int max_depth;
+    int width, height;
+    float world_radius;  // FEnvironmentLight::worldRadius (light.cc:26-33)
+    DevCamera cam;
+};
+
+}  // namespace jpbrt

@@ -1,0 +1,488 @@
+// scene_flatten.cc -- see scene_flatten.h.  Host only (compiled by g++, -O2, no FMA contraction).
+#include "scene_flatten.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <future>
+#include <limits>
+#include <thread>
+
+#include "../../include/jetpbrt_b200.h"
+
+namespace jpbrt {
+
+namespace {
+
+// Minimal float3 with the reference's evaluation order (geometry.h:65-159).
+struct H3 {
+    float x, y, z;
+    H3() : x(0), y(0), z(0) {}
+    H3(float a, float b, float c) : x(a), y(b), z(c) {}
+    explicit H3(const float* p) : x(p[0]), y(p[1]), z(p[2]) {}
+    H3 operator+(const H3& v) const { return H3(x + v.x, y + v.y, z + v.z); }
+    H3 operator-(const H3& v) const { return H3(x - v.x, y - v.y, z - v.z); }
+    H3 operator-() const { return H3(-x, -y, -z); }
+    H3 operator*(float s) const { return H3(x * s, y * s, z * s); }
+    H3 operator/(float s) const { return H3(x / s, y / s, z / s); }
+    float Length() const { return std::sqrt(x * x + y * y + z * z); }
+    H3 Normalize() const { return *this / Length(); }
+    H3 Cross(const H3& v) const { return H3(y * v.z - z * v.y, z * v.x - x * v.z, x * v.y - y * v.x); }
+};
+
+constexpr float kPi = (float)3.14159265358979323846;
+
+struct Box {
+    float mn[3], mx[3];
+    Box() {
+        for (int a = 0; a < 3; ++a) { mn[a] = std::numeric_limits<float>::max(); mx[a] = std::numeric_limits<float>::lowest(); }
+    }
+    void Add(const H3& p) {
+        mn[0] = std::min(mn[0], p.x); mn[1] = std::min(mn[1], p.y); mn[2] = std::min(mn[2], p.z);
+        mx[0] = std::max(mx[0], p.x); mx[1] = std::max(mx[1], p.y); mx[2] = std::max(mx[2], p.z);
+    }
+    void Add(const Box& b) {
+        for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], b.mn[a]); mx[a] = std::max(mx[a], b.mx[a]); }
+    }
+    void CheckThinness(float th = JPBRT_THINNESS) {  // geometry.h:299-304
+        for (int a = 0; a < 3; ++a)
+            if (mn[a] == mx[a]) { mn[a] -= th; mx[a] += th; }
+    }
+    float HalfArea() const {
+        float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+
+// FFrame(n) tangent vectors (geometry.h:344-377), needed for the disk's bounds (shape.h:239-252).
+void FrameST(const H3& nn, H3* s, H3* t) {
+    H3 n = nn.Normalize();
+    H3 tmp = (std::fabs(n.x) > 0.99f) ? H3(0, 1, 0) : H3(1, 0, 0);
+    *t = n.Cross(tmp).Normalize();
+    *s = t->Cross(n).Normalize();
+}
+
+inline float IntAsFloat(int v) { float f; memcpy(&f, &v, 4); return f; }
+
+}  // namespace
+
+bool MakeSlot(const jpbrt_shape& sh, int prim_index, Float4 q[4], Float4* nrm, float bmin[3], float bmax[3]) {
+    const int tag = (sh.type & ((1 << kTypeBits) - 1)) | (prim_index << kTypeBits);
+    const float tagf = IntAsFloat(tag);
+    for (int i = 0; i < 4; ++i) q[i] = Float4{0, 0, 0, 0};
+    H3 p0(sh.p[0]), p1(sh.p[1]), p2(sh.p[2]), p3(sh.p[3]);
+    Box b;
+    H3 n;
+    switch (sh.type) {
+    case JPBRT_SHAPE_TRIANGLE:  // shape.h:280-289, 339-349
+        n = (p1 - p0).Cross(p2 - p0).Normalize();
+        if (sh.flip_normal) n = -n;
+        b.Add(p0); b.Add(p1); b.Add(p2);
+        b.CheckThinness();
+        q[0] = Float4{p0.x, p0.y, p0.z, tagf};
+        q[1] = Float4{p1.x, p1.y, p1.z, 0};
+        q[2] = Float4{p2.x, p2.y, p2.z, 0};
+        break;
+    case JPBRT_SHAPE_RECTANGLE:  // shape.h:383-393, 449-455
+        n = (p1 - p0).Cross(p2 - p0).Normalize();
+        if (sh.flip_normal) n = -n;
+        b.Add(p0); b.Add(p1); b.Add(p2); b.Add(p3);
+        b.CheckThinness();
+        q[0] = Float4{p0.x, p0.y, p0.z, tagf};
+        q[1] = Float4{p1.x, p1.y, p1.z, 0};
+        q[2] = Float4{p2.x, p2.y, p2.z, 0};
+        q[3] = Float4{p3.x, p3.y, p3.z, 0};
+        break;
+    case JPBRT_SHAPE_SPHERE: {  // shape.h:479-485, 541-545
+        float r = sh.p[1][0];
+        H3 half(r, r, r);
+        b.Add(p0 + half); b.Add(p0 - half);
+        q[0] = Float4{p0.x, p0.y, p0.z, tagf};
+        q[1] = Float4{r, 0, 0, 0};
+        n = H3(0, 0, 0);
+        break;
+    }
+    case JPBRT_SHAPE_DISK: {  // shape.h:192-197, 239-252
+        n = p1.Normalize();
+        float r = sh.p[2][0];
+        H3 s, t;
+        FrameST(n, &s, &t);
+        H3 rb = s * r, rt = t * r;
+        b.Add(p0 + rb + rt); b.Add(p0 + rb - rt); b.Add(p0 - rb - rt); b.Add(p0 - rb + rt);
+        b.CheckThinness();
+        q[0] = Float4{p0.x, p0.y, p0.z, tagf};
+        q[1] = Float4{n.x, n.y, n.z, r};
+        break;
+    }
+    default:
+        return false;
+    }
+    *nrm = Float4{n.x, n.y, n.z, tagf};
+    for (int a = 0; a < 3; ++a) { bmin[a] = b.mn[a]; bmax[a] = b.mx[a]; }
+    return true;
+}
+
+static float Luminance(const float* c) { return 0.212671f * c[0] + 0.715160f * c[1] + 0.072169f * c[2]; }  // color.h:47-50
+
+static float RoughnessToAlpha(float roughness) {  // microfacet.h:87-92
+    roughness = std::max(roughness, (float)1e-3);
+    float x = std::log(roughness);
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+
+bool MakeMaterial(const jpbrt_material& m, Float4 out[3]) {
+    out[0] = Float4{m.a[0], m.a[1], m.a[2], IntAsFloat(m.type)};
+    out[1] = Float4{m.b[0], m.b[1], m.b[2], m.f0};
+    out[2] = Float4{m.f1, 0, 0, 0};
+    switch (m.type) {
+    case JPBRT_MAT_MATTE:
+    case JPBRT_MAT_MIRROR:
+    case JPBRT_MAT_GLASS:
+        return true;
+    case JPBRT_MAT_PLASTIC: {  // material.h:94-98, material.cc:12-29
+        float Ld = Luminance(m.a), Ls = Luminance(m.b);
+        float L = Ld + Ls;
+        float Qd = Ld / L;
+        float rough = m.f0;
+        if (m.remap_roughness) rough = RoughnessToAlpha(rough);
+        float alpha = std::max(float(0.001), rough);  // microfacet.h:73-74
+        float om = 1 - Qd;
+        out[0] = Float4{m.a[0] / Qd, m.a[1] / Qd, m.a[2] / Qd, IntAsFloat(m.type)};
+        out[1] = Float4{m.b[0] / om, m.b[1] / om, m.b[2] / om, alpha};
+        out[2] = Float4{alpha, Qd, 0, 0};
+        return true;
+    }
+    case JPBRT_MAT_METAL: {  // material.cc:31-43
+        float ur = m.f0, vr = m.f1;
+        if (m.remap_roughness) { ur = RoughnessToAlpha(ur); vr = RoughnessToAlpha(vr); }
+        out[1].w = std::max(float(0.001), ur);
+        out[2].x = std::max(float(0.001), vr);
+        return true;
+    }
+    }
+    return false;
+}
+
+// =================================================================================================
+// BVH: binned-SAH top-down build on the host, flattened depth-first with the children's boxes
+// stored in the parent.  Topology is deliberately NOT the reference's (bvh.h:59-92: random axis,
+// median split, no ordering): hits are defined by the primitive tests, the tree only prunes.
+// =================================================================================================
+namespace {
+
+struct TmpNode {
+    Box box;
+    int left = -1, right = -1;  // inner
+    int first = 0, count = 0;   // leaf when count > 0
+};
+
+struct Builder {
+    const std::vector<Box>& pb;
+    std::vector<float> cx, cy, cz;
+    std::vector<int> idx;
+    std::vector<TmpNode> nodes;
+    std::atomic<int> next{0};
+    std::atomic<int> threads_left;
+
+    explicit Builder(const std::vector<Box>& prim_boxes, int nthreads) : pb(prim_boxes), threads_left(nthreads) {
+        size_t n = pb.size();
+        cx.resize(n); cy.resize(n); cz.resize(n); idx.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            cx[i] = 0.5f * (pb[i].mn[0] + pb[i].mx[0]);
+            cy[i] = 0.5f * (pb[i].mn[1] + pb[i].mx[1]);
+            cz[i] = 0.5f * (pb[i].mn[2] + pb[i].mx[2]);
+            idx[i] = (int)i;
+        }
+        nodes.resize(std::max<size_t>(2 * n, 2));
+    }
+    float C(int axis, int i) const { return axis == 0 ? cx[i] : (axis == 1 ? cy[i] : cz[i]); }
+    int Alloc() { return next.fetch_add(1); }
+
+    void Build(int node, int first, int last) {
+        TmpNode& N = nodes[node];
+        Box box, cbox;
+        for (int i = first; i < last; ++i) {
+            int p = idx[i];
+            box.Add(pb[p]);
+            cbox.Add(H3(cx[p], cy[p], cz[p]));
+        }
+        N.box = box;
+        int count = last - first;
+        if (count <= kMaxLeafPrims) {
+            // a small set becomes a leaf unless SAH says that splitting it is clearly cheaper
+            bool leaf = true;
+            if (count > 1) {
+                float best = BestSplitCost(first, last, box, cbox, nullptr, nullptr);
+                leaf = !(best + 1.0f < (float)count);
+            }
+            if (leaf) { N.first = first; N.count = count; return; }
+        }
+        int axis = -1, mid = -1;
+        BestSplitCost(first, last, box, cbox, &axis, &mid);
+        if (mid <= first || mid >= last) {  // degenerate (coincident centroids): median by index
+            int a = 0;
+            float ext = -1;
+            for (int k = 0; k < 3; ++k) { float e = cbox.mx[k] - cbox.mn[k]; if (e > ext) { ext = e; a = k; } }
+            mid = first + count / 2;
+            std::nth_element(idx.begin() + first, idx.begin() + mid, idx.begin() + last,
+                             [&](int l, int r) { return C(a, l) < C(a, r); });
+        }
+        int l = Alloc(), r = Alloc();
+        N.left = l;
+        N.right = r;
+        N.count = 0;
+        if (count > 1 << 15 && threads_left.fetch_sub(1) > 0) {
+            auto fut = std::async(std::launch::async, [this, l, first, mid]() { Build(l, first, mid); });
+            Build(r, mid, last);
+            fut.get();
+            threads_left.fetch_add(1);
+        } else {
+            if (count > 1 << 15) threads_left.fetch_add(1);
+            Build(l, first, mid);
+            Build(r, mid, last);
+        }
+    }
+
+    // Binned SAH over the three axes.  Returns the best cost (in primitive-test units, traversal
+    // step = 1); if axis/mid are given, partitions idx[first,last) and reports the split.
+    float BestSplitCost(int first, int last, const Box& box, const Box& cbox, int* out_axis, int* out_mid) {
+        constexpr int NB = 16;
+        int count = last - first;
+        float best = std::numeric_limits<float>::infinity();
+        int best_axis = -1, best_bin = -1;
+        float parent_area = std::max(box.HalfArea(), 1e-30f);
+        for (int a = 0; a < 3; ++a) {
+            float lo = cbox.mn[a], ext = cbox.mx[a] - cbox.mn[a];
+            if (!(ext > 0)) continue;
+            float scale = (float)NB / ext;
+            Box bb[NB];
+            int bc[NB] = {0};
+            for (int i = first; i < last; ++i) {
+                int p = idx[i];
+                int b = std::min(NB - 1, std::max(0, (int)((C(a, p) - lo) * scale)));
+                bb[b].Add(pb[p]);
+                bc[b]++;
+            }
+            float right_area[NB];
+            int right_cnt[NB];
+            Box acc;
+            int c = 0;
+            for (int b = NB - 1; b > 0; --b) {
+                acc.Add(bb[b]);
+                c += bc[b];
+                right_area[b] = c ? acc.HalfArea() : 0.f;
+                right_cnt[b] = c;
+            }
+            Box accl;
+            int cl = 0;
+            for (int b = 0; b < NB - 1; ++b) {
+                accl.Add(bb[b]);
+                cl += bc[b];
+                if (cl == 0 || right_cnt[b + 1] == 0) continue;
+                float cost = 1.0f + (accl.HalfArea() * cl + right_area[b + 1] * right_cnt[b + 1]) / parent_area;
+                if (cost < best) { best = cost; best_axis = a; best_bin = b; }
+            }
+        }
+        if (out_axis && best_axis >= 0) {
+            int a = best_axis;
+            float lo = cbox.mn[a], ext = cbox.mx[a] - cbox.mn[a];
+            float scale = (float)NB / ext;
+            auto it = std::partition(idx.begin() + first, idx.begin() + last, [&](int p) {
+                int b = std::min(NB - 1, std::max(0, (int)((C(a, p) - lo) * scale)));
+                return b <= best_bin;
+            });
+            *out_axis = a;
+            *out_mid = (int)(it - idx.begin());
+        } else if (out_axis) {
+            *out_axis = -1;
+            *out_mid = -1;
+        }
+        (void)count;
+        return best;
+    }
+};
+
+int LeafRef(int first, int count) { return ~((first << kLeafCountBits) | count); }
+
+}  // namespace
+
+int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err) {
+    auto fail = [&](int code, const char* msg) { if (err) *err = msg; return code; };
+    if (!d || !out) return fail(JPBRT_ERR_INVALID, "null scene description");
+    if (d->n_primitives <= 0 || !d->primitives || !d->shapes) return fail(JPBRT_ERR_INVALID, "scene has no primitives");
+    if (d->camera.width <= 0 || d->camera.height <= 0) return fail(JPBRT_ERR_INVALID, "film resolution must be positive");
+    if (d->max_depth < 0 || d->max_depth > 126) return fail(JPBRT_ERR_INVALID, "max_depth out of range [0,126]");
+    if ((long long)d->n_primitives >= (1ll << (31 - kLeafCountBits))) return fail(JPBRT_ERR_UNSUPPORTED, "too many primitives");
+
+    HostScene& hs = *out;
+    hs = HostScene();
+    hs.max_depth = d->max_depth;
+    hs.width = d->camera.width;
+    hs.height = d->camera.height;
+    hs.n_prims = d->n_primitives;
+
+    {  // FCamera ctor, camera.h:36-49
+        const jpbrt_camera& c = d->camera;
+        H3 pos(c.pos), front = H3(c.front).Normalize(), up = H3(c.up).Normalize();
+        float res_x = (float)c.width, res_y = (float)c.height;
+        float tan_fov = std::tan(((c.vfov_deg * kPi) / (float)180) / 2);
+        float aspect = res_x / res_y;
+        H3 right = up.Cross(front).Normalize() * (tan_fov * aspect);
+        H3 up2 = front.Cross(right).Normalize() * tan_fov;
+        float* dst[4] = {hs.cam.pos, hs.cam.front, hs.cam.right, hs.cam.up};
+        H3 src[4] = {pos, front, right, up2};
+        for (int i = 0; i < 4; ++i) { dst[i][0] = src[i].x; dst[i][1] = src[i].y; dst[i][2] = src[i].z; }
+        hs.cam.res_x = res_x;
+        hs.cam.res_y = res_y;
+    }
+
+    // materials
+    hs.materials.resize((size_t)d->n_materials * kMaterialStride);
+    for (int i = 0; i < d->n_materials; ++i)
+        if (!MakeMaterial(d->materials[i], &hs.materials[(size_t)i * kMaterialStride])) return fail(JPBRT_ERR_INVALID, "unknown material type");
+
+    // primitives -> slots (pre-BVH order), bounds
+    const int N = d->n_primitives;
+    std::vector<Float4> pre_slots((size_t)N * kSlotStride), pre_nrm(N);
+    std::vector<Box> boxes(N);
+    Box world;
+    for (int i = 0; i < N; ++i) {
+        const jpbrt_primitive& p = d->primitives[i];
+        if (p.shape < 0 || p.shape >= d->n_shapes) return fail(JPBRT_ERR_INVALID, "primitive references a missing shape");
+        if (p.material >= d->n_materials) return fail(JPBRT_ERR_INVALID, "primitive references a missing material");
+        if (p.light >= d->n_lights) return fail(JPBRT_ERR_INVALID, "primitive references a missing light");
+        if (p.material < 0) hs.has_null_material = true;
+        if (!MakeSlot(d->shapes[p.shape], i, &pre_slots[(size_t)i * kSlotStride], &pre_nrm[i], boxes[i].mn, boxes[i].mx))
+            return fail(JPBRT_ERR_INVALID, "unknown shape type");
+        world.Add(boxes[i]);  // FScene::CalculateWorldBound, scene.cc:35-45
+    }
+    for (int a = 0; a < 3; ++a) { hs.world_min[a] = world.mn[a]; hs.world_max[a] = world.mx[a]; }
+    {  // FBounds3::BoundingSphere (geometry.h:307-311) as used by FEnvironmentLight::Preprocess (light.cc:26-33)
+        H3 mn(world.mn), mx(world.mx);
+        H3 c = mn + (mx - mn) * 0.5f;  // Lerp(u, v, t) = u + t * (v - u), geometry.h:137
+        bool inside = c.x >= mn.x && c.x <= mx.x && c.y >= mn.y && c.y <= mx.y && c.z >= mn.z && c.z <= mx.z;
+        hs.world_radius = inside ? (c - mx).Length() : 0.f;
+    }
+
+    // lights
+    hs.lights.assign((size_t)d->n_lights * kLightStride, Float4{0, 0, 0, 0});
+    for (int i = 0; i < d->n_lights; ++i) {
+        const jpbrt_light& l = d->lights[i];
+        Float4* o = &hs.lights[(size_t)i * kLightStride];
+        int shape_type = 0;
+        switch (l.type) {
+        case JPBRT_LIGHT_ENVIRONMENT:
+            hs.inf_lights.push_back(i);  // scene.h:101-104
+            break;
+        case JPBRT_LIGHT_AREA: {
+            if (l.shape < 0 || l.shape >= d->n_shapes) return fail(JPBRT_ERR_INVALID, "area light references a missing shape");
+            const jpbrt_shape& sh = d->shapes[l.shape];
+            shape_type = sh.type;
+            Float4 q[4], nrm;
+            float bmn[3], bmx[3];
+            if (!MakeSlot(sh, 0, q, &nrm, bmn, bmx)) return fail(JPBRT_ERR_INVALID, "unknown shape type");
+            H3 p0(sh.p[0]), p1(sh.p[1]), p2(sh.p[2]);
+            float area = 0, radius = 0;
+            switch (sh.type) {
+            case JPBRT_SHAPE_TRIANGLE: area = 0.5f * (p1 - p0).Cross(p2 - p0).Length(); break;                  // shape.h:351
+            case JPBRT_SHAPE_RECTANGLE: area = (p0 - p1).Cross(p2 - p1).Length(); break;                       // shape.h:457
+            case JPBRT_SHAPE_SPHERE: radius = sh.p[1][0]; area = 4 * kPi * (radius * radius); break;           // shape.h:547
+            case JPBRT_SHAPE_DISK: radius = sh.p[2][0]; area = kPi * radius * radius; break;                   // shape.h:254
+            }
+            o[1] = Float4{p0.x, p0.y, p0.z, 1 / area};
+            o[2] = Float4{p1.x, p1.y, p1.z, radius};
+            o[3] = Float4{p2.x, p2.y, p2.z, 0};
+            o[4] = Float4{nrm.x, nrm.y, nrm.z, 0};
+            break;
+        }
+        case JPBRT_LIGHT_POINT:
+            o[1] = Float4{l.pos[0], l.pos[1], l.pos[2], 0};
+            break;
+        case JPBRT_LIGHT_DIRECTION: {
+            H3 dn = H3(l.dir).Normalize();  // worldDir(Normalize(worlddir)), light.h:142
+            o[1] = Float4{dn.x, dn.y, dn.z, 0};
+            break;
+        }
+        default:
+            return fail(JPBRT_ERR_INVALID, "unknown light type");
+        }
+        o[0] = Float4{l.color[0], l.color[1], l.color[2], IntAsFloat(l.type | (shape_type << 8))};
+    }
+
+    // BVH
+    auto t0 = std::chrono::steady_clock::now();
+    // Conservative padding of every stored box: the reference's edge tests round, so a primitive
+    // can report a hit a few ulps outside its own bounds (DESIGN.md "Conservative boxes").
+    float maxabs = 0;
+    for (int a = 0; a < 3; ++a) maxabs = std::max(maxabs, std::max(std::fabs(world.mn[a]), std::fabs(world.mx[a])));
+    const float pad = 4e-6f * maxabs + 1e-30f;
+    int nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+    Builder bld(boxes, nthreads);
+    int root = bld.Alloc();
+    bld.Build(root, 0, N);
+
+    // flatten: inner nodes depth-first, leaves reference idx ranges (== slot ranges)
+    std::vector<Float4>& fn = hs.nodes;
+    fn.clear();
+    struct Item { int tmp; int flat; };
+    std::vector<Item> stack;
+    auto box_of = [&](int tmp, float mn[3], float mx[3]) {
+        const Box& b = bld.nodes[tmp].box;
+        for (int a = 0; a < 3; ++a) { mn[a] = b.mn[a] - pad; mx[a] = b.mx[a] + pad; }
+    };
+    auto emit_inner = [&]() { int i = (int)(fn.size() / kNodeStride); fn.resize(fn.size() + kNodeStride); return i; };
+    const float inf = std::numeric_limits<float>::infinity();
+    if (bld.nodes[root].count > 0) {
+        // root is a leaf: wrap it in an inner node whose right child is an empty, never-hit box
+        int f = emit_inner();
+        float mn[3], mx[3];
+        box_of(root, mn, mx);
+        fn[f * kNodeStride + 0] = Float4{mn[0], mn[1], mn[2], mx[0]};
+        fn[f * kNodeStride + 1] = Float4{mx[1], mx[2], inf, inf};
+        fn[f * kNodeStride + 2] = Float4{inf, -inf, -inf, -inf};
+        fn[f * kNodeStride + 3] = Float4{IntAsFloat(LeafRef(bld.nodes[root].first, bld.nodes[root].count)), IntAsFloat(LeafRef(0, 0)), 0, 0};
+    } else {
+        stack.push_back(Item{root, emit_inner()});
+        while (!stack.empty()) {
+            Item it = stack.back();
+            stack.pop_back();
+            const TmpNode& T = bld.nodes[it.tmp];
+            int refs[2];
+            int kids[2] = {T.left, T.right};
+            float mn[2][3], mx[2][3];
+            int child_flat[2] = {-1, -1};
+            for (int k = 0; k < 2; ++k) {
+                const TmpNode& K = bld.nodes[kids[k]];
+                box_of(kids[k], mn[k], mx[k]);
+                if (K.count > 0) refs[k] = LeafRef(K.first, K.count);
+                else { child_flat[k] = emit_inner(); refs[k] = child_flat[k]; }
+            }
+            fn[it.flat * kNodeStride + 0] = Float4{mn[0][0], mn[0][1], mn[0][2], mx[0][0]};
+            fn[it.flat * kNodeStride + 1] = Float4{mx[0][1], mx[0][2], mn[1][0], mn[1][1]};
+            fn[it.flat * kNodeStride + 2] = Float4{mn[1][2], mx[1][0], mx[1][1], mx[1][2]};
+            fn[it.flat * kNodeStride + 3] = Float4{IntAsFloat(refs[0]), IntAsFloat(refs[1]), 0, 0};
+            // push right first so the left subtree is laid out right after its parent
+            if (child_flat[1] >= 0) stack.push_back(Item{kids[1], child_flat[1]});
+            if (child_flat[0] >= 0) stack.push_back(Item{kids[0], child_flat[0]});
+        }
+    }
+    hs.bvh_build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+    // slots in leaf order
+    hs.slots.resize((size_t)N * kSlotStride);
+    hs.slot_nrm.resize(N);
+    hs.slot_ml.resize(N);
+    hs.prim_slot.resize(N);
+    for (int s = 0; s < N; ++s) {
+        int p = bld.idx[s];
+        for (int k = 0; k < kSlotStride; ++k) hs.slots[(size_t)s * kSlotStride + k] = pre_slots[(size_t)p * kSlotStride + k];
+        hs.slot_nrm[s] = pre_nrm[p];
+        hs.slot_ml[s] = Int2{d->primitives[p].material, d->primitives[p].light};
+        hs.prim_slot[p] = s;
+    }
+    return 0;
+}
+
+}  // namespace jpbrt

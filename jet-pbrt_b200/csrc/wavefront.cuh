@@ -1,0 +1,328 @@
+// wavefront.cuh -- the five wavefront stages of the B200 path tracer (sm_100a).
+//
+//   generate  : FSampler::GetCameraSample + FCamera::GenerateRay      (integrator.cc:100-101, camera.h:52-58)
+//   extend    : FScene::Intersect, closest hit                         (integrator.cc:327, scene.cc:25-33)
+//   shade     : Le / env, BSDF build, NEE light sampling + BSDF eval,  (integrator.cc:328-399)
+//               BSDF sampling, Russian roulette, throughput update
+//   connect   : FScene::Occluded for the NEE shadow rays + contribution (integrator.cc:367-370)
+//   accumulate: radiance sums -> film; finalize = Clamp01(mean)         (integrator.cc:102-108, film.h:64-68)
+//
+// A path is a 48-byte record (3 x float4, SoA) that is rewritten, compacted, once per bounce:
+//   o = (origin.xyz, pixel)   d = (dir.xyz, sample | bounce << 24 | specular << 31)   b = (beta.rgb, -)
+// Queues ARE the records: survivors of `shade` are written contiguously into the other half of a
+// ping-pong buffer at positions handed out by one warp-aggregated atomicAdd per warp
+// (__ballot_sync + __popc), so every stage reads and writes fully coalesced 16-byte lanes.
+// Shadow rays fan out into their own queue of 48-byte records (origin+tmax, dir+pixel, contribution).
+// All radiance goes straight to the float film with RED.ADD.F32 (no per-path radiance state).
+//
+// Kernels are persistent: grid = SMs x resident blocks, each warp pulls batches of 32 queue items
+// from a device-side work counter, and queue lengths are read from device memory -- the host
+// never reads a count back, so a whole pass is one uninterrupted stream of launches.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "bsdf.cuh"
+#include "dev_scene.h"
+#include "dmath.cuh"
+#include "intersect.cuh"
+#include "light.cuh"
+#include "rng.cuh"
+
+namespace jpbrt {
+
+enum { CNT_RAYS = 0, CNT_SHADOW = 1, CNT_W_EXTEND = 2, CNT_W_SHADE = 3, CNT_W_CONNECT = 4, CNT_KINDS = 5 };
+enum {
+    ST_SAMPLES = 0, ST_EXT_RAYS, ST_SHADOW_RAYS, ST_VERTICES, ST_BOX, ST_PRIM, ST_SH_BOX, ST_SH_PRIM, ST_INVALID, ST_DROPPED, ST_COUNT
+};
+
+struct WfParams {
+    DevScene sc;
+    float4* ray_o[2];
+    float4* ray_d[2];
+    float4* ray_b[2];
+    float2* hit;
+    float4* sh_o;
+    float4* sh_d;
+    float4* sh_c;
+    int* counters;  // [CNT_KINDS][counter_stride]
+    int counter_stride;
+    float* film;
+    unsigned long long* stats;
+    RngKey key;
+    int sample_begin;
+    int npix;
+    int blocks_per_bounce;
+    int shadow_capacity;
+};
+
+constexpr int kBlock = 256;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// One atomicAdd per warp hands out `32` consecutive work items.
+__device__ __forceinline__ int warp_fetch(int* counter) {
+    int base = 0;
+    if (lane_id() == 0) base = atomicAdd(counter, 32);
+    return __shfl_sync(kFull, base, 0);
+}
+
+// Append for whichever lanes are currently converged here (NEE fan-out inside divergent code).
+__device__ __forceinline__ int coalesced_append(int* counter) {
+    const unsigned active = __activemask();
+    const int leader = __ffs(active) - 1;
+    const int rank = __popc(active & ((1u << lane_id()) - 1));
+    int base = 0;
+    if (lane_id() == leader) base = atomicAdd(counter, __popc(active));
+    base = __shfl_sync(active, base, leader);
+    return base + rank;
+}
+
+// accumulate: film[pixel] += c   (radiance sums; FFilm::AddColor happens at finalize)
+__device__ __forceinline__ void film_add(const WfParams& p, int pixel, const f3& c) {
+    if (!(isfinite(c.x) && isfinite(c.y) && isfinite(c.z))) {  // the reference only logs these (integrator.cc:104)
+        atomicAdd(p.stats + ST_INVALID, 1ull);
+        return;
+    }
+    float* px = p.film + 3 * (size_t)pixel;
+    if (c.x != 0.f) atomicAdd(px + 0, c.x);
+    if (c.y != 0.f) atomicAdd(px + 1, c.y);
+    if (c.z != 0.f) atomicAdd(px + 2, c.z);
+}
+
+__device__ __forceinline__ void warp_stat_add(unsigned long long* dst, unsigned v) {
+    v = __reduce_add_sync(kFull, v);
+    if (lane_id() == 0 && v) atomicAdd(dst, (unsigned long long)v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// generate
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_generate(const __grid_constant__ WfParams p, int n_paths) {
+    const DevCamera& cam = p.sc.cam;
+    const f3 pos = mk3(cam.pos[0], cam.pos[1], cam.pos[2]);
+    const f3 front = mk3(cam.front[0], cam.front[1], cam.front[2]);
+    const f3 right = mk3(cam.right[0], cam.right[1], cam.right[2]);
+    const f3 up = mk3(cam.up[0], cam.up[1], cam.up[2]);
+    const int W = p.sc.width;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_paths; i += gridDim.x * blockDim.x) {
+        const int pixel = i % p.npix;
+        const int sample = p.sample_begin + i / p.npix;
+        const int x = pixel % W, y = pixel / W;
+        const float4 u = rng_block(p.key, (uint32_t)pixel, (uint32_t)sample, 0u);
+        const float fx = (float)x + u.x, fy = (float)y + u.y;  // sampler.h:152
+        const f3 dir = front + right * (fx / cam.res_x - 0.5f) + up * (0.5f - fy / cam.res_y);  // camera.h:54-55
+        const f3 d = normalize(dir);
+        p.ray_o[0][i] = make_float4(pos.x, pos.y, pos.z, __int_as_float(pixel));
+        p.ray_d[0][i] = make_float4(d.x, d.y, d.z, __int_as_float(sample & 0xffffff));
+        p.ray_b[0][i] = make_float4(1.f, 1.f, 1.f, 0.f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        p.counters[CNT_RAYS * p.counter_stride + 0] = n_paths;
+        atomicAdd(p.stats + ST_SAMPLES, (unsigned long long)n_paths);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// extend: closest hit for every ray of iteration `it`
+// ---------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_extend(const __grid_constant__ WfParams p, int it) {
+    const int n = p.counters[CNT_RAYS * p.counter_stride + it];
+    int* work = p.counters + CNT_W_EXTEND * p.counter_stride + it;
+    const int buf = it & 1;
+    unsigned nb = 0, np = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.stats + ST_EXT_RAYS, (unsigned long long)n);
+    for (;;) {
+        const int base = warp_fetch(work);
+        if (base >= n) break;
+        const int i = base + lane_id();
+        if (i < n) {
+            const float4 ro = p.ray_o[buf][i];
+            const float4 rd = p.ray_d[buf][i];
+            float tmax = __int_as_float(0x7f800000);
+            const int slot = traverse<false, COUNT>(p.sc, mk3(ro), mk3(rd), JPBRT_RAY_TMIN, tmax, nb, np);
+            p.hit[i] = make_float2(tmax, __int_as_float(slot));
+        }
+    }
+    if (COUNT) {
+        warp_stat_add(p.stats + ST_BOX, nb);
+        warp_stat_add(p.stats + ST_PRIM, np);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// connect: any-hit for every shadow ray of iteration `it`; unoccluded -> film += contribution
+// ---------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_connect(const __grid_constant__ WfParams p, int it) {
+    int n = p.counters[CNT_SHADOW * p.counter_stride + it];
+    if (n > p.shadow_capacity) n = p.shadow_capacity;
+    int* work = p.counters + CNT_W_CONNECT * p.counter_stride + it;
+    unsigned nb = 0, np = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.stats + ST_SHADOW_RAYS, (unsigned long long)n);
+    for (;;) {
+        const int base = warp_fetch(work);
+        if (base >= n) break;
+        const int i = base + lane_id();
+        if (i < n) {
+            const float4 so = p.sh_o[i];
+            const float4 sd = p.sh_d[i];
+            float tmax = so.w;
+            const int slot = traverse<true, COUNT>(p.sc, mk3(so), mk3(sd), JPBRT_RAY_TMIN, tmax, nb, np);
+            if (slot < 0) {
+                const float4 c = p.sh_c[i];
+                film_add(p, __float_as_int(sd.w), mk3(c));
+            }
+        }
+    }
+    if (COUNT) {
+        warp_stat_add(p.stats + ST_SH_BOX, nb);
+        warp_stat_add(p.stats + ST_SH_PRIM, np);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shade
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ WfParams p, int it) {
+    const DevScene& sc = p.sc;
+    const int n = p.counters[CNT_RAYS * p.counter_stride + it];
+    int* work = p.counters + CNT_W_SHADE * p.counter_stride + it;
+    int* next_count = p.counters + CNT_RAYS * p.counter_stride + it + 1;
+    int* shadow_count = p.counters + CNT_SHADOW * p.counter_stride + it;
+    const int buf = it & 1, nbuf = buf ^ 1;
+    unsigned n_vertices = 0;
+    for (;;) {
+        const int base = warp_fetch(work);
+        if (base >= n) break;
+        const int i = base + lane_id();
+        bool alive = false;
+        float4 no = make_float4(0, 0, 0, 0), nd = no, nbeta = no;
+        if (i < n) {
+            const float4 ro = p.ray_o[buf][i];
+            const float4 rd = p.ray_d[buf][i];
+            const float4 rb = p.ray_b[buf][i];
+            const float2 h = p.hit[i];
+            const f3 o = mk3(ro), d = mk3(rd);
+            f3 beta = mk3(rb);
+            const int pixel = __float_as_int(ro.w);
+            const int fl = __float_as_int(rd.w);
+            const int sample = fl & 0xffffff;
+            const int bounce = (fl >> 24) & 0x7f;
+            const bool specular = fl < 0;
+            const int slot = __float_as_int(h.y);
+            const bool add_emission = (bounce == 0) || specular;  // integrator.cc:328
+            if (slot < 0) {
+                if (add_emission)
+                    for (int k = 0; k < sc.n_inf_lights; ++k)  // integrator.cc:334-335
+                        film_add(p, pixel, cmul(beta, mk3(ldg4(sc.lights + (size_t)sc.inf_lights[k] * kLightStride))));
+            } else {
+                const float t = h.x;
+                const f3 P = o + t * d;  // FRay::operator(), geometry.h:413-417
+                const f3 N = hit_normal(sc, slot, P, d);
+                const f3 wo = -d;
+                const int2 ml = __ldg(reinterpret_cast<const int2*>(sc.slot_ml) + slot);
+                if (add_emission && ml.y >= 0) {
+                    const f3 Le = emitted(sc, ml.y, N, wo);
+                    if (!is_black(Le)) film_add(p, pixel, cmul(beta, Le));  // integrator.cc:331
+                }
+                if (bounce < sc.max_depth) {  // integrator.cc:340
+                    if (ml.x < 0) {
+                        // null material: the ray continues unchanged and the bounce is not counted (integrator.cc:349-353)
+                        alive = true;
+                        no = make_float4(P.x, P.y, P.z, ro.w);
+                        nd = rd;
+                        nbeta = rb;
+                    } else {
+                        ++n_vertices;
+                        const uint32_t blk = 1u + (uint32_t)bounce * (uint32_t)p.blocks_per_bounce;
+                        const float4 u0 = rng_block(p.key, (uint32_t)pixel, (uint32_t)sample, blk);
+                        const Bsdf bsdf = make_bsdf(sc.materials + (size_t)ml.x * kMaterialStride, u0.x);
+                        const Frame frame = make_frame(N);
+                        const f3 wo_l = to_local(frame, wo);
+                        if (!bsdf_is_delta(bsdf)) {  // integrator.cc:357-372
+                            float4 lu = make_float4(0, 0, 0, 0);
+                            for (int j = 0; j < sc.n_lights; ++j) {
+                                if ((j & 1) == 0) lu = rng_block(p.key, (uint32_t)pixel, (uint32_t)sample, blk + 1u + (uint32_t)(j >> 1));
+                                const float ux = (j & 1) ? lu.z : lu.x, uy = (j & 1) ? lu.w : lu.y;
+                                const LightSample ls = sample_light(sc, j, P, N, ux, uy);
+                                if (is_black(ls.Li) || ls.pdf == 0.f) continue;
+                                const f3 f = bsdf_eval_local(bsdf, wo_l, to_local(frame, ls.wi));
+                                if (is_black(f)) continue;
+                                // FScene::Occluded(isect, ls.pos): scene.h:36-47
+                                const f3 v = ls.pos - P;
+                                const float dist = length(v);
+                                const f3 sdir = v / dist;
+                                const f3 contrib = cmul(cmul(beta, f), ls.Li) * absdot(ls.wi, N) / ls.pdf;  // integrator.cc:369
+                                const int si = coalesced_append(shadow_count);
+                                if (si < p.shadow_capacity) {
+                                    p.sh_o[si] = make_float4(P.x, P.y, P.z, dist - 0.001f);
+                                    p.sh_d[si] = make_float4(sdir.x, sdir.y, sdir.z, ro.w);
+                                    p.sh_c[si] = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
+                                }
+                            }
+                        }
+                        BsdfSample bs = bsdf_sample_local(bsdf, wo_l, u0.y, u0.z);  // integrator.cc:375
+                        bs.wi = to_world(frame, bs.wi);                               // bsdf.h:296-302
+                        if (!(is_black(bs.f) || bs.pdf == 0.f)) {
+                            const bool spec = (bs.flags & BSDF_SPECULAR) != 0;
+                            bool survive = true;
+                            if (bounce >= JPBRT_RR_START_BOUNCE) {  // integrator.cc:383-393
+                                const float q = std_max(JPBRT_RR_QMIN, 1 - max_component(bs.f));
+                                if (u0.w < q) survive = false;
+                                else beta = cmul(beta, bs.f * absdot(bs.wi, N) / (bs.pdf * (1 - q)));
+                            } else {
+                                beta = cmul(beta, bs.f * absdot(bs.wi, N) / bs.pdf);  // integrator.cc:397
+                            }
+                            // A non-specular path that would arrive at bounce == maxDepth can add nothing
+                            // there (no emission, integrator.cc:328; loop ends, :340): do not trace it.
+                            if (survive && (spec || bounce + 1 < sc.max_depth)) {
+                                alive = true;
+                                no = make_float4(P.x, P.y, P.z, ro.w);
+                                nd = make_float4(bs.wi.x, bs.wi.y, bs.wi.z,
+                                                 __int_as_float(sample | ((bounce + 1) << 24) | (spec ? (int)0x80000000 : 0)));
+                                nbeta = make_float4(beta.x, beta.y, beta.z, 0.f);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // compaction of the survivors: one atomicAdd per warp
+        const unsigned mask = __ballot_sync(kFull, alive);
+        if (mask) {
+            int wbase = 0;
+            if (lane_id() == 0) wbase = atomicAdd(next_count, __popc(mask));
+            wbase = __shfl_sync(kFull, wbase, 0);
+            if (alive) {
+                const int dst = wbase + __popc(mask & ((1u << lane_id()) - 1));
+                p.ray_o[nbuf][dst] = no;
+                p.ray_d[nbuf][dst] = nd;
+                p.ray_b[nbuf][dst] = nbeta;
+            }
+        }
+    }
+    warp_stat_add(p.stats + ST_VERTICES, n_vertices);
+}
+
+// Paths still queued after the last iteration (only possible with null-material chains) are dropped and counted.
+__global__ void k_count_dropped(const __grid_constant__ WfParams p, int it) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int n = p.counters[CNT_RAYS * p.counter_stride + it];
+        if (n > 0) atomicAdd(p.stats + ST_DROPPED, (unsigned long long)n);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// accumulate / finalize: out = Clamp01(sum * (1/spp))   (integrator.cc:89,102,108; film.h:22-23)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_finalize(const float* __restrict__ film, float* __restrict__ out, size_t n, float ratio) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = film[i] * ratio;
+        out[i] = clampf(v, 0.f, 1.f);
+    }
+}
+
+}  // namespace jpbrt

@@ -1,0 +1,119 @@
+// capi_host.cc -- host-only entry points of the C ABI: built-in scenes and the film writers.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/jetpbrt_b200.h"
+#include "scene.h"
+
+struct jpbrt_scene {
+    std::unique_ptr<jetpbrt::Scene> scene;
+};
+
+namespace {
+
+inline float Clamp01(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
+// gamma_encoding, film.h:24
+inline uint8_t GammaEncode(float x) { return (uint8_t)(std::pow(Clamp01(x), (float)(1 / 2.2)) * 255.0); }
+
+// FFilm::SaveAsPPM, film.cc:45-60 (the reference streams uint8_t with operator<<, i.e. as characters; the
+// numbers are written as text here so the "P3" header is honoured -- DESIGN.md "Deviations").
+bool SavePPM(const std::string& fn, int w, int h, const float* rgb) {
+    std::ofstream f(fn, std::ios::binary);
+    if (!f) return false;
+    f << "P3\n" << w << " " << h << "\n255\n";
+    for (int i = 0; i < w * h; ++i)
+        f << (int)GammaEncode(rgb[3 * i]) << "  " << (int)GammaEncode(rgb[3 * i + 1]) << "  " << (int)GammaEncode(rgb[3 * i + 2]) << "\n";
+    return (bool)f;
+}
+
+// FFilm::SaveAsBMP, film.cc:62-144: 24-bit BGR, gamma 1/2.2, rows bottom-up.
+bool SaveBMP(const std::string& fn, int w, int h, const float* rgb) {
+    std::ofstream f(fn, std::ios::binary);
+    if (!f) return false;
+    const uint32_t line = ((uint32_t)w * 3 + 3) & ~3u;
+    const uint32_t image = line * (uint32_t)h;
+    uint8_t hdr[54] = {0};
+    auto put16 = [&](int off, uint16_t v) { memcpy(hdr + off, &v, 2); };
+    auto put32 = [&](int off, uint32_t v) { memcpy(hdr + off, &v, 4); };
+    put16(0, 0x4d42);
+    put32(2, 54 + image);
+    put32(10, 54);
+    put32(14, 40);
+    put32(18, (uint32_t)w);
+    put32(22, (uint32_t)h);
+    put16(26, 1);
+    put16(28, 24);
+    f.write((const char*)hdr, 54);
+    std::vector<uint8_t> row(line, 0);
+    for (int y = h - 1; y >= 0; --y) {
+        for (int x = 0; x < w; ++x) {
+            const float* p = rgb + 3 * ((size_t)y * w + x);
+            row[3 * x + 0] = GammaEncode(p[2]);
+            row[3 * x + 1] = GammaEncode(p[1]);
+            row[3 * x + 2] = GammaEncode(p[0]);
+        }
+        f.write((const char*)row.data(), line);
+    }
+    return (bool)f;
+}
+
+// FFilm::SaveAsHDR, film.cc:147-188: flat (non-RLE) RGBE.
+bool SaveHDR(const std::string& fn, int w, int h, const float* rgb) {
+    std::ofstream f(fn, std::ios::binary);
+    if (!f) return false;
+    f << "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y " << h << " +X " << w << "\n";
+    for (int i = 0; i < w * h; ++i) {
+        uint8_t rgbe[4] = {0, 0, 0, 0};
+        const float* c = rgb + 3 * (size_t)i;
+        float v = std::max({c[0], c[1], c[2]});
+        if (v >= 1e-32f) {
+            int e;
+            float m = float(std::frexp(v, &e) * 256.f / v);
+            rgbe[0] = uint8_t(c[0] * m);
+            rgbe[1] = uint8_t(c[1] * m);
+            rgbe[2] = uint8_t(c[2] * m);
+            rgbe[3] = uint8_t(e + 128);
+        }
+        f.write((const char*)rgbe, 4);
+    }
+    return (bool)f;
+}
+
+}  // namespace
+
+extern "C" {
+
+jpbrt_scene* jpbrt_scene_builtin(const char* name, int width, int height, float scale) {
+    if (!name || width <= 0 || height <= 0) return nullptr;
+    jetpbrt::Scene* s = jetpbrt::MakeBuiltinScene(name, width, height, scale);
+    if (!s) return nullptr;
+    jpbrt_scene* h = new jpbrt_scene();
+    h->scene.reset(s);
+    return h;
+}
+
+const jpbrt_scene_desc* jpbrt_scene_get_desc(jpbrt_scene* s) { return s ? s->scene->Desc() : nullptr; }
+
+void jpbrt_scene_free(jpbrt_scene* s) { delete s; }
+
+int jpbrt_save_image(const char* basename, int kind, int width, int height, const float* rgb) {
+    if (!basename || !rgb || width <= 0 || height <= 0) return JPBRT_ERR_INVALID;
+    std::string base(basename);
+    bool ok = false;
+    switch (kind) {  // EImageType, film.h:15-20
+    case 0: ok = SavePPM(base + ".ppm", width, height, rgb); break;
+    case 1: ok = SaveBMP(base + ".bmp", width, height, rgb); break;
+    case 2: ok = SaveHDR(base + ".hdr", width, height, rgb); break;
+    default: return JPBRT_ERR_INVALID;
+    }
+    return ok ? JPBRT_OK : JPBRT_ERR_IO;
+}
+
+}  // extern "C"

@@ -1,0 +1,48 @@
+// render.h -- host-side mirror of the reference's render entry point for the B200 path.
+//
+//   reference (integrator.h:25-41, film.h:27-94, main.cc:149-160)     here
+//   FFilm film(w, h)                                                   jetpbrt::Film film(w, h)
+//   FRandomSampler sampler(spp)                                        (spp argument; sampler is counter based)
+//   FPathIntegratorIteration integrator(5)                             jetpbrt::PathIntegratorIteration integrator(5)
+//   integrator.Render(scene, sampler, &film, 16)                       integrator.Render(scene, spp, &film, device)
+//   film.SaveAsImage(name, EImageType::BMP)                            film.SaveAsImage(name, EImageType::BMP)
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "scene.h"
+
+namespace jetpbrt {
+
+enum class EImageType { PPM = 0, BMP = 1, HDR = 2 };  // film.h:15-20
+
+class Film {
+public:
+    Film(int w, int h) : width_(w), height_(h), pixels_((size_t)w * h * 3, 0.f) {}
+    int Width() const { return width_; }
+    int Height() const { return height_; }
+    float* Data() { return pixels_.data(); }
+    const float* Data() const { return pixels_.data(); }
+    void Clear() { std::fill(pixels_.begin(), pixels_.end(), 0.f); }
+    bool SaveAsImage(const std::string& filename, EImageType type) const;  // film.cc:13-43
+
+private:
+    int width_, height_;
+    std::vector<float> pixels_;  // row-major RGB, row 0 = top (film.h:50-56)
+};
+
+class PathIntegratorIteration {
+public:
+    explicit PathIntegratorIteration(int maxDepth) : maxDepth_(maxDepth) {}
+    // Blocks until the film is filled, like FIntegrator::Render (integrator.cc:35-80); adds
+    // Clamp01(mean radiance) onto the film (film.h:64-68).  Returns false and prints the C-ABI
+    // error on failure (the reference's Render returns void and cannot fail).
+    bool Render(Scene* scene, int spp, Film* film, int device = 0, uint64_t seed = 1234) const;
+
+private:
+    int maxDepth_;
+};
+
+}  // namespace jetpbrt
