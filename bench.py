@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 wavefront path tracer (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config bunny|cornell|glossy|large|cornell4k]
+    python bench.py --impl reference ...        # the reference's own CPU renderer, same metric/config
+
+One "step" = one complete render of the workload: every pixel x spp samples through the hot path
+(generate, extend, shade, connect, accumulate) + the film finalize; with N > 1 every rank renders its
+own `spp` sample indices of every pixel (weak scaling, scene replicated) and the raw float32 films are
+summed with ONE NCCL reduce onto rank 0 inside the step.
+
+  value : whole-job Msamples/s over the K timed steps, scene already resident in HBM, CUDA-event time,
+          max over ranks.
+  e2e   : the same metric through the C-ABI calls a caller of FIntegrator::Render would make, with HOST
+          buffers: every step re-uploads the flattened scene from pinned host memory, renders, reduces,
+          finalizes and reads the film back to pinned host memory (wall clock with device sync).
+  roofline : the closest-hit traversal kernel (k_extend): algorithmic bytes (32 B per box test + 48 B per
+          primitive test + 48 B ray/hit record) over its CUDA-event time, against the
+          measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline : the UNMODIFIED reference (oracle/_ref, else the pinned restatement) timed on this host's
+          cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CONFIGS = {
+    # name: (scene, scale, width, height, spp per GPU, BASELINE.json config it is)
+    "bunny": ("bunny", 1.0, 1024, 1024, 50, "configs[1] bunny scene: 4 x 5,040-triangle mesh stand-in, matte/plastic/metal/glass, depth 5"),
+    "cornell": ("cornell", 1.0, 1024, 1024, 50, "configs[0] Cornell box as in main.cc, depth 5"),
+    "large": ("large", 1.0, 1024, 1024, 16, "configs[2] synthetic 5M-triangle scene, depth 8"),
+    "glossy": ("glossy", 1.0, 1024, 1024, 16, "configs[3] glossy room, 16 area lights, depth 16"),
+    "cornell4k": ("cornell", 1.0, 3840, 2160, 64, "configs[4] Cornell box 3840x2160 (spp reduced per step; throughput is spp-independent)"),
+}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's own CPU implementation of the path (parallel.cc thread pool)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import __graft_entry__ as ge
+
+    pkg, orc = ge.load_package(), ge.load_oracle()
+    scene_name, scale, w, h, spp, desc = cfg
+    kind = "reference" if orc.have("ref") else "port"
+    o = orc.Oracle("ref" if kind == "reference" else "port")
+    threads = os.cpu_count() or 1
+    sc = pkg.HostScene.builtin(scene_name, w, h, scale)
+    t0 = time.perf_counter()
+    s = o.scene(sc)
+    build_s = time.perf_counter() - t0
+    # bounded sample: 1 spp probe, then an spp that keeps one step near 6 s
+    _, probe = s.render(1, threads)
+    step_spp = max(1, min(spp, int(6.0 / max(probe, 1e-3))))
+    for _ in range(max(0, min(args.warmup, 1))):
+        s.render(step_spp, threads)
+    times = []
+    for _ in range(args.steps):
+        _, sec = s.render(step_spp, threads)
+        times.append(sec)
+    total = sum(times)
+    samples = w * h * step_spp * args.steps
+    value = samples / total / 1e6
+    line = {"impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {desc}", "width": w, "height": h, "spp_per_step": step_spp, "max_depth": sc.d.max_depth,
+                       "n_primitives": sc.d.n_primitives, "n_lights": sc.d.n_lights},
+            "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": kind,
+                             "sample": f"{w}x{h} x {step_spp} spp per step, FIntegrator::Render with numthreads={threads}; scene build {build_s:.2f}s excluded"},
+            "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="bunny", choices=sorted(CONFIGS))
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--paths-in-flight", type=int, default=0)
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    pkg = ge.load_package()
+    sys.path.insert(0, str(ROOT / "jet-pbrt_b200"))
+    import multi_gpu
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or pkg.device_count() <= local:
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    ddist = dist if world > 1 else None
+
+    scene_name, scale, w, h, spp, desc = cfg
+    if args.spp > 0:
+        spp = args.spp
+    sc = pkg.HostScene.builtin(scene_name, w, h, scale)
+    t0 = time.perf_counter()
+    ctx = pkg.Context(sc, device=local)
+    upload_s = time.perf_counter() - t0
+    if args.paths_in_flight:
+        ctx.set_option("paths_in_flight", args.paths_in_flight)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=local)
+    film = ctx.film_tensor()
+    nfloats = film.numel()
+    host_film = torch.empty(nfloats, dtype=torch.float32, pin_memory=True)
+    begin, count = multi_gpu.sample_range(spp, rank)
+    spp_total = spp * world
+    seed = 1234
+
+    def step_resident():
+        ctx.clear_film()
+        ctx.render_pass(begin, count, seed)
+        multi_gpu.reduce_film(film, ddist, 0)
+        if rank == 0:
+            ctx.finalize_film_device(film.data_ptr(), spp_total)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        # ---- counting pass (outside the timed region): box / primitive tests per ray on OUR BVH ----
+        ctx.set_option("count_traversal", 1)
+        ctx.clear_film()
+        ctx.render_pass(begin, min(count, 4), seed)
+        ctx.synchronize()
+        cst = ctx.stats()
+        ctx.set_option("count_traversal", 0)
+        box_per_ray = cst["box_tests"] / max(cst["extension_rays"], 1)
+        prim_per_ray = cst["prim_tests"] / max(cst["extension_rays"], 1)
+        bytes_per_ray = 32.0 * box_per_ray + 48.0 * prim_per_ray + 48.0
+
+        for _ in range(args.warmup):
+            step_resident()
+        barrier()
+        ctx.clear_film()
+        ctx.reset_stats()
+        ctx.set_option("stage_timing", 1)
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_resident()
+        ev1.record(stream)
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        clock_info = clocks.stop() if rank == 0 else None
+        st = ctx.stats()  # totals over the K timed steps (reset_stats() was called just before them)
+        ctx.set_option("stage_timing", 0)
+        t = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        ms_per_step = ms_total / args.steps
+        samples_per_step = w * h * spp_total
+        value = samples_per_step / (ms_per_step * 1e-3) / 1e6
+        rays_per_step_rank = (st["extension_rays"] + st["shadow_rays"]) / args.steps
+
+        # ---- e2e: host buffers in, host film out, every step ----
+        def step_e2e():
+            nbytes = ctx.reupload_scene()
+            ctx.clear_film()
+            ctx.render_pass(begin, count, seed)
+            multi_gpu.reduce_film(film, ddist, 0)
+            if rank == 0:
+                pkg._check(pkg.lib.jpbrt_read_film(ctx._ctx, pkg.C.cast(host_film.data_ptr(), pkg.C.POINTER(pkg.C.c_float)), spp_total, 1), ctx._ctx)
+            else:
+                ctx.synchronize()
+            return nbytes
+
+        for _ in range(2):
+            h2d = step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+        e2e_value = samples_per_step * args.steps / e2e_s / 1e6
+        final_mean = float(host_film.mean()) if rank == 0 else 0.0
+
+    line = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        ext_ms = st["ms_extend"]  # CUDA-event time of all k_extend launches of the K timed steps
+        ext_bytes = st["extension_rays"] * bytes_per_ray
+        achieved = ext_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+        n_ext_launches = sc.d.max_depth + 1
+        line = {
+            "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.config}: {desc}", "width": w, "height": h, "spp_per_gpu_per_step": spp, "spp_total": spp_total,
+                       "max_depth": sc.d.max_depth, "n_primitives": sc.d.n_primitives, "n_lights": sc.d.n_lights,
+                       "parallelism": f"sample-partition x{world}, scene replicated, one NCCL reduce of the f32 film per step",
+                       "l2": f"no explicit flush: each step streams {st_bytes(ctx, sc, spp, w, h) / 1e6:.0f} MB of wavefront state (> 126 MB L2); "
+                             "the scene arrays are legitimately cache-resident across the step",
+                       "seed": seed},
+            "mrays_per_s": rays_per_step_rank * world / (ms_per_step * 1e-3) / 1e6,
+            "rays_per_sample": rays_per_step_rank / (w * h * spp),
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(nfloats * 4),
+                    "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "what": "jpbrt_reupload_scene (pinned host -> HBM) + jpbrt_render_pass + reduce + jpbrt_read_film (finalize, HBM -> pinned host)"},
+            "gpu_launches": int(st["kernel_launches"]),
+            "roofline": {"bound": "hbm", "kernel": "k_extend (closest-hit BVH traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_ray": bytes_per_ray, "box_tests_per_ray": box_per_ray, "prim_tests_per_ray": prim_per_ray,
+                         "rays_per_step": int(st["extension_rays"] / args.steps), "kernel_ms_per_step": ext_ms / args.steps,
+                         "launches_per_step": n_ext_launches * max(1, -(-spp * w * h // max(1, pool_paths(args)))),
+                         "note": "scene is %.1f MB: L1/L2-resident, so the HBM fraction is an upper-bound yardstick, not a DRAM measurement"
+                                 % (st["scene_bytes"] / 1e6)},
+            "stages_ms_per_step": {k[3:]: st[k] / args.steps for k in ("ms_generate", "ms_extend", "ms_shade", "ms_connect", "ms_finalize")},
+            "clocks": clock_info,
+            "upload_s": upload_s, "bvh_build_s": st["bvh_build_seconds"], "film_mean": final_mean,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(pkg, ge, cfg, sc)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+    return 0
+
+
+def pool_paths(args):
+    return args.paths_in_flight if args.paths_in_flight else (1 << 23)
+
+
+def st_bytes(ctx, sc, spp, w, h):
+    # path records (2 x 48 B ping-pong + 8 B hit) for every path of the step, shadow records on top
+    return w * h * spp * (48 * 2 + 8)
+
+
+def cpu_baseline(pkg, ge, cfg, sc):
+    """The reference's CPU renderer on this host, on a bounded sample of the same workload."""
+    orc = ge.load_oracle()
+    scene_name, scale, w, h, spp, desc = cfg
+    kind = "reference" if orc.have("ref") else "port"
+    o = orc.Oracle("ref" if kind == "reference" else "port")
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    s = o.scene(sc)
+    build = time.perf_counter() - t0
+    _, probe = s.render(1, threads)
+    n = max(1, min(spp, int(12.0 / max(probe, 1e-3))))
+    _, sec = s.render(n, threads)
+    return {"value": w * h * n / sec / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind,
+            "sample": f"{w}x{h} x {n} spp of the same scene, FIntegrator::Render numthreads={threads}, {sec:.1f}s (BVH build {build:.2f}s excluded)"}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -58,8 +58,10 @@ int jpbrt_render_pass(jpbrt_ctx* ctx, int sample_begin, int sample_count, uint64
  * Synchronises the stream. */
 int jpbrt_read_film(jpbrt_ctx* ctx, float* rgb, int spp_total, int finalize);
 
-/* Zero the device film (FFilm::Clear, film.h:75-82) and the work counters. */
+/* Zero the device film (FFilm::Clear, film.h:75-82). */
 int jpbrt_clear_film(jpbrt_ctx* ctx);
+/* Zero the work counters, the launch count and the stage timers reported by jpbrt_get_stats. */
+int jpbrt_reset_stats(jpbrt_ctx* ctx);
 
 void        jpbrt_destroy(jpbrt_ctx* ctx);
 const char* jpbrt_last_error(const jpbrt_ctx* ctx); /* ctx may be NULL: last error of this thread */
@@ -97,7 +99,7 @@ typedef struct jpbrt_stats {
     uint64_t shadow_box_tests;
     uint64_t shadow_prim_tests;
     uint64_t invalid_contributions; /* NaN/inf radiance dropped instead of being stored */
-    uint64_t kernel_launches;  /* kernels of this library launched since the last clear */
+    uint64_t kernel_launches;  /* kernels of this library launched since the last jpbrt_reset_stats */
     double   ms_generate, ms_extend, ms_shade, ms_connect, ms_finalize; /* with option "stage_timing" = 1 */
     uint64_t n_nodes, n_prim_slots, scene_bytes;
     double   bvh_build_seconds;
@@ -146,6 +148,15 @@ void                    jpbrt_scene_free(jpbrt_scene* s);
 
 /* FFilm::SaveAsImage (film.cc:13-43): kind 0 = PPM, 1 = BMP, 2 = HDR; `basename` without extension. */
 int jpbrt_save_image(const char* basename, int kind, int width, int height, const float* rgb);
+
+/* Number of CUDA devices visible (0 if none / no driver): lets callers skip instead of fail. */
+int jpbrt_device_count(void);
+
+/* Host-only view of what jpbrt_upload_scene would upload, for validating the BVH and the flattened
+ * tables without a GPU.  `what`: 0 nodes, 1 slots, 2 slot_nrm (float4 records); 3 slot_ml (int2),
+ * 4 prim_slot (int); 5 materials, 6 lights (float4 records).  Copies up to `capacity` 32-bit words
+ * into `out` (may be NULL) and returns the total number of 32-bit words, or a negative status. */
+long long jpbrt_debug_flatten(const jpbrt_scene_desc* desc, int what, void* out, long long capacity);
 
 const char* jpbrt_version(void);
 

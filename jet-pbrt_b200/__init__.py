@@ -72,13 +72,13 @@ class Stats(C.Structure):
 
 # Every symbol include/jetpbrt_b200.h declares (tests check the library exports them all).
 EXPORTS = [
-    "jpbrt_upload_scene", "jpbrt_render_pass", "jpbrt_read_film", "jpbrt_clear_film", "jpbrt_destroy",
+    "jpbrt_upload_scene", "jpbrt_render_pass", "jpbrt_read_film", "jpbrt_clear_film", "jpbrt_reset_stats", "jpbrt_destroy",
     "jpbrt_last_error", "jpbrt_render", "jpbrt_film_device_ptr", "jpbrt_film_num_floats", "jpbrt_stream",
     "jpbrt_synchronize", "jpbrt_finalize_film_device", "jpbrt_reupload_scene", "jpbrt_set_option",
     "jpbrt_get_stats", "jpbrt_unit_intersect_shape", "jpbrt_unit_scene_intersect", "jpbrt_unit_scene_occluded",
     "jpbrt_unit_bsdf", "jpbrt_unit_light_sample", "jpbrt_unit_emitted", "jpbrt_unit_generate_rays",
     "jpbrt_unit_rng_block", "jpbrt_scene_info", "jpbrt_scene_builtin", "jpbrt_scene_get_desc",
-    "jpbrt_scene_free", "jpbrt_save_image", "jpbrt_version",
+    "jpbrt_scene_free", "jpbrt_save_image", "jpbrt_version", "jpbrt_device_count", "jpbrt_debug_flatten",
 ]
 
 
@@ -100,6 +100,7 @@ def _load():
     lib.jpbrt_render_pass.argtypes = [P, I, I, C.c_uint64]
     lib.jpbrt_read_film.argtypes = [P, F, I, I]
     lib.jpbrt_clear_film.argtypes = [P]
+    lib.jpbrt_reset_stats.argtypes = [P]
     lib.jpbrt_destroy.argtypes = [P]
     lib.jpbrt_destroy.restype = None
     lib.jpbrt_render.argtypes = [C.POINTER(SceneDesc), I, C.c_uint64, I, F, C.POINTER(C.c_double)]
@@ -131,6 +132,9 @@ def _load():
     lib.jpbrt_scene_free.argtypes = [P]
     lib.jpbrt_scene_free.restype = None
     lib.jpbrt_save_image.argtypes = [C.c_char_p, I, I, I, F]
+    lib.jpbrt_device_count.restype = I
+    lib.jpbrt_debug_flatten.argtypes = [C.POINTER(SceneDesc), I, P, C.c_longlong]
+    lib.jpbrt_debug_flatten.restype = C.c_longlong
     return lib
 
 
@@ -239,6 +243,9 @@ class Context:
 
     def clear_film(self):
         _check(lib.jpbrt_clear_film(self._ctx), self._ctx)
+
+    def reset_stats(self):
+        _check(lib.jpbrt_reset_stats(self._ctx), self._ctx)
 
     def synchronize(self):
         _check(lib.jpbrt_synchronize(self._ctx), self._ctx)
@@ -377,6 +384,25 @@ def save_image(basename: str, kind: int, film: np.ndarray):
     film = _f32(film)
     h, w = film.shape[0], film.shape[1]
     _check(lib.jpbrt_save_image(basename.encode(), kind, w, h, _f(film)))
+
+
+def device_count() -> int:
+    return lib.jpbrt_device_count()
+
+
+_TABLES = {"nodes": (0, np.float32), "slots": (1, np.float32), "slot_nrm": (2, np.float32), "slot_ml": (3, np.int32),
+           "prim_slot": (4, np.int32), "materials": (5, np.float32), "lights": (6, np.float32)}
+
+
+def debug_flatten(scene: HostScene, table: str) -> np.ndarray:
+    """Host-only copy of one flattened table (see jpbrt_debug_flatten)."""
+    what, dt = _TABLES[table]
+    n = lib.jpbrt_debug_flatten(scene.desc, what, None, 0)
+    if n < 0:
+        _check(int(n))
+    out = np.empty(int(n), dtype=dt)
+    lib.jpbrt_debug_flatten(scene.desc, what, out.ctypes.data_as(C.c_void_p), n)
+    return out
 
 
 def version() -> str:

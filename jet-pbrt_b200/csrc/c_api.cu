@@ -90,6 +90,7 @@ struct jpbrt_ctx {
     double ms_stage[5] = {0, 0, 0, 0, 0};
     std::vector<StageEvent> pending_events;
     std::vector<cudaEvent_t> free_events;
+    std::vector<void*> pinned;  // host scene arrays registered with cudaHostRegister
 };
 
 namespace {
@@ -150,6 +151,14 @@ int occupancy_grid(jpbrt_ctx* c, K kernel) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0) != cudaSuccess || per_sm <= 0) per_sm = 1;
     return c->sm_count * per_sm;
+}
+
+// Page-lock the flattened host arrays so that (re)uploads are true asynchronous DMA transfers.
+template <typename T>
+void pin_vector(jpbrt_ctx* c, std::vector<T>& v) {
+    if (v.empty()) return;
+    if (cudaHostRegister(v.data(), v.size() * sizeof(T), cudaHostRegisterDefault) == cudaSuccess) c->pinned.push_back(v.data());
+    else cudaGetLastError();
 }
 
 int upload_arrays(jpbrt_ctx* c, size_t* bytes) {
@@ -220,6 +229,33 @@ WfParams make_params(jpbrt_ctx* c, int sample_begin, uint64_t seed) {
 
 extern "C" {
 
+int jpbrt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+long long jpbrt_debug_flatten(const jpbrt_scene_desc* desc, int what, void* out, long long capacity) {
+    HostScene hs;
+    std::string err;
+    int rc = FlattenScene(desc, &hs, &err);
+    if (rc != 0) return set_error(nullptr, rc, "%s", err.c_str());
+    const void* src = nullptr;
+    long long words = 0;
+    switch (what) {
+    case 0: src = hs.nodes.data(); words = (long long)hs.nodes.size() * 4; break;
+    case 1: src = hs.slots.data(); words = (long long)hs.slots.size() * 4; break;
+    case 2: src = hs.slot_nrm.data(); words = (long long)hs.slot_nrm.size() * 4; break;
+    case 3: src = hs.slot_ml.data(); words = (long long)hs.slot_ml.size() * 2; break;
+    case 4: src = hs.prim_slot.data(); words = (long long)hs.prim_slot.size(); break;
+    case 5: src = hs.materials.data(); words = (long long)hs.materials.size() * 4; break;
+    case 6: src = hs.lights.data(); words = (long long)hs.lights.size() * 4; break;
+    default: return set_error(nullptr, JPBRT_ERR_INVALID, "unknown table %d", what);
+    }
+    if (out && capacity > 0) memcpy(out, src, (size_t)std::min(words, capacity) * 4);
+    return words;
+}
+
 const char* jpbrt_version(void) { return "jet-pbrt_b200 0.1 (sm_100a wavefront path tracer)"; }
 
 const char* jpbrt_last_error(const jpbrt_ctx* ctx) { return ctx ? ctx->error.c_str() : g_last_error.c_str(); }
@@ -247,6 +283,8 @@ int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out
         (e = c->inf_lights.Alloc(hs.inf_lights.size())) != cudaSuccess || (e = c->prim_slot.Alloc(hs.prim_slot.size())) != cudaSuccess ||
         (e = c->film.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess || (e = c->dstats.Alloc(ST_COUNT)) != cudaSuccess)
         return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)));
+    pin_vector(c, hs.nodes); pin_vector(c, hs.slots); pin_vector(c, hs.slot_nrm); pin_vector(c, hs.slot_ml);
+    pin_vector(c, hs.materials); pin_vector(c, hs.lights); pin_vector(c, hs.inf_lights); pin_vector(c, hs.prim_slot);
     rc = upload_arrays(c, nullptr);
     if (rc != 0) { g_last_error = c->error; return fail(rc); }
     DevScene& d = c->dsc;
@@ -276,6 +314,7 @@ int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out
     c->grid_connect_c = occupancy_grid(c, k_connect<true>);
     c->grid_finalize = occupancy_grid(c, k_finalize);
     rc = jpbrt_clear_film(c);
+    if (rc == 0) rc = jpbrt_reset_stats(c);
     if (rc != 0) { g_last_error = c->error; return fail(rc); }
     if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess)
         return fail(set_error(nullptr, JPBRT_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e)));
@@ -293,6 +332,14 @@ int jpbrt_clear_film(jpbrt_ctx* c) {
     if (!c) return set_error(nullptr, JPBRT_ERR_INVALID, "ctx is null");
     CU_CHECK(c, cudaSetDevice(c->device));
     CU_CHECK(c, cudaMemsetAsync(c->film.ptr, 0, c->film.count * sizeof(float), c->stream));
+    return 0;
+}
+
+int jpbrt_reset_stats(jpbrt_ctx* c) {
+    if (!c) return set_error(nullptr, JPBRT_ERR_INVALID, "ctx is null");
+    CU_CHECK(c, cudaSetDevice(c->device));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    drain_events(c);
     CU_CHECK(c, cudaMemsetAsync(c->dstats.ptr, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
     c->kernel_launches = 0;
     for (double& m : c->ms_stage) m = 0;
@@ -436,6 +483,7 @@ void jpbrt_destroy(jpbrt_ctx* c) {
     for (auto& ev : c->pending_events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto& ev : c->free_events) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
+    for (void* p : c->pinned) cudaHostUnregister(p);
     delete c;
 }
 

@@ -1,0 +1,101 @@
+"""Shared input generators for the parity tests (ray sets A/B/C, BSDF set)."""
+import numpy as np
+
+
+def unit_vectors(rng, n):
+    v = rng.normal(size=(n, 3))
+    return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), 1e-30)
+
+
+def make_rays(o, d, tmin=0.001, tmax=np.inf):
+    n = len(o)
+    return np.concatenate([o, d, np.full((n, 1), tmin), np.full((n, 1), tmax)], axis=1).astype(np.float32)
+
+
+def camera_rays(scene_oracle, rng, n, width, height):
+    """Set A: camera rays with random film jitter."""
+    pf = np.stack([rng.uniform(0, width, n), rng.uniform(0, height, n)], 1).astype(np.float32)
+    o, d = scene_oracle.generate_rays(pf)
+    return make_rays(o, d), pf
+
+
+def secondary_rays(scene_oracle, rays, rng):
+    """Set B: origins ON surfaces (closest hits of `rays`), uniform random directions: exercises tmin."""
+    prim, t, pos, nrm = scene_oracle.intersect(rays)
+    m = prim >= 0
+    P, N = pos[m], nrm[m]
+    d = unit_vectors(rng, len(P))
+    return make_rays(P, d), P, N
+
+
+def bbox_rays(info7, rng, n):
+    """Set C: uniform origins in the (slightly enlarged) world box, uniform directions."""
+    lo, hi = info7[:3], info7[3:6]
+    c, e = 0.5 * (lo + hi), 0.5 * (hi - lo) * 1.2 + 1.0
+    o = (c + rng.uniform(-1, 1, (n, 3)) * e).astype(np.float32)
+    return make_rays(o, unit_vectors(rng, n))
+
+
+def bsdf_inputs(rng, n):
+    """BSDF set: wo, wi uniform on the sphere (both hemispheres) plus exact-axis and grazing strata."""
+    nrm = unit_vectors(rng, n)
+    wo = unit_vectors(rng, n)
+    wi = unit_vectors(rng, n)
+    k = n // 16
+    nrm[:k] = np.array([0, 0, 1], np.float32)          # exact axes
+    nrm[k:2 * k] = np.array([1, 0, 0], np.float32)     # |n.x| > 0.99 branch of FFrame
+    wo[2 * k:3 * k] = nrm[2 * k:3 * k]                 # normal incidence (TrowbridgeReitzSample11 special case)
+    # grazing wo: almost perpendicular to n
+    g = slice(3 * k, 4 * k)
+    t = np.cross(nrm[g], unit_vectors(rng, k))
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    wo[g] = (t + 1e-4 * nrm[g]).astype(np.float32)
+    wo[g] /= np.linalg.norm(wo[g], axis=1, keepdims=True)
+    u2 = rng.uniform(0, 1, (n, 2)).astype(np.float32)
+    ul = rng.uniform(0, 1, n).astype(np.float32)
+    return nrm, wo.astype(np.float32), wi, u2, ul
+
+
+def materials(pkg):
+    M = pkg.Material
+    return {
+        "matte": M(pkg.MAT_MATTE, 0, (0.5, 0.4, 0.3), (0, 0, 0), 0, 0),
+        "mirror": M(pkg.MAT_MIRROR, 0, (0.9, 0.8, 0.7), (0, 0, 0), 0, 0),
+        "glass": M(pkg.MAT_GLASS, 0, (0.98, 0.98, 0.98), (0.98, 0.98, 0.98), 1.5, 0),
+        "plastic": M(pkg.MAT_PLASTIC, 0, (0.35, 0.12, 0.48), (0.65, 0.88, 0.52), 0.1, 0),
+        "plastic_remap": M(pkg.MAT_PLASTIC, 1, (0.3, 0.3, 0.32), (0.7, 0.7, 0.68), 0.3, 0),
+        "metal": M(pkg.MAT_METAL, 0, (0.18, 0.15, 0.81), (0.11, 0.11, 0.11), 0.2, 0.2),
+        "metal_aniso_remap": M(pkg.MAT_METAL, 1, (0.2, 0.92, 1.1), (3.9, 2.45, 2.14), 0.4, 0.1),
+    }
+
+
+def shapes(pkg):
+    S = pkg.Shape
+
+    def mk(t, flip, pts):
+        p = [list(map(float, q)) for q in pts] + [[0.0, 0.0, 0.0]] * (4 - len(pts))
+        return S(t, flip, tuple(tuple(q) for q in p))
+
+    return {
+        "tri": mk(pkg.SHAPE_TRIANGLE, 0, [(0, 0, 0), (1, 0, 0), (0, 1, 0)]),
+        "tri_flip_big": mk(pkg.SHAPE_TRIANGLE, 1, [(343, 548.7, -227), (343, 548.7, -332), (213, 548.7, -332)]),
+        "rect": mk(pkg.SHAPE_RECTANGLE, 0, [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0)]),
+        "rect_xz_flip": mk(pkg.SHAPE_RECTANGLE, 1, [(-100, 350, -100), (-100, 350, 100), (100, 350, 100), (100, 350, -100)]),
+        "sphere": mk(pkg.SHAPE_SPHERE, 0, [(0.5, -0.25, 2.0), (1.5, 0, 0)]),
+        "disk": mk(pkg.SHAPE_DISK, 0, [(0.2, 0.1, -0.3), (0.3, 1.0, -0.2), (0.8, 0, 0)]),
+    }
+
+
+def shape_rays(rng, n, center, radius):
+    """Rays aimed near a shape: origins on a shell around it, targets jittered around it (hits, misses, grazing)."""
+    o = (center + unit_vectors(rng, n) * radius * rng.uniform(0.2, 6, (n, 1))).astype(np.float32)
+    tgt = center + rng.normal(size=(n, 3)) * radius * 0.8
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return make_rays(o, d.astype(np.float32))

@@ -1,0 +1,111 @@
+"""Host logic of jpbrt_upload_scene without a GPU: the flattened BVH and tables (csrc/scene_flatten.cc)."""
+import numpy as np
+import pytest
+
+
+def decode(pkg, sc):
+    nodes = pkg.debug_flatten(sc, "nodes").reshape(-1, 16)
+    refs = nodes[:, 12:14].copy().view(np.int32)
+    slots = pkg.debug_flatten(sc, "slots").reshape(-1, 4, 4)
+    nrm = pkg.debug_flatten(sc, "slot_nrm").reshape(-1, 4)
+    return nodes, refs, slots, nrm
+
+
+def slot_bounds(slots, nrm):
+    """Axis-aligned bounds of every slot's geometry, from the slot records themselves."""
+    tag = nrm[:, 3].copy().view(np.int32)
+    typ = tag & 3
+    n = len(slots)
+    lo = np.empty((n, 3)); hi = np.empty((n, 3))
+    for i in range(n):
+        q = slots[i]
+        if typ[i] == 0:
+            p = q[:3, :3]
+        elif typ[i] == 1:
+            p = q[:4, :3]
+        elif typ[i] == 2:
+            r = q[1, 0]
+            p = np.stack([q[0, :3] - r, q[0, :3] + r])
+        else:
+            r = q[1, 3]
+            p = np.stack([q[0, :3] - r, q[0, :3] + r])
+        lo[i], hi[i] = p.min(0), p.max(0)
+    return lo, hi, tag >> 2
+
+
+@pytest.mark.parametrize("name,scale", [("cornell", 1.0), ("bunny", 0.3), ("glossy", 1.0), ("large", 0.03)])
+def test_bvh_is_a_partition_with_containing_boxes(pkg, name, scale):
+    sc = pkg.HostScene.builtin(name, 32, 32, scale)
+    nodes, refs, slots, nrm = decode(pkg, sc)
+    n_prims = sc.d.n_primitives
+    assert len(slots) == n_prims == len(nrm)
+    lo, hi, prim_of_slot = slot_bounds(slots, nrm)
+    assert sorted(prim_of_slot.tolist()) == list(range(n_prims))  # every primitive in exactly one slot
+    prim_slot = pkg.debug_flatten(sc, "prim_slot")
+    assert np.array_equal(prim_of_slot[prim_slot], np.arange(n_prims))
+    seen = np.zeros(n_prims, int)
+    visited = np.zeros(len(nodes), int)
+
+    def walk(ref, blo, bhi, depth):
+        assert depth < 64, "tree deeper than the traversal stack"
+        if ref < 0:
+            bits = ~ref
+            first, cnt = bits >> 4, bits & 15
+            assert cnt <= 4
+            for s in range(first, first + cnt):
+                seen[s] += 1
+                assert (lo[s] >= blo - 1e-6).all() and (hi[s] <= bhi + 1e-6).all(), "leaf box does not contain its primitive"
+            return (lo[first:first + cnt].min(0), hi[first:first + cnt].max(0)) if cnt else (blo, bhi)
+        visited[ref] += 1
+        nd = nodes[ref]
+        lmin, lmax = nd[[0, 1, 2]], nd[[3, 4, 5]]
+        rmin, rmax = nd[[6, 7, 8]], nd[[9, 10, 11]]
+        for (cmin, cmax) in ((lmin, lmax), (rmin, rmax)):
+            if np.isfinite(cmin).all():
+                assert (cmin >= blo - 1e-6).all() and (cmax <= bhi + 1e-6).all(), "child box escapes its parent"
+        walk(int(refs[ref, 0]), lmin, lmax, depth + 1)
+        walk(int(refs[ref, 1]), rmin, rmax, depth + 1)
+
+    import sys
+    sys.setrecursionlimit(10000)
+    big = np.full(3, 1e30)
+    walk(0, -big, big, 0)
+    assert (seen == 1).all(), "a primitive is missing from, or duplicated in, the leaves"
+    assert (visited == 1).all(), "an inner node is unreachable or shared"
+
+
+def test_single_primitive_scene_gets_a_wrapped_root(pkg):
+    cam = pkg.Camera((0, 0, 5), (0, 0, -1), (0, 1, 0), 60.0, 8, 8)
+    sh = pkg.Shape(pkg.SHAPE_SPHERE, 0, ((0, 0, 0), (1, 0, 0), (0, 0, 0), (0, 0, 0)))
+    sc = pkg.HostScene.from_arrays(cam, [sh], [pkg.Material(pkg.MAT_MATTE, 0, (.5, .5, .5), (0, 0, 0), 0, 0)],
+                                   [pkg.Light(pkg.LIGHT_ENVIRONMENT, -1, (1, 1, 1), (0, 0, 0), (0, 0, 0))],
+                                   [pkg.Primitive(0, 0, -1)])
+    nodes, refs, slots, nrm = decode(pkg, sc)
+    assert len(nodes) == 1 and refs[0, 0] == ~((0 << 4) | 1) and refs[0, 1] == ~0
+    assert np.isinf(nodes[0, 6:12]).all()  # the empty right box can never be hit
+
+
+def test_material_and_light_tables(pkg, port):
+    sc = pkg.HostScene.builtin("bunny", 16, 16, 0.1)
+    mats = pkg.debug_flatten(sc, "materials").reshape(-1, 3, 4)
+    d = sc.d
+    for i in range(d.n_materials):
+        m = d.materials[i]
+        assert mats[i, 0, 3:4].copy().view(np.int32)[0] == m.type
+        if m.type == pkg.MAT_PLASTIC:  # material.h:94-98: Qd = lum(Kd) / (lum(Kd) + lum(Ks))
+            f = np.float32
+            lum = lambda c: f(0.212671) * f(c[0]) + f(0.715160) * f(c[1]) + f(0.072169) * f(c[2])  # noqa: E731
+            Ld, Ls = lum(m.a), lum(m.b)
+            Qd = Ld / (Ld + Ls)
+            assert mats[i, 2, 1] == Qd
+            assert np.array_equal(mats[i, 0, :3], np.array(list(m.a), np.float32) / Qd)
+            assert np.array_equal(mats[i, 1, :3], np.array(list(m.b), np.float32) / (f(1) - Qd))
+            assert mats[i, 1, 3] == np.float32(0.1)
+    lights = pkg.debug_flatten(sc, "lights").reshape(-1, 6, 4)
+    tag = lights[1, 0, 3:4].copy().view(np.int32)[0]
+    assert tag & 0xff == pkg.LIGHT_AREA and tag >> 8 == pkg.SHAPE_RECTANGLE
+    assert lights[1, 1, 3] == np.float32(1) / np.float32(200 * 200)  # 1 / Area() of the 200 x 200 light (shape.h:457)
+    assert np.array_equal(lights[1, 4, :3], np.array([0, -1, 0], np.float32))  # flipped normal faces down
+    # environment radius equals the oracle's (light.cc:26-33)
+    info = port.scene(sc).info()
+    assert info[6] > 0
