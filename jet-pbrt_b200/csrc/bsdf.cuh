@@ -149,12 +149,18 @@ __device__ __forceinline__ float tr_pdf(float ax, float ay, const f3& wo, const 
 
 // TrowbridgeReitzSample11, microfacet.cc:256-303.  The reference's normal-incidence branch compares
 // against a double literal and calls the double-precision ::cos/::sin; both are kept.
+// The normal-incidence branch in double precision, out of line: it is taken for < 1 % of the samples but
+// its two double-precision trigonometric expansions are several hundred instructions.
+__device__ __noinline__ void tr_sample11_normal_incidence(float U1, float U2, float* slope_x, float* slope_y) {
+    float r = sqrtf(U1 / (1 - U1));
+    float phi = 6.28318530718f * U2;
+    *slope_x = (float)((double)r * cos((double)phi));
+    *slope_y = (float)((double)r * sin((double)phi));
+}
+
 __device__ __forceinline__ void tr_sample11(float cosTheta, float U1, float U2, float* slope_x, float* slope_y) {
     if ((double)cosTheta > .9999) {
-        float r = sqrtf(U1 / (1 - U1));
-        float phi = 6.28318530718f * U2;
-        *slope_x = (float)((double)r * cos((double)phi));
-        *slope_y = (float)((double)r * sin((double)phi));
+        tr_sample11_normal_incidence(U1, U2, slope_x, slope_y);
         return;
     }
     float sinTheta = sqrtf(std_max(0.f, 1.f - cosTheta * cosTheta));
@@ -201,8 +207,8 @@ __device__ __forceinline__ void concentric_disk_sample(float ux, float uy, float
     float radius, theta;
     if (fabsf(ux) > fabsf(uy)) { radius = ux; theta = JPB_PI_OVER_4 * (uy / ux); }
     else { radius = uy; theta = JPB_PI_OVER_2 - JPB_PI_OVER_4 * (ux / uy); }
-    *px = cosf(theta) * radius;
-    *py = sinf(theta) * radius;
+    *px = jp_cosf(theta) * radius;
+    *py = jp_sinf(theta) * radius;
 }
 __device__ __forceinline__ f3 cosine_hemisphere_sample(float ux, float uy) {
     float px, py;
@@ -217,20 +223,26 @@ __device__ __forceinline__ f3 bsdf_fresnel(const Bsdf& b, float cosI) {  // bsdf
     return splat(fresnel_dielectric(cosI, b.eta_i, b.eta_t));
 }
 
+// FMicrofacetReflection::Evalf_Local, bsdf.cc:35-50.  Out of line: it is needed by NEE and by Sample_Local.
+template <bool CONDUCTOR>
+__device__ __noinline__ f3 microfacet_eval(const Bsdf& b, const f3& wo, const f3& wi) {
+    float cosO = fabsf(wo.z), cosI = fabsf(wi.z);
+    f3 wh = wi + wo;
+    if (cosI == 0 || cosO == 0) return mk3(0, 0, 0);
+    if (wh.x == 0 && wh.y == 0 && wh.z == 0) return mk3(0, 0, 0);
+    wh = normalize(wh);
+    const float cosF = dot(wi, face_forward(wh, mk3(0, 0, 1)));
+    f3 F = CONDUCTOR ? fresnel_conductor(fabsf(cosF), b.eta3, b.T) : splat(fresnel_dielectric(cosF, b.eta_i, b.eta_t));  // bsdf.cc:15-24
+    return cmul(b.R * tr_D(b.ax, b.ay, wh) * tr_G(b.ax, b.ay, wo, wi), F) / (4 * cosI * cosO);
+}
+
 __device__ __forceinline__ f3 bsdf_eval_local(const Bsdf& b, const f3& wo, const f3& wi) {
     if (b.kind == K_LAMBERT) {  // bsdf.h:347-355
         if (!same_hemisphere(wo, wi)) return mk3(0, 0, 0);
         return b.R * JPB_INV_PI;
     }
-    if (b.kind >= K_MICROFACET_CONDUCTOR) {  // bsdf.cc:35-50
-        float cosO = fabsf(wo.z), cosI = fabsf(wi.z);
-        f3 wh = wi + wo;
-        if (cosI == 0 || cosO == 0) return mk3(0, 0, 0);
-        if (wh.x == 0 && wh.y == 0 && wh.z == 0) return mk3(0, 0, 0);
-        wh = normalize(wh);
-        f3 F = bsdf_fresnel(b, dot(wi, face_forward(wh, mk3(0, 0, 1))));
-        return cmul(b.R * tr_D(b.ax, b.ay, wh) * tr_G(b.ax, b.ay, wo, wi), F) / (4 * cosI * cosO);
-    }
+    if (b.kind == K_MICROFACET_CONDUCTOR) return microfacet_eval<true>(b, wo, wi);
+    if (b.kind == K_MICROFACET_DIELECTRIC) return microfacet_eval<false>(b, wo, wi);
     return mk3(0, 0, 0);  // delta BSDFs, bsdf.h:405-408,468-471
 }
 

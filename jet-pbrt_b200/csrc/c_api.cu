@@ -66,14 +66,15 @@ struct jpbrt_ctx {
     std::string error;
     HostScene hs;
     // scene on the device
-    DevBuf<Float4> nodes, slots, slot_nrm, materials, lights;
+    DevBuf<Float4> nodes, slots, slot_nrm, materials, lights, slot_frame;
     DevBuf<Int2> slot_ml;
-    DevBuf<int> inf_lights, prim_slot;
+    DevBuf<int> inf_lights, prim_slot, nee_lights;
     DevScene dsc{};
     // wavefront state
     long long paths_in_flight = 0;  // capacity of the path pool
     DevBuf<float4> ray_o[2], ray_d[2], ray_b[2], sh_o, sh_d, sh_c;
     DevBuf<float2> hit;
+    DevBuf<int> kind_queue;
     DevBuf<int> counters;
     int counter_stride = 0;
     int n_iters = 0;
@@ -83,8 +84,10 @@ struct jpbrt_ctx {
     long long opt_paths_in_flight = 0;
     bool opt_stage_timing = false;
     bool opt_count_traversal = false;
+    int opt_refill_min = 8;
+    unsigned kinds_present = 0;  // bit k set: some material of the scene can build BSDF kind k
     // launch geometry
-    int grid_generate = 0, grid_extend = 0, grid_extend_c = 0, grid_shade = 0, grid_connect = 0, grid_connect_c = 0, grid_finalize = 0;
+    int grid_generate = 0, grid_extend = 0, grid_extend_c = 0, grid_logic = 0, grid_shade[4] = {0, 0, 0, 0}, grid_connect = 0, grid_connect_c = 0, grid_finalize = 0;
     // host-side accounting
     unsigned long long kernel_launches = 0;
     double ms_stage[5] = {0, 0, 0, 0, 0};
@@ -171,6 +174,8 @@ int upload_arrays(jpbrt_ctx* c, size_t* bytes) {
     CU_CHECK(c, c->lights.Upload(hs.lights.data(), hs.lights.size(), c->stream));
     CU_CHECK(c, c->inf_lights.Upload(hs.inf_lights.data(), hs.inf_lights.size(), c->stream));
     CU_CHECK(c, c->prim_slot.Upload(hs.prim_slot.data(), hs.prim_slot.size(), c->stream));
+    CU_CHECK(c, c->slot_frame.Upload(hs.slot_frame.data(), hs.slot_frame.size(), c->stream));
+    CU_CHECK(c, c->nee_lights.Upload(hs.nee_lights.data(), hs.nee_lights.size(), c->stream));
     if (bytes) *bytes = hs.Bytes();
     return 0;
 }
@@ -197,6 +202,7 @@ int ensure_pool(jpbrt_ctx* c) {
         CU_CHECK(c, c->ray_b[b].Alloc(cap));
     }
     CU_CHECK(c, c->hit.Alloc(cap));
+    CU_CHECK(c, c->kind_queue.Alloc((size_t)cap * NUM_KINDS));
     CU_CHECK(c, c->sh_o.Alloc(shadow_cap));
     CU_CHECK(c, c->sh_d.Alloc(shadow_cap));
     CU_CHECK(c, c->sh_c.Alloc(shadow_cap));
@@ -209,6 +215,8 @@ WfParams make_params(jpbrt_ctx* c, int sample_begin, uint64_t seed) {
     p.sc = c->dsc;
     for (int b = 0; b < 2; ++b) { p.ray_o[b] = c->ray_o[b].ptr; p.ray_d[b] = c->ray_d[b].ptr; p.ray_b[b] = c->ray_b[b].ptr; }
     p.hit = c->hit.ptr;
+    p.kind_queue = c->kind_queue.ptr;
+    p.queue_capacity = (int)c->paths_in_flight;
     p.sh_o = c->sh_o.ptr;
     p.sh_d = c->sh_d.ptr;
     p.sh_c = c->sh_c.ptr;
@@ -222,6 +230,7 @@ WfParams make_params(jpbrt_ctx* c, int sample_begin, uint64_t seed) {
     p.npix = c->hs.width * c->hs.height;
     p.blocks_per_bounce = rng_blocks_per_bounce(c->dsc.n_lights);
     p.shadow_capacity = (int)std::min<size_t>(c->sh_o.count, 0x7fffffff);
+    p.refill_min = c->opt_refill_min;
     return p;
 }
 
@@ -281,15 +290,19 @@ int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out
         (e = c->slot_nrm.Alloc(hs.slot_nrm.size())) != cudaSuccess || (e = c->slot_ml.Alloc(hs.slot_ml.size())) != cudaSuccess ||
         (e = c->materials.Alloc(hs.materials.size())) != cudaSuccess || (e = c->lights.Alloc(hs.lights.size())) != cudaSuccess ||
         (e = c->inf_lights.Alloc(hs.inf_lights.size())) != cudaSuccess || (e = c->prim_slot.Alloc(hs.prim_slot.size())) != cudaSuccess ||
+        (e = c->slot_frame.Alloc(hs.slot_frame.size())) != cudaSuccess || (e = c->nee_lights.Alloc(hs.nee_lights.size())) != cudaSuccess ||
         (e = c->film.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess || (e = c->dstats.Alloc(ST_COUNT)) != cudaSuccess)
         return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)));
     pin_vector(c, hs.nodes); pin_vector(c, hs.slots); pin_vector(c, hs.slot_nrm); pin_vector(c, hs.slot_ml);
     pin_vector(c, hs.materials); pin_vector(c, hs.lights); pin_vector(c, hs.inf_lights); pin_vector(c, hs.prim_slot);
+    pin_vector(c, hs.slot_frame); pin_vector(c, hs.nee_lights);
     rc = upload_arrays(c, nullptr);
     if (rc != 0) { g_last_error = c->error; return fail(rc); }
     DevScene& d = c->dsc;
     d.nodes = c->nodes.ptr; d.slots = c->slots.ptr; d.slot_nrm = c->slot_nrm.ptr; d.slot_ml = c->slot_ml.ptr;
     d.materials = c->materials.ptr; d.lights = c->lights.ptr; d.inf_lights = c->inf_lights.ptr; d.prim_slot = c->prim_slot.ptr;
+    d.slot_frame = c->slot_frame.ptr; d.nee_lights = c->nee_lights.ptr;
+    d.n_nee_lights = (int)hs.nee_lights.size();
     d.n_nodes = (int)(hs.nodes.size() / kNodeStride);
     d.n_slots = (int)hs.slot_nrm.size();
     d.n_materials = (int)(hs.materials.size() / kMaterialStride);
@@ -301,6 +314,11 @@ int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out
     d.height = hs.height;
     d.world_radius = hs.world_radius;
     d.cam = hs.cam;
+    for (size_t m = 0; m < hs.materials.size() / kMaterialStride; ++m) {
+        int type;
+        memcpy(&type, &hs.materials[m * kMaterialStride].w, 4);
+        c->kinds_present |= type == JPBRT_MAT_MATTE ? 1u : type == JPBRT_MAT_METAL ? 2u : type == JPBRT_MAT_PLASTIC ? (1u | 4u) : 8u;
+    }
     // iterations: bounces 0..max_depth, plus slack for null-material pass-through vertices
     c->n_iters = hs.max_depth + 1 + (hs.has_null_material ? 16 : 0);
     c->counter_stride = c->n_iters + 2;
@@ -309,7 +327,11 @@ int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out
     c->grid_generate = occupancy_grid(c, k_generate);
     c->grid_extend = occupancy_grid(c, k_extend<false>);
     c->grid_extend_c = occupancy_grid(c, k_extend<true>);
-    c->grid_shade = occupancy_grid(c, k_shade);
+    c->grid_logic = occupancy_grid(c, k_logic);
+    c->grid_shade[0] = occupancy_grid(c, k_shade<0>);
+    c->grid_shade[1] = occupancy_grid(c, k_shade<1>);
+    c->grid_shade[2] = occupancy_grid(c, k_shade<2>);
+    c->grid_shade[3] = occupancy_grid(c, k_shade<3>);
     c->grid_connect = occupancy_grid(c, k_connect<false>);
     c->grid_connect_c = occupancy_grid(c, k_connect<true>);
     c->grid_finalize = occupancy_grid(c, k_finalize);
@@ -351,6 +373,7 @@ int jpbrt_set_option(jpbrt_ctx* c, const char* name, long long value) {
     if (!strcmp(name, "paths_in_flight")) { c->opt_paths_in_flight = value; return 0; }
     if (!strcmp(name, "stage_timing")) { c->opt_stage_timing = value != 0; return 0; }
     if (!strcmp(name, "count_traversal")) { c->opt_count_traversal = value != 0; return 0; }
+    if (!strcmp(name, "refill_min")) { c->opt_refill_min = (int)std::max(1ll, std::min(32ll, value)); return 0; }
     return set_error(c, JPBRT_ERR_INVALID, "unknown option '%s'", name);
 }
 
@@ -383,7 +406,14 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
             }
             {
                 StageTimer t(c, 2);
-                k_shade<<<c->grid_shade, kBlock, 0, c->stream>>>(p, it);
+                k_logic<<<c->grid_logic, kBlock, 0, c->stream>>>(p, it);
+                if (it < c->n_iters - 1 || c->hs.has_null_material) {  // at bounce == maxDepth nothing is left to shade
+                    if (c->kinds_present & 1) k_shade<0><<<c->grid_shade[0], kBlock, 0, c->stream>>>(p, it);
+                    if (c->kinds_present & 2) k_shade<1><<<c->grid_shade[1], kBlock, 0, c->stream>>>(p, it);
+                    if (c->kinds_present & 4) k_shade<2><<<c->grid_shade[2], kBlock, 0, c->stream>>>(p, it);
+                    if (c->kinds_present & 8) k_shade<3><<<c->grid_shade[3], kBlock, 0, c->stream>>>(p, it);
+                    c->kernel_launches += __builtin_popcount(c->kinds_present);
+                }
                 c->kernel_launches++;
             }
             if (it < c->n_iters - 1 || c->hs.has_null_material) {  // no NEE at bounce == maxDepth (integrator.cc:340)
@@ -534,38 +564,64 @@ __global__ void k_unit_intersect_shape(DevScene sc, int n, const float* rays8, i
     }
 }
 
-__global__ void k_unit_scene_intersect(DevScene sc, int n, const float* rays8, int* prim, float* t, float* pos3, float* nrm3) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float* q = rays8 + 8 * i;
+// The unit entry points run the SAME warp-cooperative traversal as k_extend / k_connect.
+struct UnitRayIO {
+    const float* rays8;
+    int* prim;
+    float* t;
+    float* pos3;
+    float* nrm3;
+    const DevScene* sc;
+    __device__ __forceinline__ void load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
+        const float* q = rays8 + 8 * (size_t)i;
+        o = mk3(q[0], q[1], q[2]);
+        d = mk3(q[3], q[4], q[5]);
+        tmin = q[6];
+        tmax = q[7];
+    }
+    __device__ __forceinline__ void store(int i, int slot, float tmax) const {
+        const float* q = rays8 + 8 * (size_t)i;
         const f3 o = mk3(q[0], q[1], q[2]), d = mk3(q[3], q[4], q[5]);
-        float tmax = q[7];
-        unsigned a = 0, b = 0;
-        int slot = traverse<false, false>(sc, o, d, q[6], tmax, a, b);
         f3 P = mk3(0, 0, 0), N = mk3(0, 0, 0);
         int pi = -1;
         if (slot >= 0) {
             P = o + tmax * d;
-            N = hit_normal(sc, slot, P, d);
-            pi = __float_as_int(ldg4(sc.slot_nrm + slot).w) >> kTypeBits;
+            N = hit_normal(*sc, slot, P, d);
+            pi = __float_as_int(ldg4(sc->slot_nrm + slot).w) >> kTypeBits;
         }
         prim[i] = pi;
         t[i] = slot >= 0 ? tmax : 0.f;
         if (pos3) st3(pos3, i, P);
         if (nrm3) st3(nrm3, i, N);
     }
+};
+
+__global__ void __launch_bounds__(kBlock) k_unit_scene_intersect(DevScene sc, int n, int* work, const float* rays8, int* prim, float* t, float* pos3, float* nrm3) {
+    unsigned a = 0, b = 0;
+    UnitRayIO io{rays8, prim, t, pos3, nrm3, &sc};
+    traverse_queue<false, false>(sc, n, work, io, 8, a, b);
 }
 
-__global__ void k_unit_scene_occluded(DevScene sc, int n, const float* pos3, const float* target3, int* occ) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+struct UnitOccIO {
+    const float* pos3;
+    const float* target3;
+    int* occ;
+    __device__ __forceinline__ void load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
         const f3 P = ld3(pos3, i), T = ld3(target3, i);
         const f3 v = T - P;  // scene.h:44-47: Normalize(target - pos), Distance(pos, target)
         const float dist = length(v);
-        const f3 d = v / dist;
-        float tmax = dist - 0.001f;
-        unsigned a = 0, b = 0;
-        int slot = traverse<true, false>(sc, P, d, JPBRT_RAY_TMIN, tmax, a, b);
-        occ[i] = slot >= 0 ? 1 : 0;
+        o = P;
+        d = v / dist;
+        tmin = JPBRT_RAY_TMIN;
+        tmax = dist - 0.001f;
     }
+    __device__ __forceinline__ void store(int i, int slot, float) const { occ[i] = slot >= 0 ? 1 : 0; }
+};
+
+__global__ void __launch_bounds__(kBlock) k_unit_scene_occluded(DevScene sc, int n, int* work, const float* pos3, const float* target3, int* occ) {
+    unsigned a = 0, b = 0;
+    UnitOccIO io{pos3, target3, occ};
+    traverse_queue<true, false>(sc, n, work, io, 8, a, b);
 }
 
 __global__ void k_unit_bsdf(const Float4* mat, int n, const float* nrm3, const float* wo3, const float* wi3, const float* u2,
@@ -702,7 +758,9 @@ int jpbrt_unit_scene_intersect(jpbrt_ctx* c, int n, const float* rays8, int* pri
     float* d_t = a.Out<float>(n);
     float* d_pos = pos3 ? a.Out<float>((size_t)n * 3) : nullptr;
     float* d_nrm = nrm3 ? a.Out<float>((size_t)n * 3) : nullptr;
-    if (a.err == cudaSuccess && n > 0) k_unit_scene_intersect<<<unit_grid(n), kBlock>>>(c->dsc, n, d_rays, d_prim, d_t, d_pos, d_nrm);
+    int* d_work = a.Out<int>(1);
+    if (a.err == cudaSuccess) a.err = cudaMemset(d_work, 0, sizeof(int));
+    if (a.err == cudaSuccess && n > 0) k_unit_scene_intersect<<<unit_grid(n), kBlock>>>(c->dsc, n, d_work, d_rays, d_prim, d_t, d_pos, d_nrm);
     int rc = finish_unit(c, a);
     if (rc != 0) return rc;
     a.Back(prim, d_prim, n); a.Back(t, d_t, n); a.Back(pos3, d_pos, (size_t)n * 3); a.Back(nrm3, d_nrm, (size_t)n * 3);
@@ -716,7 +774,9 @@ int jpbrt_unit_scene_occluded(jpbrt_ctx* c, int n, const float* pos3, const floa
     const float* d_pos = a.In(pos3, (size_t)n * 3);
     const float* d_tgt = a.In(target3, (size_t)n * 3);
     int* d_occ = a.Out<int>(n);
-    if (a.err == cudaSuccess && n > 0) k_unit_scene_occluded<<<unit_grid(n), kBlock>>>(c->dsc, n, d_pos, d_tgt, d_occ);
+    int* d_work = a.Out<int>(1);
+    if (a.err == cudaSuccess) a.err = cudaMemset(d_work, 0, sizeof(int));
+    if (a.err == cudaSuccess && n > 0) k_unit_scene_occluded<<<unit_grid(n), kBlock>>>(c->dsc, n, d_work, d_pos, d_tgt, d_occ);
     int rc = finish_unit(c, a);
     if (rc != 0) return rc;
     a.Back(occluded, d_occ, n);

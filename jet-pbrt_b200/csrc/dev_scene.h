@@ -7,6 +7,7 @@
 //   slots     4 x float4 / slot  (64 B)  primitive geometry in BVH leaf order
 //   slot_nrm  1 x float4 / slot          stored normal + tag, read on accepted hits and by shade
 //   slot_ml   1 x int2   / slot          (material, light) of the primitive
+//   slot_frame 3 x float4 / slot         the shading frame FFrame(normal) = (s, t, n') of flat shapes
 //   materials 3 x float4 / material
 //   lights    6 x float4 / light
 #pragma once
@@ -41,6 +42,10 @@ constexpr int kMaterialStride = 3;
 //             l2 = (p1, radius)  l3 = (p2, -)  l4 = (stored normal, -)  l5 = spare
 constexpr int kLightStride = 6;
 
+// ---- shading frame of triangles / rectangles / disks, precomputed with FFrame's expressions
+// (geometry.h:344-377): f0 = s, f1 = t, f2 = n' = Normalize(stored normal).  Spheres compute theirs per hit.
+constexpr int kFrameStride = 3;
+
 struct DevCamera {
     float pos[3];
     float front[3];
@@ -60,9 +65,11 @@ struct DevScene {
     const Int2*   slot_ml;
     const Float4* materials;
     const Float4* lights;
+    const Float4* slot_frame;
+    const int*    nee_lights;  // indices of the lights whose colour is not black (the others can never contribute)
     const int*    inf_lights;
     const int*    prim_slot;  // primitive index -> slot
-    int n_nodes, n_slots, n_materials, n_lights, n_inf_lights, n_prims;
+    int n_nodes, n_slots, n_materials, n_lights, n_inf_lights, n_prims, n_nee_lights;
     int max_depth;
     int width, height;
     float world_radius;  // FEnvironmentLight::worldRadius (light.cc:26-33)

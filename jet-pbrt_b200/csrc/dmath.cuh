@@ -61,6 +61,12 @@ __device__ __forceinline__ T clampf(T v, T lo, T hi) {  // pbrt.h:75-83
 #define JPB_PI_OVER_4 (JPB_PI / 4.0f)
 #define JPB_INV_PI (1.0f / JPB_PI)
 
+// sinf / cosf are ~150 SASS instructions each once inlined (range reduction + Payne-Hanek slow path).
+// One shared, out-of-line copy per kernel keeps the material kernels inside the instruction cache
+// (profiles/: k_shade was 63 % stalled on instruction fetch when everything was inlined).
+__device__ __noinline__ float jp_sinf(float x) { return sinf(x); }
+__device__ __noinline__ float jp_cosf(float x) { return cosf(x); }
+
 // FFrame(n): geometry.h:344-377.  n is re-normalised exactly as the reference's ctor does.
 struct Frame {
     f3 s, t, n;

@@ -98,69 +98,157 @@ __device__ __forceinline__ f3 hit_normal(const DevScene& sc, int slot, const f3&
     return n;
 }
 
-constexpr int kTraversalStack = 64;
+// FFrame(isect.normal) (geometry.h:344-377).  For flat shapes it was computed once at upload with the same
+// expressions (slot_frame); a rectangle whose normal was flipped towards the ray gets (s, -t, -n), which is
+// exactly FFrame(-n): cross(-n, tmp) = -t and cross(-t, -n) = s, and negation is exact.
+__device__ __forceinline__ Frame hit_frame(const DevScene& sc, int slot, const f3& N) {
+    const float4 nr = ldg4(sc.slot_nrm + slot);
+    const int type = __float_as_int(nr.w) & ((1 << kTypeBits) - 1);
+    if (type == SHAPE_SPHERE) return make_frame(N);
+    const Float4* fp = sc.slot_frame + (size_t)slot * kFrameStride;
+    Frame f;
+    f.s = mk3(ldg4(fp));
+    f.t = mk3(ldg4(fp + 1));
+    f.n = mk3(ldg4(fp + 2));
+    const bool flipped = (type == SHAPE_RECT) && (N.x != nr.x || N.y != nr.y || N.z != nr.z);
+    if (flipped) { f.t = -f.t; f.n = -f.n; }
+    return f;
+}
 
-// Closest-hit (ANY_HIT = false) or any-hit (ANY_HIT = true) traversal.
-// Returns the hit slot (or -1); tmax is shrunk to the hit distance.
-template <bool ANY_HIT, bool COUNT>
-__device__ __forceinline__ int traverse(const DevScene& sc, const f3& o, const f3& d, float tmin, float& tmax,
-                                        unsigned& n_box, unsigned& n_prim) {
-    const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+constexpr int kTraversalStack = 64;
+constexpr int kTravDone = 0x7fffffff;  // `cur` value of a lane whose stack is empty (or that found an any-hit)
+
+// Per-lane traversal state.  The BVH walk is a state machine so that a warp can (a) run the inner-node
+// step and the leaf step in separate, converged phases (while-while traversal) and (b) hand a finished
+// lane a new ray while the other lanes keep walking (ray replacement) -- see traverse_queue() below.
+struct Trav {
+    f3 o, d, inv, oi;
+    float tmin, tmax;
+    int cur, sp, hit;
+};  // the node stack is a separate local array so that these scalars stay in registers
+
+__device__ __forceinline__ void trav_init(Trav& t, const f3& o, const f3& d, float tmin, float tmax) {
+    t.o = o;
+    t.d = d;
+    t.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    // slab distances as one explicit FMA each: bound * inv - o * inv.  Its rounding error (about one ulp of
+    // |o * inv|) is covered by the padding baked into every stored box (4e-6 * the largest ray-origin
+    // coordinate, scene_flatten.cc) plus the 2*gamma(3) widening of tfar.
+    t.oi = mk3(-(o.x * t.inv.x), -(o.y * t.inv.y), -(o.z * t.inv.z));
+    t.tmin = tmin;
+    t.tmax = tmax;
+    t.cur = 0;  // root (always an inner node, scene_flatten.cc)
+    t.sp = 0;
+    t.hit = -1;
+}
+
+__device__ __forceinline__ bool trav_at_inner(const Trav& t) { return (unsigned)t.cur < (unsigned)kTravDone; }
+__device__ __forceinline__ bool trav_at_leaf(const Trav& t) { return t.cur < 0; }
+__device__ __forceinline__ bool trav_done(const Trav& t) { return t.cur == kTravDone; }
+__device__ __forceinline__ void trav_pop(Trav& t, const int* stack) { t.cur = t.sp ? stack[--t.sp] : kTravDone; }
+
+// One inner node: fetch 64 bytes, test both child boxes, descend into the nearer hit child.
+template <bool COUNT>
+__device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, int* stack, unsigned& n_box) {
     const float widen = 1.0000004f;  // 1 + 2*gamma(3): pbrt's conservative slab bound
-    int stack[kTraversalStack];
-    int sp = 0;
-    int cur = 0;
-    int hit_slot = -1;
-    const Float4* __restrict__ nodes = sc.nodes;
-    for (;;) {
-        if (cur >= 0) {
-            const Float4* np = nodes + (size_t)cur * kNodeStride;
-            const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
-            if (COUNT) n_box += 2;
-            // left box: min = (n0.x n0.y n0.z), max = (n0.w n1.x n1.y)
-            float a0 = (n0.x - o.x) * inv.x, a1 = (n0.w - o.x) * inv.x;
-            float b0 = (n0.y - o.y) * inv.y, b1 = (n1.x - o.y) * inv.y;
-            float c0 = (n0.z - o.z) * inv.z, c1 = (n1.y - o.z) * inv.z;
-            const float ltn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin));
-            const float ltf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tmax));
-            // right box: min = (n1.z n1.w n2.x), max = (n2.y n2.z n2.w)
-            a0 = (n1.z - o.x) * inv.x; a1 = (n2.y - o.x) * inv.x;
-            b0 = (n1.w - o.y) * inv.y; b1 = (n2.z - o.y) * inv.y;
-            c0 = (n2.x - o.z) * inv.z; c1 = (n2.w - o.z) * inv.z;
-            const float rtn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), tmin));
-            const float rtf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tmax));
-            const bool hl = ltn <= ltf * widen;
-            const bool hr = rtn <= rtf * widen;
-            const int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
-            if (hl && hr) {
-                const bool left_first = ltn <= rtn;
-                cur = left_first ? cl : cr;
-                if (sp < kTraversalStack) stack[sp++] = left_first ? cr : cl;
-            } else if (hl) {
-                cur = cl;
-            } else if (hr) {
-                cur = cr;
-            } else {
-                if (sp == 0) break;
-                cur = stack[--sp];
-            }
-        } else {
-            const int bits = ~cur;
-            const int first = bits >> kLeafCountBits;
-            const int cnt = bits & ((1 << kLeafCountBits) - 1);
-            for (int k = 0; k < cnt; ++k) {
-                const int s = first + k;
-                if (COUNT) n_prim += 1;
-                if (intersect_slot(sc.slots + (size_t)s * kSlotStride, sc.slot_nrm + s, o, d, tmin, tmax)) {
-                    hit_slot = s;
-                    if (ANY_HIT) return hit_slot;
-                }
-            }
-            if (sp == 0) break;
-            cur = stack[--sp];
+    const Float4* np = sc.nodes + (size_t)t.cur * kNodeStride;
+    const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
+    if (COUNT) n_box += 2;
+    // left box: min = (n0.x n0.y n0.z), max = (n0.w n1.x n1.y)
+    float a0 = __fmaf_rn(n0.x, t.inv.x, t.oi.x), a1 = __fmaf_rn(n0.w, t.inv.x, t.oi.x);
+    float b0 = __fmaf_rn(n0.y, t.inv.y, t.oi.y), b1 = __fmaf_rn(n1.x, t.inv.y, t.oi.y);
+    float c0 = __fmaf_rn(n0.z, t.inv.z, t.oi.z), c1 = __fmaf_rn(n1.y, t.inv.z, t.oi.z);
+    const float ltn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), t.tmin));
+    const float ltf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), t.tmax));
+    // right box: min = (n1.z n1.w n2.x), max = (n2.y n2.z n2.w)
+    a0 = __fmaf_rn(n1.z, t.inv.x, t.oi.x); a1 = __fmaf_rn(n2.y, t.inv.x, t.oi.x);
+    b0 = __fmaf_rn(n1.w, t.inv.y, t.oi.y); b1 = __fmaf_rn(n2.z, t.inv.y, t.oi.y);
+    c0 = __fmaf_rn(n2.x, t.inv.z, t.oi.z); c1 = __fmaf_rn(n2.w, t.inv.z, t.oi.z);
+    const float rtn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), t.tmin));
+    const float rtf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), t.tmax));
+    const bool hl = ltn <= ltf * widen;
+    const bool hr = rtn <= rtf * widen;
+    const int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
+    if (hl && hr) {
+        const bool left_first = ltn <= rtn;
+        t.cur = left_first ? cl : cr;
+        if (t.sp < kTraversalStack) stack[t.sp++] = left_first ? cr : cl;
+    } else if (hl) {
+        t.cur = cl;
+    } else if (hr) {
+        t.cur = cr;
+    } else {
+        trav_pop(t, stack);
+    }
+}
+
+// One leaf: test its (<= 4) primitives, then pop.
+template <bool ANY_HIT, bool COUNT>
+__device__ __forceinline__ void trav_leaf_step(const DevScene& sc, Trav& t, const int* stack, unsigned& n_prim) {
+    const int bits = ~t.cur;
+    const int first = bits >> kLeafCountBits;
+    const int cnt = bits & ((1 << kLeafCountBits) - 1);
+    for (int k = 0; k < cnt; ++k) {
+        const int s = first + k;
+        if (COUNT) n_prim += 1;
+        if (intersect_slot(sc.slots + (size_t)s * kSlotStride, sc.slot_nrm + s, t.o, t.d, t.tmin, t.tmax)) {
+            t.hit = s;
+            if (ANY_HIT) { t.cur = kTravDone; return; }
         }
     }
-    return hit_slot;
+    trav_pop(t, stack);
+}
+
+// Warp-cooperative traversal of a whole ray queue.
+//   io.load(i, o, d, tmin, tmax)    fetch ray i          io.store(i, slot, t)   deliver its result
+// Every lane owns one ray at a time.  Each trip round the outer loop has three converged phases:
+//   refill : idle lanes take the next rays from the queue (one atomicAdd per warp) once at least
+//            `refill_min` lanes are idle -- finished rays are REPLACED instead of idling until the
+//            slowest ray of the warp is done;
+//   nodes  : lanes at an inner node step until every active lane sits on a leaf (or is done);
+//   leaves : lanes at a leaf test its primitives and pop; finished lanes store their result.
+template <bool ANY_HIT, bool COUNT, typename IO>
+__device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* work, const IO& io, int refill_min,
+                                               unsigned& n_box, unsigned& n_prim) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    Trav t;
+    int stack[kTraversalStack];
+    t.cur = kTravDone;
+    int idx = -1;
+    bool exhausted = false;
+    for (;;) {
+        const unsigned idle = __ballot_sync(full, idx < 0);
+        if (!exhausted && (idle == full || __popc(idle) >= refill_min)) {
+            const int cnt = __popc(idle);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(work, cnt);
+            base = __shfl_sync(full, base, 0);
+            if (idx < 0) {
+                const int i = base + __popc(idle & ((1u << lane) - 1));
+                if (i < n) {
+                    f3 o, d;
+                    float tmin, tmax;
+                    io.load(i, o, d, tmin, tmax);
+                    trav_init(t, o, d, tmin, tmax);
+                    idx = i;
+                }
+            }
+            if (base + cnt >= n) exhausted = true;
+        }
+        if (__ballot_sync(full, idx >= 0) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        while (__any_sync(full, idx >= 0 && trav_at_inner(t))) {
+            if (idx >= 0 && trav_at_inner(t)) trav_node_step<COUNT>(sc, t, stack, n_box);
+        }
+        if (idx >= 0 && trav_at_leaf(t)) trav_leaf_step<ANY_HIT, COUNT>(sc, t, stack, n_prim);
+        if (idx >= 0 && trav_done(t)) {
+            io.store(idx, t.hit, t.tmax);
+            idx = -1;
+        }
+    }
 }
 
 }  // namespace jpbrt

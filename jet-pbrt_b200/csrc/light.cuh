@@ -22,7 +22,7 @@ __device__ __forceinline__ f3 uniform_sphere_sample(float ux, float uy) {  // sa
     float z = 1 - 2 * ux;
     float radius = sqrtf(std_max(0.f, 1.f - z * z));
     float phi = JPB_2PI * uy;
-    return mk3(radius * cosf(phi), radius * sinf(phi), z);
+    return mk3(radius * jp_cosf(phi), radius * jp_sinf(phi), z);
 }
 
 // FAreaLight::L, light.h:234-238
@@ -43,8 +43,8 @@ __device__ __forceinline__ LightSample sample_light(const DevScene& sc, int li, 
     s.pdf = 0.f;
     if (type == LIGHT_ENV) {  // light.h:265-287
         float theta = uy * JPB_PI, phi = ux * 2 * JPB_PI;
-        float cosTheta = cosf(theta), sinTheta = sinf(theta);
-        float sinPhi = sinf(phi), cosPhi = cosf(phi);
+        float cosTheta = jp_cosf(theta), sinTheta = jp_sinf(theta);
+        float sinPhi = jp_sinf(phi), cosPhi = jp_cosf(phi);
         s.wi = mk3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
         s.pos = P + s.wi * 2 * sc.world_radius;
         if (sinTheta != 0) s.pdf = 1 / (2 * JPB_PI * JPB_PI * sinTheta);
@@ -106,7 +106,7 @@ __device__ __forceinline__ LightSample sample_light(const DevScene& sc, int li, 
             float sin_alpha = sqrtf(std_max(0.f, 1.f - cos_alpha * cos_alpha));
             float phi = uy * 2 * JPB_PI;
             Frame fr = make_frame((p0 - P) * inv_dist);
-            f3 wn = (sin_alpha * cosf(phi)) * (-fr.s) + (sin_alpha * sinf(phi)) * (-fr.t) + cos_alpha * (-fr.n);
+            f3 wn = (sin_alpha * jp_cosf(phi)) * (-fr.s) + (sin_alpha * jp_sinf(phi)) * (-fr.t) + cos_alpha * (-fr.n);
             lpos = p0 + radius * wn;
             lnrm = wn;
             pdf = 1 / (2 * JPB_PI * (1 - cos_theta_max));

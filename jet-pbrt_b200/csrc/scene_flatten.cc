@@ -57,11 +57,12 @@ struct Box {
 };
 
 // FFrame(n) tangent vectors (geometry.h:344-377), needed for the disk's bounds (shape.h:239-252).
-void FrameST(const H3& nn, H3* s, H3* t) {
+void FrameST(const H3& nn, H3* s, H3* t, H3* nout = nullptr) {
     H3 n = nn.Normalize();
     H3 tmp = (std::fabs(n.x) > 0.99f) ? H3(0, 1, 0) : H3(1, 0, 0);
     *t = n.Cross(tmp).Normalize();
     *s = t->Cross(n).Normalize();
+    if (nout) *nout = n;
 }
 
 inline float IntAsFloat(int v) { float f; memcpy(&f, &v, 4); return f; }
@@ -370,6 +371,9 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err) {
     hs.lights.assign((size_t)d->n_lights * kLightStride, Float4{0, 0, 0, 0});
     for (int i = 0; i < d->n_lights; ++i) {
         const jpbrt_light& l = d->lights[i];
+        // a light whose colour is black yields Li == black for every sample and is skipped by
+        // integrator.cc:362-364; it keeps its place in the sampler's dimension schedule
+        if (!(l.color[0] == 0.f && l.color[1] == 0.f && l.color[2] == 0.f)) hs.nee_lights.push_back(i);
         Float4* o = &hs.lights[(size_t)i * kLightStride];
         int shape_type = 0;
         switch (l.type) {
@@ -417,6 +421,8 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err) {
     // can report a hit a few ulps outside its own bounds (DESIGN.md "Conservative boxes").
     float maxabs = 0;
     for (int a = 0; a < 3; ++a) maxabs = std::max(maxabs, std::max(std::fabs(world.mn[a]), std::fabs(world.mx[a])));
+    // ray origins are the camera position or points on surfaces: include the camera in the magnitude
+    for (int a = 0; a < 3; ++a) maxabs = std::max(maxabs, std::fabs(d->camera.pos[a]));
     const float pad = 4e-6f * maxabs + 1e-30f;
     int nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
     Builder bld(boxes, nthreads);
@@ -475,8 +481,16 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err) {
     hs.slot_nrm.resize(N);
     hs.slot_ml.resize(N);
     hs.prim_slot.resize(N);
+    hs.slot_frame.assign((size_t)N * kFrameStride, Float4{0, 0, 0, 0});
     for (int s = 0; s < N; ++s) {
         int p = bld.idx[s];
+        if (d->shapes[d->primitives[p].shape].type != JPBRT_SHAPE_SPHERE) {
+            H3 fs, ft, fn;
+            FrameST(H3(pre_nrm[p].x, pre_nrm[p].y, pre_nrm[p].z), &fs, &ft, &fn);
+            hs.slot_frame[(size_t)s * kFrameStride + 0] = Float4{fs.x, fs.y, fs.z, 0};
+            hs.slot_frame[(size_t)s * kFrameStride + 1] = Float4{ft.x, ft.y, ft.z, 0};
+            hs.slot_frame[(size_t)s * kFrameStride + 2] = Float4{fn.x, fn.y, fn.z, 0};
+        }
         for (int k = 0; k < kSlotStride; ++k) hs.slots[(size_t)s * kSlotStride + k] = pre_slots[(size_t)p * kSlotStride + k];
         hs.slot_nrm[s] = pre_nrm[p];
         hs.slot_ml[s] = Int2{d->primitives[p].material, d->primitives[p].light};

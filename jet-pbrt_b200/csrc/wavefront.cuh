@@ -31,7 +31,9 @@
 
 namespace jpbrt {
 
-enum { CNT_RAYS = 0, CNT_SHADOW = 1, CNT_W_EXTEND = 2, CNT_W_SHADE = 3, CNT_W_CONNECT = 4, CNT_KINDS = 5 };
+// per-iteration device counters: queue lengths and the work cursors of the persistent kernels
+enum { CNT_RAYS = 0, CNT_SHADOW = 1, CNT_W_EXTEND = 2, CNT_W_SHADE = 3, CNT_W_CONNECT = 4,
+       CNT_Q0 = 5 /* 4 kinds */, CNT_WQ0 = 9 /* 4 kinds */, CNT_KINDS = 13 };
 enum {
     ST_SAMPLES = 0, ST_EXT_RAYS, ST_SHADOW_RAYS, ST_VERTICES, ST_BOX, ST_PRIM, ST_SH_BOX, ST_SH_PRIM, ST_INVALID, ST_DROPPED, ST_COUNT
 };
@@ -45,6 +47,8 @@ struct WfParams {
     float4* sh_o;
     float4* sh_d;
     float4* sh_c;
+    int* kind_queue;     // [NUM_KINDS][queue_capacity] indices into the current ray buffer
+    int queue_capacity;
     int* counters;  // [CNT_KINDS][counter_stride]
     int counter_stride;
     float* film;
@@ -54,6 +58,7 @@ struct WfParams {
     int npix;
     int blocks_per_bounce;
     int shadow_capacity;
+    int refill_min;  // ray replacement threshold of the traversal kernels (idle lanes per warp)
 };
 
 constexpr int kBlock = 256;
@@ -127,6 +132,19 @@ __global__ void __launch_bounds__(kBlock) k_generate(const __grid_constant__ WfP
 // ---------------------------------------------------------------------------------------------
 // extend: closest hit for every ray of iteration `it`
 // ---------------------------------------------------------------------------------------------
+struct ExtendIO {
+    const float4* ro;
+    const float4* rd;
+    float2* hit;
+    __device__ __forceinline__ void load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
+        o = mk3(ro[i]);
+        d = mk3(rd[i]);
+        tmin = JPBRT_RAY_TMIN;                 // FRay default min_t, geometry.h:395
+        tmax = __int_as_float(0x7f800000);     // kInfinity
+    }
+    __device__ __forceinline__ void store(int i, int slot, float t) const { hit[i] = make_float2(t, __int_as_float(slot)); }
+};
+
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) k_extend(const __grid_constant__ WfParams p, int it) {
     const int n = p.counters[CNT_RAYS * p.counter_stride + it];
@@ -134,18 +152,8 @@ __global__ void __launch_bounds__(kBlock) k_extend(const __grid_constant__ WfPar
     const int buf = it & 1;
     unsigned nb = 0, np = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.stats + ST_EXT_RAYS, (unsigned long long)n);
-    for (;;) {
-        const int base = warp_fetch(work);
-        if (base >= n) break;
-        const int i = base + lane_id();
-        if (i < n) {
-            const float4 ro = p.ray_o[buf][i];
-            const float4 rd = p.ray_d[buf][i];
-            float tmax = __int_as_float(0x7f800000);
-            const int slot = traverse<false, COUNT>(p.sc, mk3(ro), mk3(rd), JPBRT_RAY_TMIN, tmax, nb, np);
-            p.hit[i] = make_float2(tmax, __int_as_float(slot));
-        }
-    }
+    ExtendIO io{p.ray_o[buf], p.ray_d[buf], p.hit};
+    traverse_queue<false, COUNT>(p.sc, n, work, io, p.refill_min, nb, np);
     if (COUNT) {
         warp_stat_add(p.stats + ST_BOX, nb);
         warp_stat_add(p.stats + ST_PRIM, np);
@@ -155,6 +163,20 @@ __global__ void __launch_bounds__(kBlock) k_extend(const __grid_constant__ WfPar
 // ---------------------------------------------------------------------------------------------
 // connect: any-hit for every shadow ray of iteration `it`; unoccluded -> film += contribution
 // ---------------------------------------------------------------------------------------------
+struct ConnectIO {
+    const WfParams* p;
+    __device__ __forceinline__ void load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
+        const float4 so = p->sh_o[i];
+        o = mk3(so);
+        d = mk3(p->sh_d[i]);
+        tmin = JPBRT_RAY_TMIN;  // scene.h:38
+        tmax = so.w;            // dist - 0.001
+    }
+    __device__ __forceinline__ void store(int i, int slot, float) const {
+        if (slot < 0) film_add(*p, __float_as_int(p->sh_d[i].w), mk3(p->sh_c[i]));  // integrator.cc:367-370
+    }
+};
+
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) k_connect(const __grid_constant__ WfParams p, int it) {
     int n = p.counters[CNT_SHADOW * p.counter_stride + it];
@@ -162,21 +184,8 @@ __global__ void __launch_bounds__(kBlock) k_connect(const __grid_constant__ WfPa
     int* work = p.counters + CNT_W_CONNECT * p.counter_stride + it;
     unsigned nb = 0, np = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.stats + ST_SHADOW_RAYS, (unsigned long long)n);
-    for (;;) {
-        const int base = warp_fetch(work);
-        if (base >= n) break;
-        const int i = base + lane_id();
-        if (i < n) {
-            const float4 so = p.sh_o[i];
-            const float4 sd = p.sh_d[i];
-            float tmax = so.w;
-            const int slot = traverse<true, COUNT>(p.sc, mk3(so), mk3(sd), JPBRT_RAY_TMIN, tmax, nb, np);
-            if (slot < 0) {
-                const float4 c = p.sh_c[i];
-                film_add(p, __float_as_int(sd.w), mk3(c));
-            }
-        }
-    }
+    ConnectIO io{&p};
+    traverse_queue<true, COUNT>(p.sc, n, work, io, p.refill_min, nb, np);
     if (COUNT) {
         warp_stat_add(p.stats + ST_SH_BOX, nb);
         warp_stat_add(p.stats + ST_SH_PRIM, np);
@@ -184,29 +193,58 @@ __global__ void __launch_bounds__(kBlock) k_connect(const __grid_constant__ WfPa
 }
 
 // ---------------------------------------------------------------------------------------------
-// shade
+// shade = logic + one material kernel per BSDF kind
+//
+// A single shade kernel for every material is a 7,000-instruction megakernel whose warps run ~6 of 32
+// lanes and stall on instruction fetch (profiles/r01_ncu_bunny_v0.md).  Instead:
+//   k_logic       : emission / environment, depth termination, null-material pass-through, and
+//                   CLASSIFICATION of every surviving vertex by the BSDF its material builds
+//                   (the plastic lobe pick included) into one index queue per kind;
+//   k_shade<KIND> : NEE + BSDF sampling + roulette for ONE kind: every lane of a warp runs the same
+//                   BSDF code, and each kernel's code is a fraction of the megakernel's.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ WfParams p, int it) {
+enum { KIND_LAMBERT = 0, KIND_MF_CONDUCTOR = 1, KIND_MF_DIELECTRIC = 2, KIND_DELTA = 3, NUM_KINDS = 4 };
+
+__device__ __forceinline__ int bsdf_kind_of(int k) {
+    return k == K_LAMBERT ? KIND_LAMBERT : k == K_MICROFACET_CONDUCTOR ? KIND_MF_CONDUCTOR : k == K_MICROFACET_DIELECTRIC ? KIND_MF_DIELECTRIC : KIND_DELTA;
+}
+
+// Warp-aggregated append of the survivors' records to the next iteration's ray queue.
+__device__ __forceinline__ void append_next(const WfParams& p, int* next_count, int nbuf, bool alive, const float4& no, const float4& nd,
+                                            const float4& nbeta) {
+    const unsigned mask = __ballot_sync(kFull, alive);
+    if (mask) {
+        int wbase = 0;
+        if (lane_id() == 0) wbase = atomicAdd(next_count, __popc(mask));
+        wbase = __shfl_sync(kFull, wbase, 0);
+        if (alive) {
+            const int dst = wbase + __popc(mask & ((1u << lane_id()) - 1));
+            p.ray_o[nbuf][dst] = no;
+            p.ray_d[nbuf][dst] = nd;
+            p.ray_b[nbuf][dst] = nbeta;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_logic(const __grid_constant__ WfParams p, int it) {
     const DevScene& sc = p.sc;
     const int n = p.counters[CNT_RAYS * p.counter_stride + it];
     int* work = p.counters + CNT_W_SHADE * p.counter_stride + it;
     int* next_count = p.counters + CNT_RAYS * p.counter_stride + it + 1;
-    int* shadow_count = p.counters + CNT_SHADOW * p.counter_stride + it;
     const int buf = it & 1, nbuf = buf ^ 1;
-    unsigned n_vertices = 0;
     for (;;) {
         const int base = warp_fetch(work);
         if (base >= n) break;
         const int i = base + lane_id();
         bool alive = false;
+        int kind = -1;
         float4 no = make_float4(0, 0, 0, 0), nd = no, nbeta = no;
         if (i < n) {
             const float4 ro = p.ray_o[buf][i];
             const float4 rd = p.ray_d[buf][i];
             const float4 rb = p.ray_b[buf][i];
             const float2 h = p.hit[i];
-            const f3 o = mk3(ro), d = mk3(rd);
-            f3 beta = mk3(rb);
+            const f3 o = mk3(ro), d = mk3(rd), beta = mk3(rb);
             const int pixel = __float_as_int(ro.w);
             const int fl = __float_as_int(rd.w);
             const int sample = fl & 0xffffff;
@@ -219,92 +257,144 @@ __global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ WfPara
                     for (int k = 0; k < sc.n_inf_lights; ++k)  // integrator.cc:334-335
                         film_add(p, pixel, cmul(beta, mk3(ldg4(sc.lights + (size_t)sc.inf_lights[k] * kLightStride))));
             } else {
-                const float t = h.x;
-                const f3 P = o + t * d;  // FRay::operator(), geometry.h:413-417
-                const f3 N = hit_normal(sc, slot, P, d);
-                const f3 wo = -d;
                 const int2 ml = __ldg(reinterpret_cast<const int2*>(sc.slot_ml) + slot);
-                if (add_emission && ml.y >= 0) {
-                    const f3 Le = emitted(sc, ml.y, N, wo);
-                    if (!is_black(Le)) film_add(p, pixel, cmul(beta, Le));  // integrator.cc:331
-                }
-                if (bounce < sc.max_depth) {  // integrator.cc:340
-                    if (ml.x < 0) {
-                        // null material: the ray continues unchanged and the bounce is not counted (integrator.cc:349-353)
+                const bool emits = add_emission && ml.y >= 0;
+                if (emits || (bounce < sc.max_depth && ml.x < 0)) {
+                    const f3 P = o + h.x * d;  // FRay::operator(), geometry.h:413-417
+                    if (emits) {
+                        const f3 N = hit_normal(sc, slot, P, d);
+                        const f3 Le = emitted(sc, ml.y, N, -d);
+                        if (!is_black(Le)) film_add(p, pixel, cmul(beta, Le));  // integrator.cc:331
+                    }
+                    if (bounce < sc.max_depth && ml.x < 0) {
+                        // null material: the ray continues unchanged, the bounce is not counted (integrator.cc:349-353)
                         alive = true;
                         no = make_float4(P.x, P.y, P.z, ro.w);
                         nd = rd;
                         nbeta = rb;
-                    } else {
-                        ++n_vertices;
+                    }
+                }
+                if (bounce < sc.max_depth && ml.x >= 0) {  // integrator.cc:340,348
+                    const Float4* mat = sc.materials + (size_t)ml.x * kMaterialStride;
+                    const int type = __float_as_int(ldg4(mat).w);
+                    if (type == MAT_PLASTIC) {  // the lobe pick is the first number of the bounce's block (material.cc:14)
                         const uint32_t blk = 1u + (uint32_t)bounce * (uint32_t)p.blocks_per_bounce;
                         const float4 u0 = rng_block(p.key, (uint32_t)pixel, (uint32_t)sample, blk);
-                        const Bsdf bsdf = make_bsdf(sc.materials + (size_t)ml.x * kMaterialStride, u0.x);
-                        const Frame frame = make_frame(N);
-                        const f3 wo_l = to_local(frame, wo);
-                        if (!bsdf_is_delta(bsdf)) {  // integrator.cc:357-372
-                            float4 lu = make_float4(0, 0, 0, 0);
-                            for (int j = 0; j < sc.n_lights; ++j) {
-                                if ((j & 1) == 0) lu = rng_block(p.key, (uint32_t)pixel, (uint32_t)sample, blk + 1u + (uint32_t)(j >> 1));
-                                const float ux = (j & 1) ? lu.z : lu.x, uy = (j & 1) ? lu.w : lu.y;
-                                const LightSample ls = sample_light(sc, j, P, N, ux, uy);
-                                if (is_black(ls.Li) || ls.pdf == 0.f) continue;
-                                const f3 f = bsdf_eval_local(bsdf, wo_l, to_local(frame, ls.wi));
-                                if (is_black(f)) continue;
-                                // FScene::Occluded(isect, ls.pos): scene.h:36-47
-                                const f3 v = ls.pos - P;
-                                const float dist = length(v);
-                                const f3 sdir = v / dist;
-                                const f3 contrib = cmul(cmul(beta, f), ls.Li) * absdot(ls.wi, N) / ls.pdf;  // integrator.cc:369
-                                const int si = coalesced_append(shadow_count);
-                                if (si < p.shadow_capacity) {
-                                    p.sh_o[si] = make_float4(P.x, P.y, P.z, dist - 0.001f);
-                                    p.sh_d[si] = make_float4(sdir.x, sdir.y, sdir.z, ro.w);
-                                    p.sh_c[si] = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
-                                }
-                            }
-                        }
-                        BsdfSample bs = bsdf_sample_local(bsdf, wo_l, u0.y, u0.z);  // integrator.cc:375
-                        bs.wi = to_world(frame, bs.wi);                               // bsdf.h:296-302
-                        if (!(is_black(bs.f) || bs.pdf == 0.f)) {
-                            const bool spec = (bs.flags & BSDF_SPECULAR) != 0;
-                            bool survive = true;
-                            if (bounce >= JPBRT_RR_START_BOUNCE) {  // integrator.cc:383-393
-                                const float q = std_max(JPBRT_RR_QMIN, 1 - max_component(bs.f));
-                                if (u0.w < q) survive = false;
-                                else beta = cmul(beta, bs.f * absdot(bs.wi, N) / (bs.pdf * (1 - q)));
-                            } else {
-                                beta = cmul(beta, bs.f * absdot(bs.wi, N) / bs.pdf);  // integrator.cc:397
-                            }
-                            // A non-specular path that would arrive at bounce == maxDepth can add nothing
-                            // there (no emission, integrator.cc:328; loop ends, :340): do not trace it.
-                            if (survive && (spec || bounce + 1 < sc.max_depth)) {
-                                alive = true;
-                                no = make_float4(P.x, P.y, P.z, ro.w);
-                                nd = make_float4(bs.wi.x, bs.wi.y, bs.wi.z,
-                                                 __int_as_float(sample | ((bounce + 1) << 24) | (spec ? (int)0x80000000 : 0)));
-                                nbeta = make_float4(beta.x, beta.y, beta.z, 0.f);
-                            }
-                        }
+                        kind = (u0.x < ldg4(mat + 2).y) ? KIND_LAMBERT : KIND_MF_DIELECTRIC;
+                    } else {
+                        kind = type == MAT_MATTE ? KIND_LAMBERT : type == MAT_METAL ? KIND_MF_CONDUCTOR : KIND_DELTA;
                     }
                 }
             }
         }
-        // compaction of the survivors: one atomicAdd per warp
-        const unsigned mask = __ballot_sync(kFull, alive);
-        if (mask) {
-            int wbase = 0;
-            if (lane_id() == 0) wbase = atomicAdd(next_count, __popc(mask));
-            wbase = __shfl_sync(kFull, wbase, 0);
-            if (alive) {
-                const int dst = wbase + __popc(mask & ((1u << lane_id()) - 1));
-                p.ray_o[nbuf][dst] = no;
-                p.ray_d[nbuf][dst] = nd;
-                p.ray_b[nbuf][dst] = nbeta;
+        append_next(p, next_count, nbuf, alive, no, nd, nbeta);
+#pragma unroll
+        for (int k = 0; k < NUM_KINDS; ++k) {  // one atomicAdd per warp and kind
+            const unsigned m = __ballot_sync(kFull, kind == k);
+            if (m) {
+                int qb = 0;
+                if (lane_id() == 0) qb = atomicAdd(p.counters + (CNT_Q0 + k) * p.counter_stride + it, __popc(m));
+                qb = __shfl_sync(kFull, qb, 0);
+                if (kind == k) p.kind_queue[(size_t)k * p.queue_capacity + qb + __popc(m & ((1u << lane_id()) - 1))] = i;
             }
         }
     }
-    warp_stat_add(p.stats + ST_VERTICES, n_vertices);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ WfParams p, int it) {
+    const DevScene& sc = p.sc;
+    const int n = p.counters[(CNT_Q0 + KIND) * p.counter_stride + it];
+    int* work = p.counters + (CNT_WQ0 + KIND) * p.counter_stride + it;
+    int* next_count = p.counters + CNT_RAYS * p.counter_stride + it + 1;
+    int* shadow_count = p.counters + CNT_SHADOW * p.counter_stride + it;
+    const int* __restrict__ queue = p.kind_queue + (size_t)KIND * p.queue_capacity;
+    const int buf = it & 1, nbuf = buf ^ 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.stats + ST_VERTICES, (unsigned long long)n);
+    for (;;) {
+        const int base = warp_fetch(work);
+        if (base >= n) break;
+        const int qi = base + lane_id();
+        bool alive = false;
+        float4 no = make_float4(0, 0, 0, 0), nd = no, nbeta = no;
+        if (qi < n) {
+            const int i = queue[qi];
+            const float4 ro = p.ray_o[buf][i];
+            const float4 rd = p.ray_d[buf][i];
+            const float4 rb = p.ray_b[buf][i];
+            const float2 h = p.hit[i];
+            const f3 o = mk3(ro), d = mk3(rd);
+            f3 beta = mk3(rb);
+            const int pixel = __float_as_int(ro.w);
+            const int fl = __float_as_int(rd.w);
+            const int sample = fl & 0xffffff;
+            const int bounce = (fl >> 24) & 0x7f;
+            const int slot = __float_as_int(h.y);
+            const f3 P = o + h.x * d;  // FRay::operator(), geometry.h:413-417
+            const f3 N = hit_normal(sc, slot, P, d);
+            const f3 wo = -d;
+            const int2 ml = __ldg(reinterpret_cast<const int2*>(sc.slot_ml) + slot);
+            const uint32_t blk = 1u + (uint32_t)bounce * (uint32_t)p.blocks_per_bounce;
+            const float4 u0 = rng_block(p.key, (uint32_t)pixel, (uint32_t)sample, blk);
+            Bsdf bsdf = make_bsdf(sc.materials + (size_t)ml.x * kMaterialStride, u0.x);
+            if (KIND == KIND_LAMBERT) bsdf.kind = K_LAMBERT;  // known at compile time: the other BSDFs' code is pruned
+            if (KIND == KIND_MF_CONDUCTOR) bsdf.kind = K_MICROFACET_CONDUCTOR;
+            if (KIND == KIND_MF_DIELECTRIC) bsdf.kind = K_MICROFACET_DIELECTRIC;
+            if (KIND == KIND_DELTA && bsdf.kind != K_SPECULAR) bsdf.kind = K_FRESNEL_SPECULAR;
+            const Frame frame = hit_frame(sc, slot, N);
+            const f3 wo_l = to_local(frame, wo);
+            if (KIND != KIND_DELTA) {  // integrator.cc:357-372
+                float4 lu = make_float4(0, 0, 0, 0);
+                int lu_block = -1;
+                for (int k = 0; k < sc.n_nee_lights; ++k) {  // black lights are skipped (integrator.cc:362), not sampled
+                    const int j = __ldg(sc.nee_lights + k);
+                    if ((j >> 1) != lu_block) {
+                        lu_block = j >> 1;
+                        lu = rng_block(p.key, (uint32_t)pixel, (uint32_t)sample, blk + 1u + (uint32_t)lu_block);
+                    }
+                    const float ux = (j & 1) ? lu.z : lu.x, uy = (j & 1) ? lu.w : lu.y;
+                    const LightSample ls = sample_light(sc, j, P, N, ux, uy);
+                    if (is_black(ls.Li) || ls.pdf == 0.f) continue;
+                    const f3 f = bsdf_eval_local(bsdf, wo_l, to_local(frame, ls.wi));
+                    if (is_black(f)) continue;
+                    // FScene::Occluded(isect, ls.pos): scene.h:36-47
+                    const f3 v = ls.pos - P;
+                    const float dist = length(v);
+                    const f3 sdir = v / dist;
+                    const f3 contrib = cmul(cmul(beta, f), ls.Li) * absdot(ls.wi, N) / ls.pdf;  // integrator.cc:369
+                    const int si = coalesced_append(shadow_count);
+                    if (si < p.shadow_capacity) {
+                        p.sh_o[si] = make_float4(P.x, P.y, P.z, dist - 0.001f);
+                        p.sh_d[si] = make_float4(sdir.x, sdir.y, sdir.z, ro.w);
+                        p.sh_c[si] = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
+                    }
+                }
+            }
+            BsdfSample bs = bsdf_sample_local(bsdf, wo_l, u0.y, u0.z);  // integrator.cc:375
+            bs.wi = to_world(frame, bs.wi);                               // bsdf.h:296-302
+            if (!(is_black(bs.f) || bs.pdf == 0.f)) {
+                const bool spec = (bs.flags & BSDF_SPECULAR) != 0;
+                bool survive = true;
+                if (bounce >= JPBRT_RR_START_BOUNCE) {  // integrator.cc:383-393
+                    const float q = std_max(JPBRT_RR_QMIN, 1 - max_component(bs.f));
+                    if (u0.w < q) survive = false;
+                    else beta = cmul(beta, bs.f * absdot(bs.wi, N) / (bs.pdf * (1 - q)));
+                } else {
+                    beta = cmul(beta, bs.f * absdot(bs.wi, N) / bs.pdf);  // integrator.cc:397
+                }
+                // A non-specular path that would arrive at bounce == maxDepth can add nothing there (no
+                // emission, integrator.cc:328; loop ends, :340): do not trace it.
+                if (survive && (spec || bounce + 1 < sc.max_depth)) {
+                    alive = true;
+                    no = make_float4(P.x, P.y, P.z, ro.w);
+                    nd = make_float4(bs.wi.x, bs.wi.y, bs.wi.z,
+                                     __int_as_float(sample | ((bounce + 1) << 24) | (spec ? (int)0x80000000 : 0)));
+                    nbeta = make_float4(beta.x, beta.y, beta.z, 0.f);
+                }
+            }
+        }
+        append_next(p, next_count, nbuf, alive, no, nd, nbeta);
+    }
 }
 
 // Paths still queued after the last iteration (only possible with null-material chains) are dropped and counted.
