@@ -84,7 +84,7 @@ struct jpbrt_ctx {
     long long opt_paths_in_flight = 0;
     bool opt_stage_timing = false;
     bool opt_count_traversal = false;
-    int opt_refill_min = 8;
+    int opt_refill_min = 16;
     unsigned kinds_present = 0;  // bit k set: some material of the scene can build BSDF kind k
     // launch geometry
     int grid_generate = 0, grid_extend = 0, grid_extend_c = 0, grid_logic = 0, grid_shade[4] = {0, 0, 0, 0}, grid_connect = 0, grid_connect_c = 0, grid_finalize = 0;
@@ -314,9 +314,10 @@ int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out
     d.height = hs.height;
     d.world_radius = hs.world_radius;
     d.cam = hs.cam;
-    for (size_t m = 0; m < hs.materials.size() / kMaterialStride; ++m) {
+    for (const Int2& ml : hs.slot_ml) {  // BSDF kinds that materials bound to primitives can build
+        if (ml.x < 0) continue;
         int type;
-        memcpy(&type, &hs.materials[m * kMaterialStride].w, 4);
+        memcpy(&type, &hs.materials[(size_t)ml.x * kMaterialStride].w, 4);
         c->kinds_present |= type == JPBRT_MAT_MATTE ? 1u : type == JPBRT_MAT_METAL ? 2u : type == JPBRT_MAT_PLASTIC ? (1u | 4u) : 8u;
     }
     // iterations: bounces 0..max_depth, plus slack for null-material pass-through vertices
