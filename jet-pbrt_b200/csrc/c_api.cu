@@ -187,7 +187,7 @@ int ensure_pool(jpbrt_ctx* c) {
     long long k = std::max(1ll, want / npix);
     long long cap = k * npix;
     if (cap > 0x7fff0000ll) return set_error(c, JPBRT_ERR_UNSUPPORTED, "film too large for one wavefront (%lld pixels)", npix);
-    int n_lights = std::max(1, (int)(c->hs.lights.size() / kLightStride));
+    int n_lights = std::max(1, (int)c->hs.nee_lights.size());  // one shadow slot per (vertex, non-black light)
     long long shadow_cap = cap * n_lights;
     if (shadow_cap > 0x7fff0000ll) {  // keep queue indices in int range
         k = std::max(1ll, 0x7fff0000ll / (npix * n_lights));
@@ -573,12 +573,13 @@ struct UnitRayIO {
     float* pos3;
     float* nrm3;
     const DevScene* sc;
-    __device__ __forceinline__ void load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
+    __device__ __forceinline__ bool load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
         const float* q = rays8 + 8 * (size_t)i;
         o = mk3(q[0], q[1], q[2]);
         d = mk3(q[3], q[4], q[5]);
         tmin = q[6];
         tmax = q[7];
+        return true;
     }
     __device__ __forceinline__ void store(int i, int slot, float tmax) const {
         const float* q = rays8 + 8 * (size_t)i;
@@ -607,7 +608,7 @@ struct UnitOccIO {
     const float* pos3;
     const float* target3;
     int* occ;
-    __device__ __forceinline__ void load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
+    __device__ __forceinline__ bool load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
         const f3 P = ld3(pos3, i), T = ld3(target3, i);
         const f3 v = T - P;  // scene.h:44-47: Normalize(target - pos), Distance(pos, target)
         const float dist = length(v);
@@ -615,6 +616,7 @@ struct UnitOccIO {
         d = v / dist;
         tmin = JPBRT_RAY_TMIN;
         tmax = dist - 0.001f;
+        return true;
     }
     __device__ __forceinline__ void store(int i, int slot, float) const { occ[i] = slot >= 0 ? 1 : 0; }
 };

@@ -200,7 +200,7 @@ __device__ __forceinline__ void trav_leaf_step(const DevScene& sc, Trav& t, cons
 }
 
 // Warp-cooperative traversal of a whole ray queue.
-//   io.load(i, o, d, tmin, tmax)    fetch ray i          io.store(i, slot, t)   deliver its result
+//   io.load(i, o, d, tmin, tmax)    fetch ray i (false: slot i holds no ray)   io.store(i, slot, t)   deliver its result
 // Every lane owns one ray at a time.  Each trip round the outer loop has three converged phases:
 //   refill : idle lanes take the next rays from the queue (one atomicAdd per warp) once at least
 //            `refill_min` lanes are idle -- finished rays are REPLACED instead of idling until the
@@ -229,9 +229,10 @@ __device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* w
                 if (i < n) {
                     f3 o, d;
                     float tmin, tmax;
-                    io.load(i, o, d, tmin, tmax);
-                    trav_init(t, o, d, tmin, tmax);
-                    idx = i;
+                    if (io.load(i, o, d, tmin, tmax)) {
+                        trav_init(t, o, d, tmin, tmax);
+                        idx = i;
+                    }
                 }
             }
             if (base + cnt >= n) exhausted = true;

@@ -136,11 +136,12 @@ struct ExtendIO {
     const float4* ro;
     const float4* rd;
     float2* hit;
-    __device__ __forceinline__ void load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
+    __device__ __forceinline__ bool load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
         o = mk3(ro[i]);
         d = mk3(rd[i]);
         tmin = JPBRT_RAY_TMIN;                 // FRay default min_t, geometry.h:395
         tmax = __int_as_float(0x7f800000);     // kInfinity
+        return true;
     }
     __device__ __forceinline__ void store(int i, int slot, float t) const { hit[i] = make_float2(t, __int_as_float(slot)); }
 };
@@ -163,29 +164,42 @@ __global__ void __launch_bounds__(kBlock) k_extend(const __grid_constant__ WfPar
 // ---------------------------------------------------------------------------------------------
 // connect: any-hit for every shadow ray of iteration `it`; unoccluded -> film += contribution
 // ---------------------------------------------------------------------------------------------
+// Shadow rays live in STATIC slots: vertex v of the iteration (v = its position in the concatenated
+// lambert | conductor | dielectric kind queues) and non-black light k own slot k * n_vertices + v, so
+// k_shade needs no atomics to emit them and the slots of one light are contiguous (coalesced writes,
+// and coherent rays for k_connect).  A slot whose sample cannot contribute holds tmax < 0.
 struct ConnectIO {
     const WfParams* p;
-    __device__ __forceinline__ void load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
+    unsigned* n_traced;
+    __device__ __forceinline__ bool load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
         const float4 so = p->sh_o[i];
+        if (so.w < 0.f) return false;
         o = mk3(so);
         d = mk3(p->sh_d[i]);
         tmin = JPBRT_RAY_TMIN;  // scene.h:38
         tmax = so.w;            // dist - 0.001
+        ++*n_traced;
+        return true;
     }
     __device__ __forceinline__ void store(int i, int slot, float) const {
         if (slot < 0) film_add(*p, __float_as_int(p->sh_d[i].w), mk3(p->sh_c[i]));  // integrator.cc:367-370
     }
 };
 
+__device__ __forceinline__ int nee_vertex_count(const WfParams& p, int it) {
+    return p.counters[(CNT_Q0 + 0) * p.counter_stride + it] + p.counters[(CNT_Q0 + 1) * p.counter_stride + it] +
+           p.counters[(CNT_Q0 + 2) * p.counter_stride + it];
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) k_connect(const __grid_constant__ WfParams p, int it) {
-    int n = p.counters[CNT_SHADOW * p.counter_stride + it];
-    if (n > p.shadow_capacity) n = p.shadow_capacity;
+    const long long slots = (long long)nee_vertex_count(p, it) * p.sc.n_nee_lights;
+    const int n = (int)(slots < p.shadow_capacity ? slots : p.shadow_capacity);
     int* work = p.counters + CNT_W_CONNECT * p.counter_stride + it;
-    unsigned nb = 0, np = 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.stats + ST_SHADOW_RAYS, (unsigned long long)n);
-    ConnectIO io{&p};
+    unsigned nb = 0, np = 0, traced = 0;
+    ConnectIO io{&p, &traced};
     traverse_queue<true, COUNT>(p.sc, n, work, io, p.refill_min, nb, np);
+    warp_stat_add(p.stats + ST_SHADOW_RAYS, traced);
     if (COUNT) {
         warp_stat_add(p.stats + ST_SH_BOX, nb);
         warp_stat_add(p.stats + ST_SH_PRIM, np);
@@ -226,76 +240,114 @@ __device__ __forceinline__ void append_next(const WfParams& p, int* next_count, 
     }
 }
 
+constexpr int kChunksPerFetch = 4;  // work is fetched up to 128 items at a time: fewer atomics on the hot queue cursors
+
+// Items per fetch: 128 while the queue is long, shrinking to 32 when it is short relative to the number of
+// resident warps, so that late, small iterations still spread over the whole chip.
+__device__ __forceinline__ int chunks_for(int n) {
+    const int total_warps = (gridDim.x * blockDim.x) >> 5;
+    return max(1, min(kChunksPerFetch, n / (total_warps * 64)));
+}
+
+__device__ __forceinline__ int warp_fetch_n(int* counter, int amount) {
+    int base = 0;
+    if (lane_id() == 0) base = atomicAdd(counter, amount);
+    return __shfl_sync(kFull, base, 0);
+}
+
 __global__ void __launch_bounds__(kBlock) k_logic(const __grid_constant__ WfParams p, int it) {
     const DevScene& sc = p.sc;
     const int n = p.counters[CNT_RAYS * p.counter_stride + it];
     int* work = p.counters + CNT_W_SHADE * p.counter_stride + it;
     int* next_count = p.counters + CNT_RAYS * p.counter_stride + it + 1;
     const int buf = it & 1, nbuf = buf ^ 1;
+    const int nchunks = chunks_for(n);
     for (;;) {
-        const int base = warp_fetch(work);
+        const int base = warp_fetch_n(work, 32 * nchunks);
         if (base >= n) break;
-        const int i = base + lane_id();
-        bool alive = false;
-        int kind = -1;
-        float4 no = make_float4(0, 0, 0, 0), nd = no, nbeta = no;
-        if (i < n) {
-            const float4 ro = p.ray_o[buf][i];
-            const float4 rd = p.ray_d[buf][i];
-            const float4 rb = p.ray_b[buf][i];
-            const float2 h = p.hit[i];
-            const f3 o = mk3(ro), d = mk3(rd), beta = mk3(rb);
-            const int pixel = __float_as_int(ro.w);
-            const int fl = __float_as_int(rd.w);
-            const int sample = fl & 0xffffff;
-            const int bounce = (fl >> 24) & 0x7f;
-            const bool specular = fl < 0;
-            const int slot = __float_as_int(h.y);
-            const bool add_emission = (bounce == 0) || specular;  // integrator.cc:328
-            if (slot < 0) {
-                if (add_emission)
-                    for (int k = 0; k < sc.n_inf_lights; ++k)  // integrator.cc:334-335
-                        film_add(p, pixel, cmul(beta, mk3(ldg4(sc.lights + (size_t)sc.inf_lights[k] * kLightStride))));
-            } else {
-                const int2 ml = __ldg(reinterpret_cast<const int2*>(sc.slot_ml) + slot);
-                const bool emits = add_emission && ml.y >= 0;
-                if (emits || (bounce < sc.max_depth && ml.x < 0)) {
-                    const f3 P = o + h.x * d;  // FRay::operator(), geometry.h:413-417
-                    if (emits) {
-                        const f3 N = hit_normal(sc, slot, P, d);
-                        const f3 Le = emitted(sc, ml.y, N, -d);
-                        if (!is_black(Le)) film_add(p, pixel, cmul(beta, Le));  // integrator.cc:331
+        int kinds[kChunksPerFetch];
+        unsigned masks[kChunksPerFetch][NUM_KINDS];
+#pragma unroll
+        for (int c = 0; c < kChunksPerFetch; ++c) {
+            const int i = base + 32 * c + lane_id();
+            bool alive = false;
+            int kind = -1;
+            float4 no = make_float4(0, 0, 0, 0), nd = no, nbeta = no;
+            if (c < nchunks && i < n) {
+                const float4 rd = p.ray_d[buf][i];
+                const float2 h = p.hit[i];
+                const int fl = __float_as_int(rd.w);
+                const int bounce = (fl >> 24) & 0x7f;
+                const bool specular = fl < 0;
+                const int slot = __float_as_int(h.y);
+                const bool add_emission = (bounce == 0) || specular;  // integrator.cc:328
+                if (slot < 0) {
+                    if (add_emission && sc.n_inf_lights > 0) {
+                        const int pixel = __float_as_int(p.ray_o[buf][i].w);
+                        const f3 beta = mk3(p.ray_b[buf][i]);
+                        for (int k = 0; k < sc.n_inf_lights; ++k)  // integrator.cc:334-335
+                            film_add(p, pixel, cmul(beta, mk3(ldg4(sc.lights + (size_t)sc.inf_lights[k] * kLightStride))));
                     }
-                    if (bounce < sc.max_depth && ml.x < 0) {
-                        // null material: the ray continues unchanged, the bounce is not counted (integrator.cc:349-353)
-                        alive = true;
-                        no = make_float4(P.x, P.y, P.z, ro.w);
-                        nd = rd;
-                        nbeta = rb;
+                } else {
+                    const int2 ml = __ldg(reinterpret_cast<const int2*>(sc.slot_ml) + slot);
+                    const bool emits = add_emission && ml.y >= 0;
+                    const bool pass = bounce < sc.max_depth && ml.x < 0;
+                    if (emits || pass) {
+                        const float4 ro = p.ray_o[buf][i];
+                        const float4 rb = p.ray_b[buf][i];
+                        const f3 o = mk3(ro), d = mk3(rd);
+                        const f3 P = o + h.x * d;  // FRay::operator(), geometry.h:413-417
+                        if (emits) {
+                            const f3 N = hit_normal(sc, slot, P, d);
+                            const f3 Le = emitted(sc, ml.y, N, -d);
+                            if (!is_black(Le)) film_add(p, __float_as_int(ro.w), cmul(mk3(rb), Le));  // integrator.cc:331
+                        }
+                        if (pass) {
+                            // null material: the ray continues unchanged, the bounce is not counted (integrator.cc:349-353)
+                            alive = true;
+                            no = make_float4(P.x, P.y, P.z, ro.w);
+                            nd = rd;
+                            nbeta = rb;
+                        }
                     }
-                }
-                if (bounce < sc.max_depth && ml.x >= 0) {  // integrator.cc:340,348
-                    const Float4* mat = sc.materials + (size_t)ml.x * kMaterialStride;
-                    const int type = __float_as_int(ldg4(mat).w);
-                    if (type == MAT_PLASTIC) {  // the lobe pick is the first number of the bounce's block (material.cc:14)
-                        const uint32_t blk = 1u + (uint32_t)bounce * (uint32_t)p.blocks_per_bounce;
-                        const float4 u0 = rng_block(p.key, (uint32_t)pixel, (uint32_t)sample, blk);
-                        kind = (u0.x < ldg4(mat + 2).y) ? KIND_LAMBERT : KIND_MF_DIELECTRIC;
-                    } else {
-                        kind = type == MAT_MATTE ? KIND_LAMBERT : type == MAT_METAL ? KIND_MF_CONDUCTOR : KIND_DELTA;
+                    if (bounce < sc.max_depth && ml.x >= 0) {  // integrator.cc:340,348
+                        const Float4* mat = sc.materials + (size_t)ml.x * kMaterialStride;
+                        const int type = __float_as_int(ldg4(mat).w);
+                        if (type == MAT_PLASTIC) {  // the lobe pick is the first number of the bounce's block (material.cc:14)
+                            const int pixel = __float_as_int(p.ray_o[buf][i].w);
+                            const uint32_t blk = 1u + (uint32_t)bounce * (uint32_t)p.blocks_per_bounce;
+                            const float4 u0 = rng_block(p.key, (uint32_t)pixel, (uint32_t)(fl & 0xffffff), blk);
+                            kind = (u0.x < ldg4(mat + 2).y) ? KIND_LAMBERT : KIND_MF_DIELECTRIC;
+                        } else {
+                            kind = type == MAT_MATTE ? KIND_LAMBERT : type == MAT_METAL ? KIND_MF_CONDUCTOR : KIND_DELTA;
+                        }
                     }
                 }
             }
-        }
-        append_next(p, next_count, nbuf, alive, no, nd, nbeta);
+            append_next(p, next_count, nbuf, alive, no, nd, nbeta);
+            kinds[c] = kind;
 #pragma unroll
-        for (int k = 0; k < NUM_KINDS; ++k) {  // one atomicAdd per warp and kind
-            const unsigned m = __ballot_sync(kFull, kind == k);
-            if (m) {
-                int qb = 0;
-                if (lane_id() == 0) qb = atomicAdd(p.counters + (CNT_Q0 + k) * p.counter_stride + it, __popc(m));
-                qb = __shfl_sync(kFull, qb, 0);
-                if (kind == k) p.kind_queue[(size_t)k * p.queue_capacity + qb + __popc(m & ((1u << lane_id()) - 1))] = i;
+            for (int k = 0; k < NUM_KINDS; ++k) masks[c][k] = __ballot_sync(kFull, kind == k);
+        }
+        // one atomicAdd per kind for all 128 items; the four are issued back to back
+        int totals[NUM_KINDS], bases[NUM_KINDS];
+#pragma unroll
+        for (int k = 0; k < NUM_KINDS; ++k) {
+            totals[k] = 0;
+#pragma unroll
+            for (int c = 0; c < kChunksPerFetch; ++c) totals[k] += __popc(masks[c][k]);
+            bases[k] = 0;
+            if (lane_id() == 0 && totals[k]) bases[k] = atomicAdd(p.counters + (CNT_Q0 + k) * p.counter_stride + it, totals[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < NUM_KINDS; ++k) bases[k] = __shfl_sync(kFull, bases[k], 0);
+#pragma unroll
+        for (int c = 0; c < kChunksPerFetch; ++c) {
+#pragma unroll
+            for (int k = 0; k < NUM_KINDS; ++k) {
+                if (kinds[c] == k)
+                    p.kind_queue[(size_t)k * p.queue_capacity + bases[k] + __popc(masks[c][k] & ((1u << lane_id()) - 1))] = base + 32 * c + lane_id();
+                bases[k] += __popc(masks[c][k]);
             }
         }
     }
@@ -307,93 +359,116 @@ __global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ WfPara
     const int n = p.counters[(CNT_Q0 + KIND) * p.counter_stride + it];
     int* work = p.counters + (CNT_WQ0 + KIND) * p.counter_stride + it;
     int* next_count = p.counters + CNT_RAYS * p.counter_stride + it + 1;
-    int* shadow_count = p.counters + CNT_SHADOW * p.counter_stride + it;
     const int* __restrict__ queue = p.kind_queue + (size_t)KIND * p.queue_capacity;
     const int buf = it & 1, nbuf = buf ^ 1;
+    // static shadow slots (see ConnectIO): this kind's vertices start at `kind_base` of the iteration's vertex list
+    const int n_vertices = nee_vertex_count(p, it);
+    int kind_base = 0;
+#pragma unroll
+    for (int k = 0; k < NUM_KINDS; ++k)
+        if (k < KIND) kind_base += p.counters[(CNT_Q0 + k) * p.counter_stride + it];
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.stats + ST_VERTICES, (unsigned long long)n);
+    const int nchunks = chunks_for(n);
     for (;;) {
-        const int base = warp_fetch(work);
-        if (base >= n) break;
-        const int qi = base + lane_id();
-        bool alive = false;
-        float4 no = make_float4(0, 0, 0, 0), nd = no, nbeta = no;
-        if (qi < n) {
-            const int i = queue[qi];
-            const float4 ro = p.ray_o[buf][i];
-            const float4 rd = p.ray_d[buf][i];
-            const float4 rb = p.ray_b[buf][i];
-            const float2 h = p.hit[i];
-            const f3 o = mk3(ro), d = mk3(rd);
-            f3 beta = mk3(rb);
-            const int pixel = __float_as_int(ro.w);
-            const int fl = __float_as_int(rd.w);
-            const int sample = fl & 0xffffff;
-            const int bounce = (fl >> 24) & 0x7f;
-            const int slot = __float_as_int(h.y);
-            const f3 P = o + h.x * d;  // FRay::operator(), geometry.h:413-417
-            const f3 N = hit_normal(sc, slot, P, d);
-            const f3 wo = -d;
-            const int2 ml = __ldg(reinterpret_cast<const int2*>(sc.slot_ml) + slot);
-            const uint32_t blk = 1u + (uint32_t)bounce * (uint32_t)p.blocks_per_bounce;
-            const float4 u0 = rng_block(p.key, (uint32_t)pixel, (uint32_t)sample, blk);
-            Bsdf bsdf = make_bsdf(sc.materials + (size_t)ml.x * kMaterialStride, u0.x);
-            if (KIND == KIND_LAMBERT) bsdf.kind = K_LAMBERT;  // known at compile time: the other BSDFs' code is pruned
-            if (KIND == KIND_MF_CONDUCTOR) bsdf.kind = K_MICROFACET_CONDUCTOR;
-            if (KIND == KIND_MF_DIELECTRIC) bsdf.kind = K_MICROFACET_DIELECTRIC;
-            if (KIND == KIND_DELTA && bsdf.kind != K_SPECULAR) bsdf.kind = K_FRESNEL_SPECULAR;
-            const Frame frame = hit_frame(sc, slot, N);
-            const f3 wo_l = to_local(frame, wo);
-            if (KIND != KIND_DELTA) {  // integrator.cc:357-372
-                float4 lu = make_float4(0, 0, 0, 0);
-                int lu_block = -1;
-                for (int k = 0; k < sc.n_nee_lights; ++k) {  // black lights are skipped (integrator.cc:362), not sampled
-                    const int j = __ldg(sc.nee_lights + k);
-                    if ((j >> 1) != lu_block) {
-                        lu_block = j >> 1;
-                        lu = rng_block(p.key, (uint32_t)pixel, (uint32_t)sample, blk + 1u + (uint32_t)lu_block);
+        const int fetch_base = warp_fetch_n(work, 32 * nchunks);
+        if (fetch_base >= n) break;
+#pragma unroll 1
+        for (int c = 0; c < nchunks; ++c) {
+            if (fetch_base + 32 * c >= n) break;
+            const int qi = fetch_base + 32 * c + lane_id();
+            bool alive = false;
+            float4 no = make_float4(0, 0, 0, 0), nd = no, nbeta = no;
+            if (qi < n) {
+                const int i = queue[qi];
+                const float4 ro = p.ray_o[buf][i];
+                const float4 rd = p.ray_d[buf][i];
+                const float4 rb = p.ray_b[buf][i];
+                const float2 h = p.hit[i];
+                const f3 o = mk3(ro), d = mk3(rd);
+                f3 beta = mk3(rb);
+                const int pixel = __float_as_int(ro.w);
+                const int fl = __float_as_int(rd.w);
+                const int sample = fl & 0xffffff;
+                const int bounce = (fl >> 24) & 0x7f;
+                const int slot = __float_as_int(h.y);
+                const f3 P = o + h.x * d;  // FRay::operator(), geometry.h:413-417
+                const f3 N = hit_normal(sc, slot, P, d);
+                const f3 wo = -d;
+                const int2 ml = __ldg(reinterpret_cast<const int2*>(sc.slot_ml) + slot);
+                const uint32_t blk = 1u + (uint32_t)bounce * (uint32_t)p.blocks_per_bounce;
+                const float4 u0 = rng_block(p.key, (uint32_t)pixel, (uint32_t)sample, blk);
+                Bsdf bsdf = make_bsdf(sc.materials + (size_t)ml.x * kMaterialStride, u0.x);
+                if (KIND == KIND_LAMBERT) bsdf.kind = K_LAMBERT;  // known at compile time: the other BSDFs' code is pruned
+                if (KIND == KIND_MF_CONDUCTOR) bsdf.kind = K_MICROFACET_CONDUCTOR;
+                if (KIND == KIND_MF_DIELECTRIC) bsdf.kind = K_MICROFACET_DIELECTRIC;
+                if (KIND == KIND_DELTA && bsdf.kind != K_SPECULAR) bsdf.kind = K_FRESNEL_SPECULAR;
+                const Frame frame = hit_frame(sc, slot, N);
+                const f3 wo_l = to_local(frame, wo);
+                if (KIND != KIND_DELTA) {  // integrator.cc:357-372
+                    float4 lu = make_float4(0, 0, 0, 0);
+                    int lu_block = -1;
+                    for (int k = 0; k < sc.n_nee_lights; ++k) {  // black lights are skipped (integrator.cc:362), not sampled
+                        const int j = __ldg(sc.nee_lights + k);
+                        if ((j >> 1) != lu_block) {
+                            lu_block = j >> 1;
+                            lu = rng_block(p.key, (uint32_t)pixel, (uint32_t)sample, blk + 1u + (uint32_t)lu_block);
+                        }
+                        const float ux = (j & 1) ? lu.z : lu.x, uy = (j & 1) ? lu.w : lu.y;
+                        const long long si = (long long)k * n_vertices + kind_base + qi;  // this (vertex, light)'s slot
+                        const bool fits = si < p.shadow_capacity;
+                        const LightSample ls = sample_light(sc, j, P, N, ux, uy);
+                        bool valid = !(is_black(ls.Li) || ls.pdf == 0.f);
+                        f3 f = mk3(0, 0, 0);
+                        if (valid) {
+                            f = bsdf_eval_local(bsdf, wo_l, to_local(frame, ls.wi));
+                            valid = !is_black(f);
+                        }
+                        if (valid && fits) {
+                            // FScene::Occluded(isect, ls.pos): scene.h:36-47
+                            const f3 v = ls.pos - P;
+                            const float dist = length(v);
+                            const f3 sdir = v / dist;
+                            const f3 contrib = cmul(cmul(beta, f), ls.Li) * absdot(ls.wi, N) / ls.pdf;  // integrator.cc:369
+                            // a degenerate distance (tmax <= 0 or NaN) can hit nothing: the sample is unoccluded
+                            const float tmax = dist - 0.001f;
+                            if (tmax > 0.f) {
+                                p.sh_o[si] = make_float4(P.x, P.y, P.z, tmax);
+                                p.sh_d[si] = make_float4(sdir.x, sdir.y, sdir.z, ro.w);
+                                p.sh_c[si] = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
+                            } else {
+                                p.sh_o[si] = make_float4(0.f, 0.f, 0.f, -1.f);
+                                film_add(p, pixel, contrib);
+                            }
+                        } else if (fits) {
+                            p.sh_o[si] = make_float4(0.f, 0.f, 0.f, -1.f);
+                        }
                     }
-                    const float ux = (j & 1) ? lu.z : lu.x, uy = (j & 1) ? lu.w : lu.y;
-                    const LightSample ls = sample_light(sc, j, P, N, ux, uy);
-                    if (is_black(ls.Li) || ls.pdf == 0.f) continue;
-                    const f3 f = bsdf_eval_local(bsdf, wo_l, to_local(frame, ls.wi));
-                    if (is_black(f)) continue;
-                    // FScene::Occluded(isect, ls.pos): scene.h:36-47
-                    const f3 v = ls.pos - P;
-                    const float dist = length(v);
-                    const f3 sdir = v / dist;
-                    const f3 contrib = cmul(cmul(beta, f), ls.Li) * absdot(ls.wi, N) / ls.pdf;  // integrator.cc:369
-                    const int si = coalesced_append(shadow_count);
-                    if (si < p.shadow_capacity) {
-                        p.sh_o[si] = make_float4(P.x, P.y, P.z, dist - 0.001f);
-                        p.sh_d[si] = make_float4(sdir.x, sdir.y, sdir.z, ro.w);
-                        p.sh_c[si] = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
+                }
+                BsdfSample bs = bsdf_sample_local(bsdf, wo_l, u0.y, u0.z);  // integrator.cc:375
+                bs.wi = to_world(frame, bs.wi);                               // bsdf.h:296-302
+                if (!(is_black(bs.f) || bs.pdf == 0.f)) {
+                    const bool spec = (bs.flags & BSDF_SPECULAR) != 0;
+                    bool survive = true;
+                    if (bounce >= JPBRT_RR_START_BOUNCE) {  // integrator.cc:383-393
+                        const float q = std_max(JPBRT_RR_QMIN, 1 - max_component(bs.f));
+                        if (u0.w < q) survive = false;
+                        else beta = cmul(beta, bs.f * absdot(bs.wi, N) / (bs.pdf * (1 - q)));
+                    } else {
+                        beta = cmul(beta, bs.f * absdot(bs.wi, N) / bs.pdf);  // integrator.cc:397
+                    }
+                    // A non-specular path that would arrive at bounce == maxDepth can add nothing there (no
+                    // emission, integrator.cc:328; loop ends, :340): do not trace it.
+                    if (survive && (spec || bounce + 1 < sc.max_depth)) {
+                        alive = true;
+                        no = make_float4(P.x, P.y, P.z, ro.w);
+                        nd = make_float4(bs.wi.x, bs.wi.y, bs.wi.z,
+                                         __int_as_float(sample | ((bounce + 1) << 24) | (spec ? (int)0x80000000 : 0)));
+                        nbeta = make_float4(beta.x, beta.y, beta.z, 0.f);
                     }
                 }
             }
-            BsdfSample bs = bsdf_sample_local(bsdf, wo_l, u0.y, u0.z);  // integrator.cc:375
-            bs.wi = to_world(frame, bs.wi);                               // bsdf.h:296-302
-            if (!(is_black(bs.f) || bs.pdf == 0.f)) {
-                const bool spec = (bs.flags & BSDF_SPECULAR) != 0;
-                bool survive = true;
-                if (bounce >= JPBRT_RR_START_BOUNCE) {  // integrator.cc:383-393
-                    const float q = std_max(JPBRT_RR_QMIN, 1 - max_component(bs.f));
-                    if (u0.w < q) survive = false;
-                    else beta = cmul(beta, bs.f * absdot(bs.wi, N) / (bs.pdf * (1 - q)));
-                } else {
-                    beta = cmul(beta, bs.f * absdot(bs.wi, N) / bs.pdf);  // integrator.cc:397
-                }
-                // A non-specular path that would arrive at bounce == maxDepth can add nothing there (no
-                // emission, integrator.cc:328; loop ends, :340): do not trace it.
-                if (survive && (spec || bounce + 1 < sc.max_depth)) {
-                    alive = true;
-                    no = make_float4(P.x, P.y, P.z, ro.w);
-                    nd = make_float4(bs.wi.x, bs.wi.y, bs.wi.z,
-                                     __int_as_float(sample | ((bounce + 1) << 24) | (spec ? (int)0x80000000 : 0)));
-                    nbeta = make_float4(beta.x, beta.y, beta.z, 0.f);
-                }
-            }
+            append_next(p, next_count, nbuf, alive, no, nd, nbeta);
         }
-        append_next(p, next_count, nbuf, alive, no, nd, nbeta);
     }
 }
 
