@@ -94,7 +94,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def run_reference(args, cfg):
+def run_reference(args, cfg, emit):
     """--impl reference: the reference's own CPU implementation of the path (parallel.cc thread pool)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -131,7 +131,7 @@ def run_reference(args, cfg):
                              "sample": f"{w}x{h} x {step_spp} spp per step, FIntegrator::Render with numthreads={threads}; scene build {build_s:.2f}s excluded"},
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -147,8 +147,17 @@ def main():
     ap.add_argument("--paths-in-flight", type=int, default=0)
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
+    # stdout carries exactly ONE JSON line: everything else (NCCL banners, library chatter) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+
     if args.impl == "reference":
-        return run_reference(args, cfg)
+        return run_reference(args, cfg, emit)
     args.warmup = max(args.warmup, 3)
 
     import numpy as np
@@ -309,7 +318,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line))
+        emit(line)
     return 0
 
 

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <future>
 #include <limits>
@@ -179,7 +180,18 @@ struct TmpNode {
     int first = 0, count = 0;   // leaf when count > 0
 };
 
+// Build knobs; overridable for experiments through the environment: JPBRT_BVH_LEAF (max primitives per
+// leaf, <= 15) and JPBRT_BVH_TRAV (cost of a traversal step in primitive-test units x 100).  Defaults from
+// the B200 sweep in profiles/r01_bvh_sweep.txt: leaf 4 / cost 1.0 (Cornell traversal 11 % faster than with
+// cost 2.0, the bunny scene is flat within 3 % over leaf 2-8 x cost 0.5-4).
+static int EnvInt(const char* name, int def) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : def;
+}
+
 struct Builder {
+    int max_leaf = std::max(1, std::min(15, EnvInt("JPBRT_BVH_LEAF", kMaxLeafPrims)));
+    float trav_cost = EnvInt("JPBRT_BVH_TRAV", 100) * 0.01f;
     const std::vector<Box>& pb;
     std::vector<float> cx, cy, cz;
     std::vector<int> idx;
@@ -211,12 +223,12 @@ struct Builder {
         }
         N.box = box;
         int count = last - first;
-        if (count <= kMaxLeafPrims) {
+        if (count <= max_leaf) {
             // a small set becomes a leaf unless SAH says that splitting it is clearly cheaper
             bool leaf = true;
             if (count > 1) {
                 float best = BestSplitCost(first, last, box, cbox, nullptr, nullptr);
-                leaf = !(best + 1.0f < (float)count);
+                leaf = !(best < (float)count);
             }
             if (leaf) { N.first = first; N.count = count; return; }
         }
@@ -282,7 +294,7 @@ struct Builder {
                 accl.Add(bb[b]);
                 cl += bc[b];
                 if (cl == 0 || right_cnt[b + 1] == 0) continue;
-                float cost = 1.0f + (accl.HalfArea() * cl + right_area[b + 1] * right_cnt[b + 1]) / parent_area;
+                float cost = trav_cost + (accl.HalfArea() * cl + right_area[b + 1] * right_cnt[b + 1]) / parent_area;
                 if (cost < best) { best = cost; best_axis = a; best_bin = b; }
             }
         }

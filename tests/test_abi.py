@@ -110,3 +110,13 @@ def test_save_image_formats(pkg, tmp_path):
     hdr = (tmp_path / "img.hdr").read_bytes()
     assert hdr.startswith(b"#?RADIANCE") and hdr.endswith(bytes(4)) is False
     assert len(hdr.split(b"\n", 4)[4]) == w * h * 4
+
+
+def test_cli_binary_exists_and_prints_usage(pkg):
+    """jet-pbrt_b200/jetpbrt keeps the reference's command line (main.cc:121-124): no arguments -> usage, exit 0."""
+    import subprocess
+
+    exe = ROOT / "jet-pbrt_b200" / "jetpbrt"
+    assert exe.exists(), "run make -C jet-pbrt_b200"
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=30)
+    assert r.returncode == 0 and "pbrt.exe  sceneid   spp" in r.stdout

@@ -183,3 +183,22 @@ def test_large_scene_full_size_renders(pkg, gpu):
     assert np.isfinite(f).all() and 0.05 < f.mean() < 0.95 and st["invalid_contributions"] == 0
     assert st["samples"] == 512 * 512 * 2
     ctx.close()
+
+
+def test_cli_renders_cornell_bmp(pkg, port, gpu, tmp_path):
+    """The drop-in program: `jetpbrt sceneid spp [w h]` renders and writes <scene>_<spp>.bmp like main.cc:158-160."""
+    import subprocess
+    from pathlib import Path
+
+    exe = Path(pkg.LIB_PATH).parent / "jetpbrt"
+    r = subprocess.run([str(exe), "0", "8", "96", "96"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "current scene: cornell_box_scene" in r.stdout and "FIntegrator::Render used" in r.stdout
+    bmp = (tmp_path / "cornell_box_scene_8.bmp").read_bytes()
+    assert bmp[:2] == b"BM" and len(bmp) == 54 + 96 * 96 * 3
+    img = np.frombuffer(bmp[54:], np.uint8).reshape(96, 96, 3)[::-1, :, ::-1].astype(np.float64) / 255.0  # bottom-up BGR
+    sc = pkg.HostScene.builtin("cornell", 96, 96)
+    ref_film, _ = port.scene(sc).render(8, 8)
+    ref_img = np.floor(np.clip(ref_film, 0, 1) ** (1 / 2.2) * 255.0) / 255.0  # gamma_encoding, film.h:24
+    assert abs(img.mean() - ref_img.mean()) < 0.02
+    assert np.corrcoef(img.ravel(), ref_img.ravel())[0, 1] > 0.9
