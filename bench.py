@@ -45,6 +45,13 @@ CONFIGS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of k_extend per ray, from the committed `ncu --set full` captures
+# (profiles/r01_ncu_bunny_v2.md launch #0: 272.53 + 59.30 MB for 8,388,608 rays; profiles/r01_ncu_cornell_v2.md
+# launch #0: 268.52 + 52.58 MB for 8,388,608 rays).  The scene itself is cache-resident: DRAM only sees the
+# 32-byte ray read and the 8-byte hit write.
+NCU_EXTEND_DRAM_BYTES_PER_RAY = {"bunny": 39.55, "cornell": 38.28}
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -283,7 +290,7 @@ def main():
         ext_ms = st["ms_extend"]  # CUDA-event time of all k_extend launches of the K timed steps
         ext_bytes = st["extension_rays"] * bytes_per_ray
         achieved = ext_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
-        n_ext_launches = sc.d.max_depth + 1
+        n_ext_launches = (sc.d.max_depth + 1) * max(1, -(-spp // max(1, pool_paths(args) // (w * h))))
         line = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -301,10 +308,15 @@ def main():
                     "what": "jpbrt_reupload_scene (pinned host -> HBM) + jpbrt_render_pass + reduce + jpbrt_read_film (finalize, HBM -> pinned host)"},
             "gpu_launches": int(st["kernel_launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_extend (closest-hit BVH traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": (NCU_EXTEND_DRAM_BYTES_PER_RAY[args.config] * st["extension_rays"] / args.steps / n_ext_launches
+                                     if args.config in NCU_EXTEND_DRAM_BYTES_PER_RAY else None),
+                         "traffic_unit": "bytes per launch (ncu dram bytes per ray x rays per launch)",
+                         "algorithmic_bytes_per_launch": ext_bytes / args.steps / n_ext_launches,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_ray": bytes_per_ray, "box_tests_per_ray": box_per_ray, "prim_tests_per_ray": prim_per_ray,
                          "rays_per_step": int(st["extension_rays"] / args.steps), "kernel_ms_per_step": ext_ms / args.steps,
-                         "launches_per_step": n_ext_launches * max(1, -(-spp * w * h // max(1, pool_paths(args)))),
+                         "launches_per_step": n_ext_launches,
                          "note": "scene is %.1f MB: L1/L2-resident, so the HBM fraction is an upper-bound yardstick, not a DRAM measurement"
                                  % (st["scene_bytes"] / 1e6)},
             "stages_ms_per_step": {k[3:]: st[k] / args.steps for k in ("ms_generate", "ms_extend", "ms_shade", "ms_connect", "ms_finalize")},

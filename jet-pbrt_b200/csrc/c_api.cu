@@ -85,9 +85,10 @@ struct jpbrt_ctx {
     bool opt_stage_timing = false;
     bool opt_count_traversal = false;
     int opt_refill_min = 16;
+    int opt_trav_blocks = 6;  // resident blocks per SM the traversal kernels are compiled for: 6 (40 registers, default) or 5 (48)
     unsigned kinds_present = 0;  // bit k set: some material of the scene can build BSDF kind k
     // launch geometry
-    int grid_generate = 0, grid_extend = 0, grid_extend_c = 0, grid_logic = 0, grid_shade[4] = {0, 0, 0, 0}, grid_connect = 0, grid_connect_c = 0, grid_finalize = 0;
+    int grid_generate = 0, grid_extend = 0, grid_extend_c = 0, grid_extend6 = 0, grid_connect6 = 0, grid_logic = 0, grid_shade[4] = {0, 0, 0, 0}, grid_connect = 0, grid_connect_c = 0, grid_finalize = 0;
     // host-side accounting
     unsigned long long kernel_launches = 0;
     double ms_stage[5] = {0, 0, 0, 0, 0};
@@ -326,15 +327,17 @@ int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out
     if ((e = c->counters.Alloc((size_t)CNT_KINDS * c->counter_stride)) != cudaSuccess)
         return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)));
     c->grid_generate = occupancy_grid(c, k_generate);
-    c->grid_extend = occupancy_grid(c, k_extend<false>);
-    c->grid_extend_c = occupancy_grid(c, k_extend<true>);
+    c->grid_extend = occupancy_grid(c, k_extend<false, 5>);
+    c->grid_extend6 = occupancy_grid(c, k_extend<false, 6>);
+    c->grid_extend_c = occupancy_grid(c, k_extend<true, 5>);
     c->grid_logic = occupancy_grid(c, k_logic);
     c->grid_shade[0] = occupancy_grid(c, k_shade<0>);
     c->grid_shade[1] = occupancy_grid(c, k_shade<1>);
     c->grid_shade[2] = occupancy_grid(c, k_shade<2>);
     c->grid_shade[3] = occupancy_grid(c, k_shade<3>);
-    c->grid_connect = occupancy_grid(c, k_connect<false>);
-    c->grid_connect_c = occupancy_grid(c, k_connect<true>);
+    c->grid_connect = occupancy_grid(c, k_connect<false, 5>);
+    c->grid_connect6 = occupancy_grid(c, k_connect<false, 6>);
+    c->grid_connect_c = occupancy_grid(c, k_connect<true, 5>);
     c->grid_finalize = occupancy_grid(c, k_finalize);
     rc = jpbrt_clear_film(c);
     if (rc == 0) rc = jpbrt_reset_stats(c);
@@ -374,6 +377,7 @@ int jpbrt_set_option(jpbrt_ctx* c, const char* name, long long value) {
     if (!strcmp(name, "paths_in_flight")) { c->opt_paths_in_flight = value; return 0; }
     if (!strcmp(name, "stage_timing")) { c->opt_stage_timing = value != 0; return 0; }
     if (!strcmp(name, "count_traversal")) { c->opt_count_traversal = value != 0; return 0; }
+    if (!strcmp(name, "trav_blocks")) { c->opt_trav_blocks = (int)value; return 0; }
     if (!strcmp(name, "refill_min")) { c->opt_refill_min = (int)std::max(1ll, std::min(32ll, value)); return 0; }
     return set_error(c, JPBRT_ERR_INVALID, "unknown option '%s'", name);
 }
@@ -401,8 +405,9 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
         for (int it = 0; it < c->n_iters; ++it) {
             {
                 StageTimer t(c, 1);
-                if (count) k_extend<true><<<c->grid_extend_c, kBlock, 0, c->stream>>>(p, it);
-                else k_extend<false><<<c->grid_extend, kBlock, 0, c->stream>>>(p, it);
+                if (count) k_extend<true, 5><<<c->grid_extend_c, kBlock, 0, c->stream>>>(p, it);
+                else if (c->opt_trav_blocks >= 6) k_extend<false, 6><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
+                else k_extend<false, 5><<<c->grid_extend, kBlock, 0, c->stream>>>(p, it);
                 c->kernel_launches++;
             }
             {
@@ -419,8 +424,9 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
             }
             if (it < c->n_iters - 1 || c->hs.has_null_material) {  // no NEE at bounce == maxDepth (integrator.cc:340)
                 StageTimer t(c, 3);
-                if (count) k_connect<true><<<c->grid_connect_c, kBlock, 0, c->stream>>>(p, it);
-                else k_connect<false><<<c->grid_connect, kBlock, 0, c->stream>>>(p, it);
+                if (count) k_connect<true, 5><<<c->grid_connect_c, kBlock, 0, c->stream>>>(p, it);
+                else if (c->opt_trav_blocks >= 6) k_connect<false, 6><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
+                else k_connect<false, 5><<<c->grid_connect, kBlock, 0, c->stream>>>(p, it);
                 c->kernel_launches++;
             }
         }

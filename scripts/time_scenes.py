@@ -7,6 +7,7 @@ import __graft_entry__ as ge
 pkg = ge.load_package()
 opts = {}
 scenes = ["cornell", "bunny", "glossy"]
+scales = {"large": 1.0}
 spp = 8
 for a in sys.argv[1:]:
     if a.startswith("--scenes="): scenes = a.split("=")[1].split(",")
