@@ -273,8 +273,11 @@ def main():
             h2d = step_e2e()
         barrier()
         t0 = time.perf_counter()
+        e2e_steps_ms = []
         for _ in range(args.steps):
-            step_e2e()
+            ts = time.perf_counter()
+            step_e2e()  # ends with a device->host copy + stream synchronize on rank 0
+            e2e_steps_ms.append(1e3 * (time.perf_counter() - ts))
         barrier()
         e2e_s = time.perf_counter() - t0
         t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
@@ -304,7 +307,7 @@ def main():
             "mrays_per_s": rays_per_step_rank * world / (ms_per_step * 1e-3) / 1e6,
             "rays_per_sample": rays_per_step_rank / (w * h * spp),
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(nfloats * 4),
-                    "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "ms_each_step": [round(x, 2) for x in e2e_steps_ms],
                     "what": "jpbrt_reupload_scene (pinned host -> HBM) + jpbrt_render_pass + reduce + jpbrt_read_film (finalize, HBM -> pinned host)"},
             "gpu_launches": int(st["kernel_launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_extend (closest-hit BVH traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",

