@@ -293,7 +293,8 @@ def main():
         ext_ms = st["ms_extend"]  # CUDA-event time of all k_extend launches of the K timed steps
         ext_bytes = st["extension_rays"] * bytes_per_ray
         achieved = ext_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
-        n_ext_launches = (sc.d.max_depth + 1) * max(1, -(-spp // max(1, pool_paths(args) // (w * h))))
+        n_waves = max(1, -(-spp // max(1, int(st["paths_in_flight"]) // (w * h))))  # wavefronts per render_pass
+        n_ext_launches = (sc.d.max_depth + 1) * n_waves
         line = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -301,6 +302,7 @@ def main():
             "config": {"workload": f"{args.config}: {desc}", "width": w, "height": h, "spp_per_gpu_per_step": spp, "spp_total": spp_total,
                        "max_depth": sc.d.max_depth, "n_primitives": sc.d.n_primitives, "n_lights": sc.d.n_lights,
                        "parallelism": f"sample-partition x{world}, scene replicated, one NCCL reduce of the f32 film per step",
+                       "paths_in_flight": int(st["paths_in_flight"]),
                        "l2": f"no explicit flush: each step streams {st_bytes(ctx, sc, spp, w, h) / 1e6:.0f} MB of wavefront state (> 126 MB L2); "
                              "the scene arrays are legitimately cache-resident across the step",
                        "seed": seed},
@@ -335,10 +337,6 @@ def main():
     if line is not None:
         emit(line)
     return 0
-
-
-def pool_paths(args):
-    return args.paths_in_flight if args.paths_in_flight else (1 << 23)
 
 
 def st_bytes(ctx, sc, spp, w, h):

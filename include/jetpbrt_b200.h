@@ -103,6 +103,7 @@ typedef struct jpbrt_stats {
     double   ms_generate, ms_extend, ms_shade, ms_connect, ms_finalize; /* with option "stage_timing" = 1 */
     uint64_t n_nodes, n_prim_slots, scene_bytes;
     double   bvh_build_seconds;
+    uint64_t paths_in_flight;  /* capacity of the path pool (paths per wavefront), 0 before the first pass */
 } jpbrt_stats;
 int jpbrt_get_stats(jpbrt_ctx* ctx, jpbrt_stats* out);
 

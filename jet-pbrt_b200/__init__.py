@@ -64,7 +64,7 @@ class Stats(C.Structure):
                 ("ms_generate", C.c_double), ("ms_extend", C.c_double), ("ms_shade", C.c_double),
                 ("ms_connect", C.c_double), ("ms_finalize", C.c_double),
                 ("n_nodes", C.c_uint64), ("n_prim_slots", C.c_uint64), ("scene_bytes", C.c_uint64),
-                ("bvh_build_seconds", C.c_double)]
+                ("bvh_build_seconds", C.c_double), ("paths_in_flight", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

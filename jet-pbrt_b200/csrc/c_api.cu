@@ -182,14 +182,29 @@ int upload_arrays(jpbrt_ctx* c, size_t* bytes) {
     return 0;
 }
 
+// Bytes of wavefront state per path in flight: 2 x 48 B ray records + 8 B hit + 4 kind-queue indices + one
+// 48 B shadow slot per non-black light.
+size_t bytes_per_path(int n_nee_lights) { return 2 * 48 + 8 + 4 * NUM_KINDS + (size_t)48 * std::max(1, n_nee_lights); }
+
 int ensure_pool(jpbrt_ctx* c) {
     const long long npix = (long long)c->hs.width * c->hs.height;
-    long long want = c->opt_paths_in_flight > 0 ? c->opt_paths_in_flight : (1ll << 23);
+    const int n_lights = std::max(1, (int)c->hs.nee_lights.size());  // one shadow slot per (vertex, non-black light)
+    // Default pool: 2^25 paths (measured on B200: 8 M -> 32 M paths in flight is +13 % on the bunny scene, +6 % on
+    // Cornell: longer launches, shorter tails), but never more than a quarter of the device's free memory.
+    long long want = c->opt_paths_in_flight > 0 ? c->opt_paths_in_flight : (1ll << 25);
+    if (c->opt_paths_in_flight <= 0) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && c->paths_in_flight == 0) {
+            long long fit = (long long)(free_b / 4 / bytes_per_path(n_lights));
+            want = std::min(want, std::max(fit, npix));
+        } else if (c->paths_in_flight > 0) {
+            want = c->paths_in_flight;  // keep what was sized at the first pass
+        }
+    }
     // whole samples only: the pool holds k full-frame samples
     long long k = std::max(1ll, want / npix);
     long long cap = k * npix;
     if (cap > 0x7fff0000ll) return set_error(c, JPBRT_ERR_UNSUPPORTED, "film too large for one wavefront (%lld pixels)", npix);
-    int n_lights = std::max(1, (int)c->hs.nee_lights.size());  // one shadow slot per (vertex, non-black light)
     long long shadow_cap = cap * n_lights;
     if (shadow_cap > 0x7fff0000ll) {  // keep queue indices in int range
         k = std::max(1ll, 0x7fff0000ll / (npix * n_lights));
@@ -392,7 +407,10 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
     int rc = ensure_pool(c);
     if (rc != 0) return rc;
     const long long npix = (long long)c->hs.width * c->hs.height;
-    const int chunk = (int)(c->paths_in_flight / npix);
+    const int chunk_max = (int)(c->paths_in_flight / npix);
+    // equal wavefronts: 50 spp with room for 32 run as 25 + 25, not 32 + 18 (short wavefronts are less efficient)
+    const int n_waves = (sample_count + chunk_max - 1) / std::max(1, chunk_max);
+    const int chunk = n_waves > 0 ? (sample_count + n_waves - 1) / n_waves : chunk_max;
     const bool count = c->opt_count_traversal;
     for (int done = 0; done < sample_count;) {
         const int spp = std::min(chunk, sample_count - done);
@@ -510,6 +528,7 @@ int jpbrt_get_stats(jpbrt_ctx* c, jpbrt_stats* out) {
     out->n_prim_slots = c->dsc.n_slots;
     out->scene_bytes = c->hs.Bytes();
     out->bvh_build_seconds = c->hs.bvh_build_seconds;
+    out->paths_in_flight = (uint64_t)c->paths_in_flight;
     return 0;
 }
 

@@ -202,3 +202,69 @@ def test_cli_renders_cornell_bmp(pkg, port, gpu, tmp_path):
     ref_img = np.floor(np.clip(ref_film, 0, 1) ** (1 / 2.2) * 255.0) / 255.0  # gamma_encoding, film.h:24
     assert abs(img.mean() - ref_img.mean()) < 0.02
     assert np.corrcoef(img.ravel(), ref_img.ravel())[0, 1] > 0.9
+
+
+def test_edge_cases_small_and_ragged(pkg, port, gpu):
+    """Empty and ragged inputs, extreme parameters: 1x1 and non-square films, depth 0 and 1, zero-length ray sets,
+    ray counts that are not a multiple of the warp size, zero-sample passes, two contexts alive at once."""
+    # zero-length and ragged unit inputs
+    sc = pkg.HostScene.builtin("cornell", 37, 23)   # odd, non-square film
+    ctx = pkg.Context(sc)
+    ps = port.scene(sc)
+    for n in (0, 1, 31, 33, 1000):
+        pf = np.random.default_rng(n).uniform(0, 23, (n, 2)).astype(np.float32)
+        o, d = ctx.unit_generate_rays(pf)
+        assert o.shape == (n, 3)
+        if n:
+            rays = np.concatenate([o, d, np.full((n, 1), 0.001, np.float32), np.full((n, 1), np.inf, np.float32)], 1)
+            for a, b in zip(ctx.unit_scene_intersect(rays), ps.intersect(rays)):
+                assert np.array_equal(a, b)
+    ctx.render_pass(0, 0, seed=1)                   # zero samples: a no-op
+    assert not ctx.read_film(finalize=False).any()
+    ctx.render_pass(0, 3, seed=1)
+    g = ctx.read_film(finalize=False)
+    c, _ = ps.render_counter(0, 3, 1, numthreads=4)
+    assert g.shape == (23, 37, 3) and abs(g.mean() - c.mean()) <= 5e-3 * c.mean()
+    # a second context on the same device, different depth, while the first is alive
+    for depth in (0, 1):
+        sc2 = pkg.HostScene.builtin("cornell", 16, 16)
+        sc2.set_max_depth(depth)
+        c2 = pkg.Context(sc2)
+        c2.render_pass(0, 4, seed=3)
+        g2 = c2.read_film(finalize=False)
+        o2, _ = port.scene(sc2).render_counter(0, 4, 3, numthreads=2)
+        np.testing.assert_allclose(g2, o2, rtol=1e-4, atol=1e-5)   # depth 0: emission only; depth 1: one bounce of NEE
+        st = c2.stats()
+        assert st["shadow_rays"] == 0 if depth == 0 else st["shadow_rays"] > 0
+        c2.close()
+    ctx.close()
+    # 1 x 1 film, a single sphere under an environment light only
+    cam = pkg.Camera((0, 0, 5), (0, 0, -1), (0, 1, 0), 40.0, 1, 1)
+    z3 = (0.0, 0.0, 0.0)
+    one = pkg.HostScene.from_arrays(cam, [pkg.Shape(pkg.SHAPE_SPHERE, 0, ((0, 0, 0), (1.0, 0, 0), z3, z3))],
+                                    [pkg.Material(pkg.MAT_MATTE, 0, (.8, .8, .8), z3, 0, 0)],
+                                    [pkg.Light(pkg.LIGHT_ENVIRONMENT, -1, (1, 1, 1), z3, z3)], [pkg.Primitive(0, 0, -1)], max_depth=3)
+    c1 = pkg.Context(one)
+    c1.render_pass(0, 64, seed=5)
+    g1 = c1.read_film(finalize=False)
+    o1, _ = port.scene(one).render_counter(0, 64, 5, numthreads=1)
+    assert g1.shape == (1, 1, 3) and np.isfinite(g1).all()
+    np.testing.assert_allclose(g1, o1, rtol=2e-2)
+    c1.close()
+    # invalid arguments are errors, not crashes
+    with pytest.raises(pkg.JpbrtError):
+        pkg.Context(sc, device=99)
+    ctx = pkg.Context(sc)
+    with pytest.raises(pkg.JpbrtError):
+        ctx.render_pass(-1, 4)
+    with pytest.raises(pkg.JpbrtError):
+        ctx.render_pass(0, 1 << 25)
+    with pytest.raises(pkg.JpbrtError):
+        ctx.set_option("no_such_option", 1)
+    ctx.close()
+
+
+def test_smoke_entry_point(gpu):
+    import __graft_entry__ as ge
+
+    ge.smoke()
