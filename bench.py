@@ -258,10 +258,14 @@ def main():
         rays_per_step_rank = (st["extension_rays"] + st["shadow_rays"]) / args.steps
 
         # ---- e2e: host buffers in, host film out, every step ----
+        queue_ms = []
+
         def step_e2e():
+            tq = time.perf_counter()
             nbytes = ctx.reupload_scene()
             ctx.clear_film()
             ctx.render_pass(begin, count, seed)
+            queue_ms.append(1e3 * (time.perf_counter() - tq))  # host time to queue the step's copies and launches
             multi_gpu.reduce_film(film, ddist, 0)
             if rank == 0:
                 pkg._check(pkg.lib.jpbrt_read_film(ctx._ctx, pkg.C.cast(host_film.data_ptr(), pkg.C.POINTER(pkg.C.c_float)), spp_total, 1), ctx._ctx)
@@ -272,6 +276,10 @@ def main():
         for _ in range(2):
             h2d = step_e2e()
         barrier()
+        import gc
+        gc.collect()
+        gc.disable()  # no collector pauses inside the timed region
+        queue_ms.clear()
         t0 = time.perf_counter()
         e2e_steps_ms = []
         for _ in range(args.steps):
@@ -280,6 +288,7 @@ def main():
             e2e_steps_ms.append(1e3 * (time.perf_counter() - ts))
         barrier()
         e2e_s = time.perf_counter() - t0
+        gc.enable()
         t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -310,6 +319,7 @@ def main():
             "rays_per_sample": rays_per_step_rank / (w * h * spp),
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(nfloats * 4),
                     "ms_per_step": 1e3 * e2e_s / args.steps, "ms_each_step": [round(x, 2) for x in e2e_steps_ms],
+                    "host_queue_ms_each_step": [round(x, 2) for x in queue_ms],
                     "what": "jpbrt_reupload_scene (pinned host -> HBM) + jpbrt_render_pass + reduce + jpbrt_read_film (finalize, HBM -> pinned host)"},
             "gpu_launches": int(st["kernel_launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_extend (closest-hit BVH traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -81,6 +81,13 @@ struct jpbrt_ctx {
     DevBuf<float> film;
     DevBuf<float> film_final;  // Clamp01(mean) staging buffer of jpbrt_read_film (no cudaMalloc/cudaFree per call)
     DevBuf<unsigned long long> dstats;
+    DevBuf<PassArgs> pass_args;
+    // one wavefront (generate + all iterations) captured as a CUDA graph; rebuilt when an option that changes the
+    // launch sequence changes
+    cudaGraphExec_t wave_graph = nullptr;
+    int wave_graph_key = -1;
+    unsigned long long wave_graph_launches = 0;
+    bool opt_use_graph = true;
     // options
     long long opt_paths_in_flight = 0;
     bool opt_stage_timing = false;
@@ -213,6 +220,7 @@ int ensure_pool(jpbrt_ctx* c) {
         if (shadow_cap > 0x7fff0000ll) return set_error(c, JPBRT_ERR_UNSUPPORTED, "pixels x lights too large for one wavefront");
     }
     if (cap == c->paths_in_flight) return 0;
+    if (c->wave_graph) { cudaGraphExecDestroy(c->wave_graph); c->wave_graph = nullptr; }  // it holds the old buffers' addresses
     for (int b = 0; b < 2; ++b) {
         CU_CHECK(c, c->ray_o[b].Alloc(cap));
         CU_CHECK(c, c->ray_d[b].Alloc(cap));
@@ -227,7 +235,7 @@ int ensure_pool(jpbrt_ctx* c) {
     return 0;
 }
 
-WfParams make_params(jpbrt_ctx* c, int sample_begin, uint64_t seed) {
+WfParams make_params(jpbrt_ctx* c) {
     WfParams p{};
     p.sc = c->dsc;
     for (int b = 0; b < 2; ++b) { p.ray_o[b] = c->ray_o[b].ptr; p.ray_d[b] = c->ray_d[b].ptr; p.ray_b[b] = c->ray_b[b].ptr; }
@@ -241,9 +249,7 @@ WfParams make_params(jpbrt_ctx* c, int sample_begin, uint64_t seed) {
     p.counter_stride = c->counter_stride;
     p.film = c->film.ptr;
     p.stats = c->dstats.ptr;
-    p.key.k0 = (uint32_t)seed;
-    p.key.k1 = (uint32_t)(seed >> 32);
-    p.sample_begin = sample_begin;
+    p.args = c->pass_args.ptr;
     p.npix = c->hs.width * c->hs.height;
     p.blocks_per_bounce = rng_blocks_per_bounce(c->dsc.n_lights);
     p.shadow_capacity = (int)std::min<size_t>(c->sh_o.count, 0x7fffffff);
@@ -309,7 +315,8 @@ int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out
         (e = c->inf_lights.Alloc(hs.inf_lights.size())) != cudaSuccess || (e = c->prim_slot.Alloc(hs.prim_slot.size())) != cudaSuccess ||
         (e = c->slot_frame.Alloc(hs.slot_frame.size())) != cudaSuccess || (e = c->nee_lights.Alloc(hs.nee_lights.size())) != cudaSuccess ||
         (e = c->film.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess ||
-        (e = c->film_final.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess || (e = c->dstats.Alloc(ST_COUNT)) != cudaSuccess)
+        (e = c->film_final.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess || (e = c->dstats.Alloc(ST_COUNT)) != cudaSuccess ||
+        (e = c->pass_args.Alloc(1)) != cudaSuccess)
         return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)));
     pin_vector(c, hs.nodes); pin_vector(c, hs.slots); pin_vector(c, hs.slot_nrm); pin_vector(c, hs.slot_ml);
     pin_vector(c, hs.materials); pin_vector(c, hs.lights); pin_vector(c, hs.inf_lights); pin_vector(c, hs.prim_slot);
@@ -395,8 +402,54 @@ int jpbrt_set_option(jpbrt_ctx* c, const char* name, long long value) {
     if (!strcmp(name, "stage_timing")) { c->opt_stage_timing = value != 0; return 0; }
     if (!strcmp(name, "count_traversal")) { c->opt_count_traversal = value != 0; return 0; }
     if (!strcmp(name, "trav_blocks")) { c->opt_trav_blocks = (int)value; return 0; }
+    if (!strcmp(name, "use_graph")) { c->opt_use_graph = value != 0; return 0; }
     if (!strcmp(name, "refill_min")) { c->opt_refill_min = (int)std::max(1ll, std::min(32ll, value)); return 0; }
     return set_error(c, JPBRT_ERR_INVALID, "unknown option '%s'", name);
+}
+
+// Queue (or capture) the launches of ONE wavefront on the context's stream: generate, then for every bounce
+// extend -> logic -> shade<kind>... -> connect.  Everything that differs between wavefronts is in PassArgs.
+static int queue_wavefront(jpbrt_ctx* c, bool count) {
+    WfParams p = make_params(c);
+    CU_CHECK(c, cudaMemsetAsync(c->counters.ptr, 0, c->counters.count * sizeof(int), c->stream));
+    {
+        StageTimer t(c, 0);
+        k_generate<<<c->grid_generate, kBlock, 0, c->stream>>>(p);
+        c->kernel_launches++;
+    }
+    for (int it = 0; it < c->n_iters; ++it) {
+        {
+            StageTimer t(c, 1);
+            if (count) k_extend<true, 5><<<c->grid_extend_c, kBlock, 0, c->stream>>>(p, it);
+            else if (c->opt_trav_blocks >= 6) k_extend<false, 6><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
+            else k_extend<false, 5><<<c->grid_extend, kBlock, 0, c->stream>>>(p, it);
+            c->kernel_launches++;
+        }
+        {
+            StageTimer t(c, 2);
+            k_logic<<<c->grid_logic, kBlock, 0, c->stream>>>(p, it);
+            if (it < c->n_iters - 1 || c->hs.has_null_material) {  // at bounce == maxDepth nothing is left to shade
+                if (c->kinds_present & 1) k_shade<0><<<c->grid_shade[0], kBlock, 0, c->stream>>>(p, it);
+                if (c->kinds_present & 2) k_shade<1><<<c->grid_shade[1], kBlock, 0, c->stream>>>(p, it);
+                if (c->kinds_present & 4) k_shade<2><<<c->grid_shade[2], kBlock, 0, c->stream>>>(p, it);
+                if (c->kinds_present & 8) k_shade<3><<<c->grid_shade[3], kBlock, 0, c->stream>>>(p, it);
+                c->kernel_launches += __builtin_popcount(c->kinds_present);
+            }
+            c->kernel_launches++;
+        }
+        if (it < c->n_iters - 1 || c->hs.has_null_material) {  // no NEE at bounce == maxDepth (integrator.cc:340)
+            StageTimer t(c, 3);
+            if (count) k_connect<true, 5><<<c->grid_connect_c, kBlock, 0, c->stream>>>(p, it);
+            else if (c->opt_trav_blocks >= 6) k_connect<false, 6><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
+            else k_connect<false, 5><<<c->grid_connect, kBlock, 0, c->stream>>>(p, it);
+            c->kernel_launches++;
+        }
+    }
+    if (c->hs.has_null_material) {
+        k_count_dropped<<<1, 32, 0, c->stream>>>(p, c->n_iters);
+        c->kernel_launches++;
+    }
+    return 0;
 }
 
 int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t seed) {
@@ -412,47 +465,40 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
     const int n_waves = (sample_count + chunk_max - 1) / std::max(1, chunk_max);
     const int chunk = n_waves > 0 ? (sample_count + n_waves - 1) / n_waves : chunk_max;
     const bool count = c->opt_count_traversal;
+    // Graph replay needs a launch sequence that never changes: no per-launch events, no counting variant.
+    const bool use_graph = c->opt_use_graph && !c->opt_stage_timing && !count;
+    const int graph_key = c->opt_trav_blocks * 64 + c->opt_refill_min;
+    if (use_graph && (c->wave_graph == nullptr || c->wave_graph_key != graph_key)) {
+        if (c->wave_graph) { cudaGraphExecDestroy(c->wave_graph); c->wave_graph = nullptr; }
+        cudaGraph_t graph = nullptr;
+        CU_CHECK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const unsigned long long before = c->kernel_launches;
+        int qrc = queue_wavefront(c, false);
+        cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+        c->wave_graph_launches = c->kernel_launches - before;
+        c->kernel_launches = before;
+        if (qrc != 0) { if (graph) cudaGraphDestroy(graph); return qrc; }
+        if (ce != cudaSuccess) return set_error(c, JPBRT_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&c->wave_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { c->wave_graph = nullptr; return set_error(c, JPBRT_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
+        c->wave_graph_key = graph_key;
+    }
     for (int done = 0; done < sample_count;) {
         const int spp = std::min(chunk, sample_count - done);
-        const int n_paths = (int)(npix * spp);
-        WfParams p = make_params(c, sample_begin + done, seed);
-        CU_CHECK(c, cudaMemsetAsync(c->counters.ptr, 0, c->counters.count * sizeof(int), c->stream));
-        {
-            StageTimer t(c, 0);
-            k_generate<<<c->grid_generate, kBlock, 0, c->stream>>>(p, n_paths);
-            c->kernel_launches++;
-        }
-        for (int it = 0; it < c->n_iters; ++it) {
-            {
-                StageTimer t(c, 1);
-                if (count) k_extend<true, 5><<<c->grid_extend_c, kBlock, 0, c->stream>>>(p, it);
-                else if (c->opt_trav_blocks >= 6) k_extend<false, 6><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
-                else k_extend<false, 5><<<c->grid_extend, kBlock, 0, c->stream>>>(p, it);
-                c->kernel_launches++;
-            }
-            {
-                StageTimer t(c, 2);
-                k_logic<<<c->grid_logic, kBlock, 0, c->stream>>>(p, it);
-                if (it < c->n_iters - 1 || c->hs.has_null_material) {  // at bounce == maxDepth nothing is left to shade
-                    if (c->kinds_present & 1) k_shade<0><<<c->grid_shade[0], kBlock, 0, c->stream>>>(p, it);
-                    if (c->kinds_present & 2) k_shade<1><<<c->grid_shade[1], kBlock, 0, c->stream>>>(p, it);
-                    if (c->kinds_present & 4) k_shade<2><<<c->grid_shade[2], kBlock, 0, c->stream>>>(p, it);
-                    if (c->kinds_present & 8) k_shade<3><<<c->grid_shade[3], kBlock, 0, c->stream>>>(p, it);
-                    c->kernel_launches += __builtin_popcount(c->kinds_present);
-                }
-                c->kernel_launches++;
-            }
-            if (it < c->n_iters - 1 || c->hs.has_null_material) {  // no NEE at bounce == maxDepth (integrator.cc:340)
-                StageTimer t(c, 3);
-                if (count) k_connect<true, 5><<<c->grid_connect_c, kBlock, 0, c->stream>>>(p, it);
-                else if (c->opt_trav_blocks >= 6) k_connect<false, 6><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
-                else k_connect<false, 5><<<c->grid_connect, kBlock, 0, c->stream>>>(p, it);
-                c->kernel_launches++;
-            }
-        }
-        if (c->hs.has_null_material) {
-            k_count_dropped<<<1, 32, 0, c->stream>>>(p, c->n_iters);
-            c->kernel_launches++;
+        PassArgs a;
+        a.k0 = (uint32_t)seed;
+        a.k1 = (uint32_t)(seed >> 32);
+        a.sample_begin = sample_begin + done;
+        a.n_paths = (int)(npix * spp);
+        k_set_args<<<1, 1, 0, c->stream>>>(c->pass_args.ptr, a);
+        c->kernel_launches++;
+        if (use_graph) {
+            CU_CHECK(c, cudaGraphLaunch(c->wave_graph, c->stream));
+            c->kernel_launches += c->wave_graph_launches;
+        } else {
+            int qrc = queue_wavefront(c, count);
+            if (qrc != 0) return qrc;
         }
         CU_CHECK(c, cudaGetLastError());
         done += spp;
@@ -538,6 +584,7 @@ void jpbrt_destroy(jpbrt_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& ev : c->pending_events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto& ev : c->free_events) cudaEventDestroy(ev);
+    if (c->wave_graph) cudaGraphExecDestroy(c->wave_graph);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (void* p : c->pinned) cudaHostUnregister(p);
     delete c;

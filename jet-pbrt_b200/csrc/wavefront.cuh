@@ -12,7 +12,7 @@
 // Queues ARE the records: survivors of `shade` are written contiguously into the other half of a
 // ping-pong buffer at positions handed out by one warp-aggregated atomicAdd per warp
 // (__ballot_sync + __popc), so every stage reads and writes fully coalesced 16-byte lanes.
-// Shadow rays fan out into their own queue of 48-byte records (origin+tmax, dir+pixel, contribution).
+// Shadow rays go to static 48-byte slots (origin+tmax, dir+pixel, contribution), one per (vertex, light).
 // All radiance goes straight to the float film with RED.ADD.F32 (no per-path radiance state).
 //
 // Kernels are persistent: grid = SMs x resident blocks, each warp pulls batches of 32 queue items
@@ -32,11 +32,23 @@
 namespace jpbrt {
 
 // per-iteration device counters: queue lengths and the work cursors of the persistent kernels
-enum { CNT_RAYS = 0, CNT_SHADOW = 1, CNT_W_EXTEND = 2, CNT_W_SHADE = 3, CNT_W_CONNECT = 4,
+enum { CNT_RAYS = 0, CNT_UNUSED = 1, CNT_W_EXTEND = 2, CNT_W_SHADE = 3, CNT_W_CONNECT = 4,
        CNT_Q0 = 5 /* 4 kinds */, CNT_WQ0 = 9 /* 4 kinds */, CNT_KINDS = 13 };
 enum {
     ST_SAMPLES = 0, ST_EXT_RAYS, ST_SHADOW_RAYS, ST_VERTICES, ST_BOX, ST_PRIM, ST_SH_BOX, ST_SH_PRIM, ST_INVALID, ST_DROPPED, ST_COUNT
 };
+
+// The only values that change from one wavefront to the next.  They live in device memory (written by
+// k_set_args) so that the launch sequence of a wavefront is IDENTICAL every time and can be replayed as one
+// CUDA graph: a step is then a single host call instead of ~90 launches (bench.py measured the host taking
+// 10-70 ms to queue a step when the box's CPUs are busy).
+struct PassArgs {
+    uint32_t k0, k1;   // sampler key (seed)
+    int sample_begin;  // first sample index of this wavefront
+    int n_paths;       // pixels x samples of this wavefront
+};
+
+__global__ void k_set_args(PassArgs* dst, PassArgs v) { *dst = v; }
 
 struct WfParams {
     DevScene sc;
@@ -53,8 +65,7 @@ struct WfParams {
     int counter_stride;
     float* film;
     unsigned long long* stats;
-    RngKey key;
-    int sample_begin;
+    const PassArgs* args;
     int npix;
     int blocks_per_bounce;
     int shadow_capacity;
@@ -65,24 +76,6 @@ constexpr int kBlock = 256;
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-
-// One atomicAdd per warp hands out `32` consecutive work items.
-__device__ __forceinline__ int warp_fetch(int* counter) {
-    int base = 0;
-    if (lane_id() == 0) base = atomicAdd(counter, 32);
-    return __shfl_sync(kFull, base, 0);
-}
-
-// Append for whichever lanes are currently converged here (NEE fan-out inside divergent code).
-__device__ __forceinline__ int coalesced_append(int* counter) {
-    const unsigned active = __activemask();
-    const int leader = __ffs(active) - 1;
-    const int rank = __popc(active & ((1u << lane_id()) - 1));
-    int base = 0;
-    if (lane_id() == leader) base = atomicAdd(counter, __popc(active));
-    base = __shfl_sync(active, base, leader);
-    return base + rank;
-}
 
 // accumulate: film[pixel] += c   (radiance sums; FFilm::AddColor happens at finalize)
 __device__ __forceinline__ void film_add(const WfParams& p, int pixel, const f3& c) {
@@ -104,8 +97,11 @@ __device__ __forceinline__ void warp_stat_add(unsigned long long* dst, unsigned 
 // ---------------------------------------------------------------------------------------------
 // generate
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_generate(const __grid_constant__ WfParams p, int n_paths) {
+__global__ void __launch_bounds__(kBlock) k_generate(const __grid_constant__ WfParams p) {
     const DevCamera& cam = p.sc.cam;
+    const PassArgs a = *p.args;
+    const RngKey key{a.k0, a.k1};
+    const int n_paths = a.n_paths;
     const f3 pos = mk3(cam.pos[0], cam.pos[1], cam.pos[2]);
     const f3 front = mk3(cam.front[0], cam.front[1], cam.front[2]);
     const f3 right = mk3(cam.right[0], cam.right[1], cam.right[2]);
@@ -113,9 +109,9 @@ __global__ void __launch_bounds__(kBlock) k_generate(const __grid_constant__ WfP
     const int W = p.sc.width;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_paths; i += gridDim.x * blockDim.x) {
         const int pixel = i % p.npix;
-        const int sample = p.sample_begin + i / p.npix;
+        const int sample = a.sample_begin + i / p.npix;
         const int x = pixel % W, y = pixel / W;
-        const float4 u = rng_block(p.key, (uint32_t)pixel, (uint32_t)sample, 0u);
+        const float4 u = rng_block(key, (uint32_t)pixel, (uint32_t)sample, 0u);
         const float fx = (float)x + u.x, fy = (float)y + u.y;  // sampler.h:152
         const f3 dir = front + right * (fx / cam.res_x - 0.5f) + up * (0.5f - fy / cam.res_y);  // camera.h:54-55
         const f3 d = normalize(dir);
@@ -264,6 +260,7 @@ __global__ void __launch_bounds__(kBlock) k_logic(const __grid_constant__ WfPara
     int* next_count = p.counters + CNT_RAYS * p.counter_stride + it + 1;
     const int buf = it & 1, nbuf = buf ^ 1;
     const int nchunks = chunks_for(n);
+    const RngKey key{p.args->k0, p.args->k1};
     for (;;) {
         const int base = warp_fetch_n(work, 32 * nchunks);
         if (base >= n) break;
@@ -318,7 +315,7 @@ __global__ void __launch_bounds__(kBlock) k_logic(const __grid_constant__ WfPara
                         if (type == MAT_PLASTIC) {  // the lobe pick is the first number of the bounce's block (material.cc:14)
                             const int pixel = __float_as_int(p.ray_o[buf][i].w);
                             const uint32_t blk = 1u + (uint32_t)bounce * (uint32_t)p.blocks_per_bounce;
-                            const float4 u0 = rng_block(p.key, (uint32_t)pixel, (uint32_t)(fl & 0xffffff), blk);
+                            const float4 u0 = rng_block(key, (uint32_t)pixel, (uint32_t)(fl & 0xffffff), blk);
                             kind = (u0.x < ldg4(mat + 2).y) ? KIND_LAMBERT : KIND_MF_DIELECTRIC;
                         } else {
                             kind = type == MAT_MATTE ? KIND_LAMBERT : type == MAT_METAL ? KIND_MF_CONDUCTOR : KIND_DELTA;
@@ -375,6 +372,7 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
         if (k < KIND) kind_base += p.counters[(CNT_Q0 + k) * p.counter_stride + it];
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.stats + ST_VERTICES, (unsigned long long)n);
     const int nchunks = chunks_for(n);
+    const RngKey key{p.args->k0, p.args->k1};
     for (;;) {
         const int fetch_base = warp_fetch_n(work, 32 * nchunks);
         if (fetch_base >= n) break;
@@ -402,7 +400,7 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
                 const f3 wo = -d;
                 const int2 ml = __ldg(reinterpret_cast<const int2*>(sc.slot_ml) + slot);
                 const uint32_t blk = 1u + (uint32_t)bounce * (uint32_t)p.blocks_per_bounce;
-                const float4 u0 = rng_block(p.key, (uint32_t)pixel, (uint32_t)sample, blk);
+                const float4 u0 = rng_block(key, (uint32_t)pixel, (uint32_t)sample, blk);
                 Bsdf bsdf = make_bsdf(sc.materials + (size_t)ml.x * kMaterialStride, u0.x);
                 if (KIND == KIND_LAMBERT) bsdf.kind = K_LAMBERT;  // known at compile time: the other BSDFs' code is pruned
                 if (KIND == KIND_MF_CONDUCTOR) bsdf.kind = K_MICROFACET_CONDUCTOR;
@@ -417,7 +415,7 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
                         const int j = __ldg(sc.nee_lights + k);
                         if ((j >> 1) != lu_block) {
                             lu_block = j >> 1;
-                            lu = rng_block(p.key, (uint32_t)pixel, (uint32_t)sample, blk + 1u + (uint32_t)lu_block);
+                            lu = rng_block(key, (uint32_t)pixel, (uint32_t)sample, blk + 1u + (uint32_t)lu_block);
                         }
                         const float ux = (j & 1) ? lu.z : lu.x, uy = (j & 1) ? lu.w : lu.y;
                         const long long si = (long long)k * n_vertices + kind_base + qi;  // this (vertex, light)'s slot
