@@ -267,3 +267,22 @@ def test_sphere_and_delta_lights(pkg, checker, gpu):
     for a, b in zip(ctx.unit_scene_intersect(rays), ks.intersect(rays)):
         assert np.array_equal(a, b)
     ctx.close()
+
+
+def test_full_size_five_million_triangle_scene_hits(pkg, checker, port, gpu):
+    """BASELINE config C3 at FULL size (4,999,001 triangles): closest hits and occlusion against the checker
+    (its BVH is the reference's own median-split tree, built here in ~12 s)."""
+    sc = pkg.HostScene.builtin("large", 256, 256, 1.0)
+    ctx, ks, ps = pkg.Context(sc), checker.scene(sc), port.scene(sc)
+    rng = np.random.default_rng(31337)
+    report = []
+    raysA, _ = common.camera_rays(ks, rng, 1 << 15, 256, 256)
+    check_hits("large", sc, "A:camera", ctx, ks, ps, raysA, report)
+    raysB, P, N = common.secondary_rays(ks, raysA, rng)
+    check_hits("large", sc, "B:surface", ctx, ks, ps, raysB, report)
+    tgt = (P + raysB[:, 3:6] * rng.uniform(0.5, 1500, (len(P), 1))).astype(np.float32)
+    og, ok = ctx.unit_scene_occluded(P, tgt), ks.occluded(P, tgt)
+    report.append(("large-full", "occluded", len(P), int((og != ok).sum())))
+    assert (og != ok).mean() <= 2e-2
+    print("flagged grazing cases (full-size C3):", report)
+    ctx.close()
