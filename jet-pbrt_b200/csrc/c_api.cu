@@ -68,7 +68,7 @@ struct jpbrt_ctx {
     // scene on the device
     DevBuf<Float4> nodes, slots, slot_nrm, materials, lights, slot_frame;
     DevBuf<Int2> slot_ml;
-    DevBuf<int> inf_lights, prim_slot, nee_lights;
+    DevBuf<int> inf_lights, prim_slot, nee_lights, pixel_order;
     DevScene dsc{};
     // wavefront state
     long long paths_in_flight = 0;  // capacity of the path pool
@@ -314,6 +314,7 @@ int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out
         (e = c->materials.Alloc(hs.materials.size())) != cudaSuccess || (e = c->lights.Alloc(hs.lights.size())) != cudaSuccess ||
         (e = c->inf_lights.Alloc(hs.inf_lights.size())) != cudaSuccess || (e = c->prim_slot.Alloc(hs.prim_slot.size())) != cudaSuccess ||
         (e = c->slot_frame.Alloc(hs.slot_frame.size())) != cudaSuccess || (e = c->nee_lights.Alloc(hs.nee_lights.size())) != cudaSuccess ||
+        (e = c->pixel_order.Alloc(hs.pixel_order.size())) != cudaSuccess ||
         (e = c->film.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess ||
         (e = c->film_final.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess || (e = c->dstats.Alloc(ST_COUNT)) != cudaSuccess ||
         (e = c->pass_args.Alloc(1)) != cudaSuccess)
@@ -322,8 +323,11 @@ int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out
     pin_vector(c, hs.materials); pin_vector(c, hs.lights); pin_vector(c, hs.inf_lights); pin_vector(c, hs.prim_slot);
     pin_vector(c, hs.slot_frame); pin_vector(c, hs.nee_lights);
     rc = upload_arrays(c, nullptr);
+    if (rc == 0 && c->pixel_order.Upload(hs.pixel_order.data(), hs.pixel_order.size(), c->stream) != cudaSuccess)
+        rc = set_error(c, JPBRT_ERR_CUDA, "pixel order upload failed");
     if (rc != 0) { g_last_error = c->error; return fail(rc); }
     DevScene& d = c->dsc;
+    d.pixel_order = c->pixel_order.ptr;
     d.nodes = c->nodes.ptr; d.slots = c->slots.ptr; d.slot_nrm = c->slot_nrm.ptr; d.slot_ml = c->slot_ml.ptr;
     d.materials = c->materials.ptr; d.lights = c->lights.ptr; d.inf_lights = c->inf_lights.ptr; d.prim_slot = c->prim_slot.ptr;
     d.slot_frame = c->slot_frame.ptr; d.nee_lights = c->nee_lights.ptr;

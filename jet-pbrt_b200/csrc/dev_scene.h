@@ -69,6 +69,7 @@ struct DevScene {
     const int*    nee_lights;  // indices of the lights whose colour is not black (the others can never contribute)
     const int*    inf_lights;
     const int*    prim_slot;  // primitive index -> slot
+    const int*    pixel_order;  // path i of a wavefront renders pixel pixel_order[i % npix]: 8x4 tiles in Morton order
     int n_nodes, n_slots, n_materials, n_lights, n_inf_lights, n_prims, n_nee_lights;
     int max_depth;
     int width, height;

@@ -351,6 +351,25 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err) {
         hs.cam.res_y = res_y;
     }
 
+    {   // Pixel visiting order of a wavefront: a warp's 32 consecutive paths cover one 8 x 4 pixel tile and tiles
+        // follow a Morton curve, so the rays a warp traces -- and the surface points they hit -- are neighbours
+        // (the reference walks rows, integrator.cc:90-92; the order is unobservable in the film).
+        const int W = hs.width, H = hs.height;
+        auto spread = [](uint32_t v) {  // interleave 16 bits with zeros
+            v &= 0xffff; v = (v | (v << 8)) & 0x00ff00ff; v = (v | (v << 4)) & 0x0f0f0f0f;
+            v = (v | (v << 2)) & 0x33333333; v = (v | (v << 1)) & 0x55555555; return v;
+        };
+        std::vector<std::pair<uint64_t, int>> keyed((size_t)W * H);
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                uint64_t tile = (uint64_t)(spread((uint32_t)(x >> 3)) | (spread((uint32_t)(y >> 2)) << 1));
+                keyed[(size_t)y * W + x] = {(tile << 5) | (uint64_t)(((y & 3) << 3) | (x & 7)), y * W + x};
+            }
+        std::sort(keyed.begin(), keyed.end());
+        hs.pixel_order.resize(keyed.size());
+        for (size_t i = 0; i < keyed.size(); ++i) hs.pixel_order[i] = keyed[i].second;
+    }
+
     // materials
     hs.materials.resize((size_t)d->n_materials * kMaterialStride);
     for (int i = 0; i < d->n_materials; ++i)

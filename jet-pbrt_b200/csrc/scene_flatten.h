@@ -19,7 +19,7 @@ namespace jpbrt {
 struct HostScene {
     std::vector<Float4> nodes, slots, slot_nrm, materials, lights, slot_frame;
     std::vector<Int2> slot_ml;
-    std::vector<int> inf_lights, prim_slot, nee_lights;
+    std::vector<int> inf_lights, prim_slot, nee_lights, pixel_order;
     DevCamera cam{};
     float world_min[3]{}, world_max[3]{};
     float world_radius = 0;
@@ -30,7 +30,7 @@ struct HostScene {
     double bvh_build_seconds = 0;
     size_t Bytes() const {
         return (nodes.size() + slots.size() + slot_nrm.size() + materials.size() + lights.size() + slot_frame.size()) * sizeof(Float4) +
-               slot_ml.size() * sizeof(Int2) + (inf_lights.size() + prim_slot.size() + nee_lights.size()) * sizeof(int);
+               slot_ml.size() * sizeof(Int2) + (inf_lights.size() + prim_slot.size() + nee_lights.size()) * sizeof(int);  // pixel_order is film state, not scene
     }
 };
 

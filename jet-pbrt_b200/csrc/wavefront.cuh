@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kBlock) k_generate(const __grid_constant__ WfP
     const f3 up = mk3(cam.up[0], cam.up[1], cam.up[2]);
     const int W = p.sc.width;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_paths; i += gridDim.x * blockDim.x) {
-        const int pixel = i % p.npix;
+        const int pixel = __ldg(p.sc.pixel_order + i % p.npix);
         const int sample = a.sample_begin + i / p.npix;
         const int x = pixel % W, y = pixel / W;
         const float4 u = rng_block(key, (uint32_t)pixel, (uint32_t)sample, 0u);
