@@ -340,6 +340,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(pkg, ge, cfg, sc)
+            line["image_error_vs_cpu"] = image_error(pkg, ge, cfg, local)
     ctx.close()
     if world > 1:
         dist.barrier()
@@ -369,6 +370,29 @@ def cpu_baseline(pkg, ge, cfg, sc):
     _, sec = s.render(n, threads)
     return {"value": w * h * n / sec / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind,
             "sample": f"{w}x{h} x {n} spp of the same scene, FIntegrator::Render numthreads={threads}, {sec:.1f}s (BVH build {build:.2f}s excluded)"}
+
+
+def image_error(pkg, ge, cfg, device):
+    """BASELINE.json metric, second half: image RMSE of the GPU render against the reference CPU render at EQUAL
+    spp, next to the CPU-vs-CPU figure for two independent seeds (the Monte Carlo noise floor).  Outside every
+    timed region, at 256 x 256 x 64 spp so that the CPU side costs about a second."""
+    import numpy as np
+
+    orc = ge.load_oracle()
+    scene_name, scale, w, h, spp, desc = cfg
+    res, n = 256, 64
+    sc = pkg.HostScene.builtin(scene_name, res, res * h // w if h != w else res, scale)
+    o = orc.Oracle("ref" if orc.have("ref") else "port").scene(sc)
+    threads = os.cpu_count() or 1
+    cpu_a, _ = o.render(n, threads, seed=1234)
+    cpu_b, _ = o.render(n, threads, seed=4321)
+    gpu, _ = pkg.render(sc, n, seed=5, device=device)
+    rmse = lambda a, b: float(np.sqrt(np.mean((a - b) ** 2)))  # noqa: E731
+    relmse = lambda a, b: float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))  # noqa: E731
+    return {"what": f"{res}x{sc.d.camera.height} x {n} spp, clamped linear film values",
+            "rmse_gpu_vs_cpu": rmse(gpu, cpu_a), "rmse_cpu_vs_cpu": rmse(cpu_b, cpu_a),
+            "relmse_gpu_vs_cpu": relmse(gpu, cpu_a), "relmse_cpu_vs_cpu": relmse(cpu_b, cpu_a),
+            "mean_gpu": float(gpu.mean()), "mean_cpu": float(cpu_a.mean())}
 
 
 if __name__ == "__main__":
