@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--paths-in-flight", type=int, default=0)
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks during the timed region")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     # stdout carries exactly ONE JSON line: everything else (NCCL banners, library chatter) goes to stderr
@@ -231,33 +232,9 @@ def main():
         for _ in range(args.warmup):
             step_resident()
         barrier()
-        ctx.clear_film()
-        ctx.reset_stats()
-        ctx.set_option("stage_timing", 1)
-        clocks = ClockSampler(local)
-        if rank == 0:
-            clocks.start()
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        for _ in range(args.steps):
-            step_resident()
-        ev1.record(stream)
-        barrier()
-        ms_total = ev0.elapsed_time(ev1)
-        clock_info = clocks.stop() if rank == 0 else None
-        st = ctx.stats()  # totals over the K timed steps (reset_stats() was called just before them)
-        ctx.set_option("stage_timing", 0)
-        t = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-        ms_per_step = ms_total / args.steps
-        samples_per_step = w * h * spp_total
-        value = samples_per_step / (ms_per_step * 1e-3) / 1e6
-        rays_per_step_rank = (st["extension_rays"] + st["shadow_rays"]) / args.steps
-
-        # ---- e2e: host buffers in, host film out, every step ----
+        # ---- e2e: host buffers in, host film out, every step.  Measured BEFORE the nvidia-smi clock sampler of the
+        # `value` loop is started: on these boxes host driver calls stall for 30-80 ms for a while after (and
+        # during) nvidia-smi polling, which an asynchronous launch loop hides but a per-step round trip does not. ----
         queue_ms = []
 
         def step_e2e():
@@ -293,7 +270,35 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-        e2e_value = samples_per_step * args.steps / e2e_s / 1e6
+        e2e_value = w * h * spp_total * args.steps / e2e_s / 1e6
+        ctx.set_option("stage_timing", 1)  # per-launch CUDA events => the eager launch path, not the graph
+        step_resident()                    # one more untimed step on exactly that path (creates its event pool)
+        barrier()
+        ctx.clear_film()
+        ctx.reset_stats()
+        clocks = ClockSampler(local)
+        if rank == 0 and not args.no_clocks:
+            clocks.start()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step_resident()
+        ev1.record(stream)
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        clock_info = clocks.stop() if rank == 0 else None
+        st = ctx.stats()  # totals over the K timed steps (reset_stats() was called just before them)
+        ctx.set_option("stage_timing", 0)
+        t = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        ms_per_step = ms_total / args.steps
+        samples_per_step = w * h * spp_total
+        value = samples_per_step / (ms_per_step * 1e-3) / 1e6
+        rays_per_step_rank = (st["extension_rays"] + st["shadow_rays"]) / args.steps
+
         final_mean = float(host_film.mean()) if rank == 0 else 0.0
 
     line = None
