@@ -34,6 +34,18 @@ typedef enum jpbrt_status {
 
 typedef struct jpbrt_ctx jpbrt_ctx;
 
+/* Which FIntegrator::Li a pass evaluates (the reference picks one at compile time, main.cc:151-154).
+ * Option "integrator" of jpbrt_set_option; the default is the one main.cc ships with. */
+typedef enum jpbrt_integrator {
+    JPBRT_INTEGRATOR_PATH = 0,           /* FPathIntegratorIteration (integrator.cc:316-403) -- the hot path */
+    JPBRT_INTEGRATOR_PATH_RECURSIVE = 1, /* FPathIntegratorRecursive (integrator.cc:233-307): the same estimator and the
+                                            same sampler draws, so it runs the same kernels; results equal the
+                                            reference's up to the float evaluation order of the throughput */
+    JPBRT_INTEGRATOR_WHITTED = 2,        /* FWhittedIntegrator (integrator.cc:115-220): direct light at every vertex,
+                                            recursion through specular lobes only (a mirror is traced twice, as there) */
+    JPBRT_INTEGRATOR_DEBUG = 3           /* FDebugIntegrator (integrator.h:44-58): the hit normal as the colour */
+} jpbrt_integrator;
+
 /* ------------------------------------------------------------------------------------------
  * The render trio (BASELINE.json north_star: upload_scene / render_pass / read_film).
  * ---------------------------------------------------------------------------------------- */
@@ -71,6 +83,10 @@ const char* jpbrt_last_error(const jpbrt_ctx* ctx); /* ctx may be NULL: last err
  * interval the reference prints (integrator.cc:77-79). */
 int jpbrt_render(const jpbrt_scene_desc* desc, int spp, uint64_t seed, int device, float* rgb, double* seconds_out);
 
+/* Same with one of the reference's other integrators (jpbrt_integrator). */
+int jpbrt_render_integrator(const jpbrt_scene_desc* desc, int integrator, int spp, uint64_t seed, int device, float* rgb,
+                            double* seconds_out);
+
 /* ------------------------------------------------------------------------------------------
  * Plumbing for multi-GPU (one process per GPU; the film sum is reduced by the caller with NCCL,
  * e.g. torch.distributed.reduce on a tensor aliasing this buffer) and for timing.
@@ -85,8 +101,9 @@ int    jpbrt_finalize_film_device(jpbrt_ctx* ctx, void* out_device, int spp_tota
  * caller pays for a changed scene); returns bytes copied through *bytes. */
 int    jpbrt_reupload_scene(jpbrt_ctx* ctx, size_t* bytes);
 
-/* Tunables: paths in flight per wavefront (0 = default), per-stage CUDA-event timing on/off,
- * counting build of the traversal kernels on/off (node/primitive test counters). */
+/* Options: "integrator" (jpbrt_integrator), "paths_in_flight" per wavefront (0 = default), "stage_timing"
+ * (per-stage CUDA events) on/off, "count_traversal" (node/primitive test counters) on/off, "use_graph",
+ * "trav_blocks", "refill_min" (traversal kernel tunables). */
 int jpbrt_set_option(jpbrt_ctx* ctx, const char* name, long long value);
 
 typedef struct jpbrt_stats {

@@ -73,7 +73,7 @@ class Stats(C.Structure):
 # Every symbol include/jetpbrt_b200.h declares (tests check the library exports them all).
 EXPORTS = [
     "jpbrt_upload_scene", "jpbrt_render_pass", "jpbrt_read_film", "jpbrt_clear_film", "jpbrt_reset_stats", "jpbrt_destroy",
-    "jpbrt_last_error", "jpbrt_render", "jpbrt_film_device_ptr", "jpbrt_film_num_floats", "jpbrt_stream",
+    "jpbrt_last_error", "jpbrt_render", "jpbrt_render_integrator", "jpbrt_film_device_ptr", "jpbrt_film_num_floats", "jpbrt_stream",
     "jpbrt_synchronize", "jpbrt_finalize_film_device", "jpbrt_reupload_scene", "jpbrt_set_option",
     "jpbrt_get_stats", "jpbrt_unit_intersect_shape", "jpbrt_unit_scene_intersect", "jpbrt_unit_scene_occluded",
     "jpbrt_unit_bsdf", "jpbrt_unit_light_sample", "jpbrt_unit_emitted", "jpbrt_unit_generate_rays",
@@ -104,6 +104,7 @@ def _load():
     lib.jpbrt_destroy.argtypes = [P]
     lib.jpbrt_destroy.restype = None
     lib.jpbrt_render.argtypes = [C.POINTER(SceneDesc), I, C.c_uint64, I, F, C.POINTER(C.c_double)]
+    lib.jpbrt_render_integrator.argtypes = [C.POINTER(SceneDesc), I, I, C.c_uint64, I, F, C.POINTER(C.c_double)]
     lib.jpbrt_film_device_ptr.argtypes = [P]
     lib.jpbrt_film_device_ptr.restype = P
     lib.jpbrt_film_num_floats.argtypes = [P]
@@ -372,11 +373,15 @@ def unit_rng_block(pixel, sample, block, seed: int, device: int = 0):
     return out
 
 
-def render(scene: HostScene, spp: int, seed: int = 1234, device: int = 0):
+# jpbrt_integrator (include/jetpbrt_b200.h): the reference's FIntegrator subclasses (main.cc:151-154)
+INTEGRATORS = {"path": 0, "path_recursive": 1, "whitted": 2, "debug": 3}
+
+
+def render(scene: HostScene, spp: int, seed: int = 1234, device: int = 0, integrator: str = "path"):
     """FIntegrator::Render equivalent: returns (film[h,w,3] = clamp01(mean), seconds)."""
     out = np.empty((scene.d.camera.height, scene.d.camera.width, 3), dtype=np.float32)
     sec = C.c_double(0)
-    _check(lib.jpbrt_render(scene.desc, spp, seed, device, _f(out), C.byref(sec)))
+    _check(lib.jpbrt_render_integrator(scene.desc, INTEGRATORS[integrator], spp, seed, device, _f(out), C.byref(sec)))
     return out, sec.value
 
 

@@ -93,10 +93,12 @@ struct jpbrt_ctx {
     bool opt_stage_timing = false;
     bool opt_count_traversal = false;
     int opt_refill_min = 16;
+    int opt_integrator = JPBRT_INTEGRATOR_PATH;  // jpbrt_integrator: which FIntegrator::Li the passes evaluate
+    bool has_mirror = false;                     // Whitted traces a mirror vertex twice: the ray tree can grow
     int opt_trav_blocks = 6;  // resident blocks per SM the traversal kernels are compiled for: 6 (40 registers, default) or 5 (48)
     unsigned kinds_present = 0;  // bit k set: some material of the scene can build BSDF kind k
     // launch geometry
-    int grid_generate = 0, grid_extend = 0, grid_extend_c = 0, grid_extend6 = 0, grid_connect6 = 0, grid_logic = 0, grid_shade[4] = {0, 0, 0, 0}, grid_connect = 0, grid_connect_c = 0, grid_finalize = 0;
+    int grid_generate = 0, grid_extend = 0, grid_extend_c = 0, grid_extend6 = 0, grid_connect6 = 0, grid_logic = 0, grid_logic_w = 0, grid_debug = 0, grid_shade[4] = {0, 0, 0, 0}, grid_shade_w[4] = {0, 0, 0, 0}, grid_connect = 0, grid_connect_c = 0, grid_finalize = 0;
     // host-side accounting
     unsigned long long kernel_launches = 0;
     double ms_stage[5] = {0, 0, 0, 0, 0};
@@ -348,6 +350,7 @@ int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out
         int type;
         memcpy(&type, &hs.materials[(size_t)ml.x * kMaterialStride].w, 4);
         c->kinds_present |= type == JPBRT_MAT_MATTE ? 1u : type == JPBRT_MAT_METAL ? 2u : type == JPBRT_MAT_PLASTIC ? (1u | 4u) : 8u;
+        if (type == JPBRT_MAT_MIRROR) c->has_mirror = true;
     }
     // iterations: bounces 0..max_depth, plus slack for null-material pass-through vertices
     c->n_iters = hs.max_depth + 1 + (hs.has_null_material ? 16 : 0);
@@ -358,11 +361,17 @@ int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out
     c->grid_extend = occupancy_grid(c, k_extend<false, 5>);
     c->grid_extend6 = occupancy_grid(c, k_extend<false, 6>);
     c->grid_extend_c = occupancy_grid(c, k_extend<true, 5>);
-    c->grid_logic = occupancy_grid(c, k_logic);
+    c->grid_logic = occupancy_grid(c, k_logic<false>);
+    c->grid_logic_w = occupancy_grid(c, k_logic<true>);
+    c->grid_debug = occupancy_grid(c, k_debug);
     c->grid_shade[0] = occupancy_grid(c, k_shade<0>);
     c->grid_shade[1] = occupancy_grid(c, k_shade<1>);
     c->grid_shade[2] = occupancy_grid(c, k_shade<2>);
     c->grid_shade[3] = occupancy_grid(c, k_shade<3>);
+    c->grid_shade_w[0] = occupancy_grid(c, k_shade<0, true>);
+    c->grid_shade_w[1] = occupancy_grid(c, k_shade<1, true>);
+    c->grid_shade_w[2] = occupancy_grid(c, k_shade<2, true>);
+    c->grid_shade_w[3] = occupancy_grid(c, k_shade<3, true>);
     c->grid_connect = occupancy_grid(c, k_connect<false, 5>);
     c->grid_connect6 = occupancy_grid(c, k_connect<false, 6>);
     c->grid_connect_c = occupancy_grid(c, k_connect<true, 5>);
@@ -407,6 +416,11 @@ int jpbrt_set_option(jpbrt_ctx* c, const char* name, long long value) {
     if (!strcmp(name, "count_traversal")) { c->opt_count_traversal = value != 0; return 0; }
     if (!strcmp(name, "trav_blocks")) { c->opt_trav_blocks = (int)value; return 0; }
     if (!strcmp(name, "use_graph")) { c->opt_use_graph = value != 0; return 0; }
+    if (!strcmp(name, "integrator")) {
+        if (value < JPBRT_INTEGRATOR_PATH || value > JPBRT_INTEGRATOR_DEBUG) return set_error(c, JPBRT_ERR_INVALID, "unknown integrator %lld", value);
+        c->opt_integrator = (int)value;
+        return 0;
+    }
     if (!strcmp(name, "refill_min")) { c->opt_refill_min = (int)std::max(1ll, std::min(32ll, value)); return 0; }
     return set_error(c, JPBRT_ERR_INVALID, "unknown option '%s'", name);
 }
@@ -421,7 +435,9 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
         k_generate<<<c->grid_generate, kBlock, 0, c->stream>>>(p);
         c->kernel_launches++;
     }
-    for (int it = 0; it < c->n_iters; ++it) {
+    const bool whitted = c->opt_integrator == JPBRT_INTEGRATOR_WHITTED;
+    const bool debug = c->opt_integrator == JPBRT_INTEGRATOR_DEBUG;
+    for (int it = 0; it < (debug ? 1 : c->n_iters); ++it) {
         {
             StageTimer t(c, 1);
             if (count) k_extend<true, 5><<<c->grid_extend_c, kBlock, 0, c->stream>>>(p, it);
@@ -429,9 +445,31 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
             else k_extend<false, 5><<<c->grid_extend, kBlock, 0, c->stream>>>(p, it);
             c->kernel_launches++;
         }
+        if (debug) {  // FDebugIntegrator: the hit normal is the radiance (integrator.h:47-57)
+            StageTimer t(c, 2);
+            k_debug<<<c->grid_debug, kBlock, 0, c->stream>>>(p);
+            c->kernel_launches++;
+            break;
+        }
+        if (whitted) {  // FWhittedIntegrator (integrator.cc:115-220): every vertex is shaded, only specular lobes continue
+            {
+                StageTimer t(c, 2);
+                k_logic<true><<<c->grid_logic_w, kBlock, 0, c->stream>>>(p, it);
+                if (c->kinds_present & 1) k_shade<0, true><<<c->grid_shade_w[0], kBlock, 0, c->stream>>>(p, it);
+                if (c->kinds_present & 2) k_shade<1, true><<<c->grid_shade_w[1], kBlock, 0, c->stream>>>(p, it);
+                if (c->kinds_present & 4) k_shade<2, true><<<c->grid_shade_w[2], kBlock, 0, c->stream>>>(p, it);
+                if (c->kinds_present & 8) k_shade<3, true><<<c->grid_shade_w[3], kBlock, 0, c->stream>>>(p, it);
+                c->kernel_launches += 1 + __builtin_popcount(c->kinds_present);
+            }
+            StageTimer t(c, 3);
+            if (count) k_connect<true, 5><<<c->grid_connect_c, kBlock, 0, c->stream>>>(p, it);
+            else k_connect<false, 6><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
+            c->kernel_launches++;
+            continue;
+        }
         {
             StageTimer t(c, 2);
-            k_logic<<<c->grid_logic, kBlock, 0, c->stream>>>(p, it);
+            k_logic<false><<<c->grid_logic, kBlock, 0, c->stream>>>(p, it);
             if (it < c->n_iters - 1 || c->hs.has_null_material) {  // at bounce == maxDepth nothing is left to shade
                 if (c->kinds_present & 1) k_shade<0><<<c->grid_shade[0], kBlock, 0, c->stream>>>(p, it);
                 if (c->kinds_present & 2) k_shade<1><<<c->grid_shade[1], kBlock, 0, c->stream>>>(p, it);
@@ -449,7 +487,7 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
             c->kernel_launches++;
         }
     }
-    if (c->hs.has_null_material) {
+    if (c->hs.has_null_material && !debug) {
         k_count_dropped<<<1, 32, 0, c->stream>>>(p, c->n_iters);
         c->kernel_launches++;
     }
@@ -464,14 +502,16 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
     int rc = ensure_pool(c);
     if (rc != 0) return rc;
     const long long npix = (long long)c->hs.width * c->hs.height;
-    const int chunk_max = (int)(c->paths_in_flight / npix);
+    int chunk_max = (int)(c->paths_in_flight / npix);
+    if (c->opt_integrator == JPBRT_INTEGRATOR_WHITTED && c->has_mirror)  // room for the ray tree: x2 per mirror bounce, at most x8
+        chunk_max = std::max(1, chunk_max >> std::min(3, std::max(0, c->hs.max_depth - 1)));
     // equal wavefronts: 50 spp with room for 32 run as 25 + 25, not 32 + 18 (short wavefronts are less efficient)
     const int n_waves = (sample_count + chunk_max - 1) / std::max(1, chunk_max);
     const int chunk = n_waves > 0 ? (sample_count + n_waves - 1) / n_waves : chunk_max;
     const bool count = c->opt_count_traversal;
     // Graph replay needs a launch sequence that never changes: no per-launch events, no counting variant.
     const bool use_graph = c->opt_use_graph && !c->opt_stage_timing && !count;
-    const int graph_key = c->opt_trav_blocks * 64 + c->opt_refill_min;
+    const int graph_key = (c->opt_integrator * 16 + c->opt_trav_blocks) * 64 + c->opt_refill_min;
     if (use_graph && (c->wave_graph == nullptr || c->wave_graph_key != graph_key)) {
         if (c->wave_graph) { cudaGraphExecDestroy(c->wave_graph); c->wave_graph = nullptr; }
         cudaGraph_t graph = nullptr;
@@ -595,10 +635,17 @@ void jpbrt_destroy(jpbrt_ctx* c) {
 }
 
 int jpbrt_render(const jpbrt_scene_desc* desc, int spp, uint64_t seed, int device, float* rgb, double* seconds_out) {
+    return jpbrt_render_integrator(desc, JPBRT_INTEGRATOR_PATH, spp, seed, device, rgb, seconds_out);
+}
+
+int jpbrt_render_integrator(const jpbrt_scene_desc* desc, int integrator, int spp, uint64_t seed, int device, float* rgb,
+                            double* seconds_out) {
     if (spp <= 0 || !rgb) return set_error(nullptr, JPBRT_ERR_INVALID, "spp must be positive and rgb non-null");
     jpbrt_ctx* c = nullptr;
     int rc = jpbrt_upload_scene(desc, device, &c);
     if (rc != 0) return rc;
+    rc = jpbrt_set_option(c, "integrator", integrator);
+    if (rc != 0) { g_last_error = c->error; jpbrt_destroy(c); return rc; }
     auto t0 = std::chrono::steady_clock::now();
     rc = jpbrt_render_pass(c, 0, spp, seed);
     if (rc == 0) rc = jpbrt_read_film(c, rgb, spp, 1);

@@ -36,8 +36,10 @@ struct RngKey {
     uint32_t k0, k1;
 };
 
-__device__ __forceinline__ float4 rng_block(const RngKey& key, uint32_t pixel, uint32_t sample, uint32_t block) {
-    uint4 r = philox4x32_10(pixel, sample, block, 0u, key.k0, key.k1);
+// `branch` (4th counter word) is 0 for a path; the Whitted mode numbers the vertices of its ray TREE with it
+// (children of node n: 3n+1 SpecularReflect, 3n+2 SpecularTransmit, 3n+3 SpecularReflectAndTransmit).
+__device__ __forceinline__ float4 rng_block(const RngKey& key, uint32_t pixel, uint32_t sample, uint32_t block, uint32_t branch = 0u) {
+    uint4 r = philox4x32_10(pixel, sample, block, branch, key.k0, key.k1);
     return make_float4(u32_to_unit(r.x), u32_to_unit(r.y), u32_to_unit(r.z), u32_to_unit(r.w));
 }
 

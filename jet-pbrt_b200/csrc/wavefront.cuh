@@ -15,6 +15,13 @@
 // Shadow rays go to static 48-byte slots (origin+tmax, dir+pixel, contribution), one per (vertex, light).
 // All radiance goes straight to the float film with RED.ADD.F32 (no per-path radiance state).
 //
+// The same stages serve the reference's other integrators as MODES of the pipeline:
+//   FPathIntegratorRecursive (integrator.cc:233-307): the same estimator and draws -> the same kernels;
+//   FWhittedIntegrator (integrator.cc:115-220): k_logic<true> / k_shade<KIND, true> -- emission at every vertex,
+//     NEE at every non-delta vertex, continuation through SPECULAR lobes only, a mirror spawning TWO rays
+//     (bsdf.h:282 subset match; the path record's b.w carries the vertex's number in the ray tree);
+//   FDebugIntegrator (integrator.h:44-58): generate -> extend -> k_debug (hit normal as colour).
+//
 // Kernels are persistent: grid = SMs x resident blocks, each warp pulls batches of 32 queue items
 // from a device-side work counter, and queue lengths are read from device memory -- the host
 // never reads a count back, so a whole pass is one uninterrupted stream of launches.
@@ -146,7 +153,7 @@ struct ExtendIO {
 // 6 is 1-3 % faster on all scenes, 8 = 32 registers spills and is 15-25 % slower).
 template <bool COUNT, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) k_extend(const __grid_constant__ WfParams p, int it) {
-    const int n = p.counters[CNT_RAYS * p.counter_stride + it];
+    const int n = min(p.counters[CNT_RAYS * p.counter_stride + it], p.queue_capacity);
     int* work = p.counters + CNT_W_EXTEND * p.counter_stride + it;
     const int buf = it & 1;
     unsigned nb = 0, np = 0;
@@ -222,6 +229,9 @@ __device__ __forceinline__ int bsdf_kind_of(int k) {
 }
 
 // Warp-aggregated append of the survivors' records to the next iteration's ray queue.
+// GUARD: the Whitted mode's ray tree can outgrow the pool (a mirror spawns two rays); rays past the end of the
+// queue are dropped and counted (stats.invalid_contributions) -- consumers clamp the queue length to the capacity.
+template <bool GUARD = false>
 __device__ __forceinline__ void append_next(const WfParams& p, int* next_count, int nbuf, bool alive, const float4& no, const float4& nd,
                                             const float4& nbeta) {
     const unsigned mask = __ballot_sync(kFull, alive);
@@ -231,6 +241,10 @@ __device__ __forceinline__ void append_next(const WfParams& p, int* next_count, 
         wbase = __shfl_sync(kFull, wbase, 0);
         if (alive) {
             const int dst = wbase + __popc(mask & ((1u << lane_id()) - 1));
+            if (GUARD && dst >= p.queue_capacity) {
+                atomicAdd(p.stats + ST_DROPPED, 1ull);
+                return;
+            }
             p.ray_o[nbuf][dst] = no;
             p.ray_d[nbuf][dst] = nd;
             p.ray_b[nbuf][dst] = nbeta;
@@ -253,9 +267,10 @@ __device__ __forceinline__ int warp_fetch_n(int* counter, int amount) {
     return __shfl_sync(kFull, base, 0);
 }
 
+template <bool WHITTED>
 __global__ void __launch_bounds__(kBlock) k_logic(const __grid_constant__ WfParams p, int it) {
     const DevScene& sc = p.sc;
-    const int n = p.counters[CNT_RAYS * p.counter_stride + it];
+    const int n = min(p.counters[CNT_RAYS * p.counter_stride + it], p.queue_capacity);
     int* work = p.counters + CNT_W_SHADE * p.counter_stride + it;
     int* next_count = p.counters + CNT_RAYS * p.counter_stride + it + 1;
     const int buf = it & 1, nbuf = buf ^ 1;
@@ -279,7 +294,8 @@ __global__ void __launch_bounds__(kBlock) k_logic(const __grid_constant__ WfPara
                 const int bounce = (fl >> 24) & 0x7f;
                 const bool specular = fl < 0;
                 const int slot = __float_as_int(h.y);
-                const bool add_emission = (bounce == 0) || specular;  // integrator.cc:328
+                const bool add_emission = WHITTED || (bounce == 0) || specular;  // integrator.cc:328; Whitted: always (:124,141)
+                const bool in_depth = WHITTED || bounce < sc.max_depth;           // Whitted bounds the depth where it spawns (:157)
                 if (slot < 0) {
                     if (add_emission && sc.n_inf_lights > 0) {
                         const int pixel = __float_as_int(p.ray_o[buf][i].w);
@@ -289,8 +305,8 @@ __global__ void __launch_bounds__(kBlock) k_logic(const __grid_constant__ WfPara
                     }
                 } else {
                     const int2 ml = __ldg(reinterpret_cast<const int2*>(sc.slot_ml) + slot);
-                    const bool emits = add_emission && ml.y >= 0;
-                    const bool pass = bounce < sc.max_depth && ml.x < 0;
+                    const bool emits = add_emission && ml.y >= 0 && !(WHITTED && ml.x < 0);  // Whitted: null material returns first (:136)
+                    const bool pass = in_depth && ml.x < 0;
                     if (emits || pass) {
                         const float4 ro = p.ray_o[buf][i];
                         const float4 rb = p.ray_b[buf][i];
@@ -309,13 +325,14 @@ __global__ void __launch_bounds__(kBlock) k_logic(const __grid_constant__ WfPara
                             nbeta = rb;
                         }
                     }
-                    if (bounce < sc.max_depth && ml.x >= 0) {  // integrator.cc:340,348
+                    if (in_depth && ml.x >= 0) {  // integrator.cc:340,348
                         const Float4* mat = sc.materials + (size_t)ml.x * kMaterialStride;
                         const int type = __float_as_int(ldg4(mat).w);
                         if (type == MAT_PLASTIC) {  // the lobe pick is the first number of the bounce's block (material.cc:14)
                             const int pixel = __float_as_int(p.ray_o[buf][i].w);
                             const uint32_t blk = 1u + (uint32_t)bounce * (uint32_t)p.blocks_per_bounce;
-                            const float4 u0 = rng_block(key, (uint32_t)pixel, (uint32_t)(fl & 0xffffff), blk);
+                            const uint32_t node = WHITTED ? __float_as_uint(p.ray_b[buf][i].w) : 0u;
+                            const float4 u0 = rng_block(key, (uint32_t)pixel, (uint32_t)(fl & 0xffffff), blk, node);
                             kind = (u0.x < ldg4(mat + 2).y) ? KIND_LAMBERT : KIND_MF_DIELECTRIC;
                         } else {
                             kind = type == MAT_MATTE ? KIND_LAMBERT : type == MAT_METAL ? KIND_MF_CONDUCTOR : KIND_DELTA;
@@ -323,7 +340,7 @@ __global__ void __launch_bounds__(kBlock) k_logic(const __grid_constant__ WfPara
                     }
                 }
             }
-            append_next(p, next_count, nbuf, alive, no, nd, nbeta);
+            append_next<WHITTED>(p, next_count, nbuf, alive, no, nd, nbeta);
             kinds[c] = kind;
 #pragma unroll
             for (int k = 0; k < NUM_KINDS; ++k) masks[c][k] = __ballot_sync(kFull, kind == k);
@@ -356,7 +373,7 @@ __global__ void __launch_bounds__(kBlock) k_logic(const __grid_constant__ WfPara
 #ifndef JPB_SHADE_MIN_BLOCKS
 #define JPB_SHADE_MIN_BLOCKS 3
 #endif
-template <int KIND>
+template <int KIND, bool WHITTED = false>
 __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ WfParams p, int it) {
     const DevScene& sc = p.sc;
     const int n = p.counters[(CNT_Q0 + KIND) * p.counter_stride + it];
@@ -380,8 +397,8 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
         for (int c = 0; c < nchunks; ++c) {
             if (fetch_base + 32 * c >= n) break;
             const int qi = fetch_base + 32 * c + lane_id();
-            bool alive = false;
-            float4 no = make_float4(0, 0, 0, 0), nd = no, nbeta = no;
+            bool alive = false, alive2 = false;  // alive2: a mirror's second ray in the Whitted mode
+            float4 no = make_float4(0, 0, 0, 0), nd = no, nbeta = no, nbeta2 = no;
             if (qi < n) {
                 const int i = queue[qi];
                 const float4 ro = p.ray_o[buf][i];
@@ -400,7 +417,8 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
                 const f3 wo = -d;
                 const int2 ml = __ldg(reinterpret_cast<const int2*>(sc.slot_ml) + slot);
                 const uint32_t blk = 1u + (uint32_t)bounce * (uint32_t)p.blocks_per_bounce;
-                const float4 u0 = rng_block(key, (uint32_t)pixel, (uint32_t)sample, blk);
+                const uint32_t node = WHITTED ? __float_as_uint(rb.w) : 0u;
+                const float4 u0 = rng_block(key, (uint32_t)pixel, (uint32_t)sample, blk, node);
                 Bsdf bsdf = make_bsdf(sc.materials + (size_t)ml.x * kMaterialStride, u0.x);
                 if (KIND == KIND_LAMBERT) bsdf.kind = K_LAMBERT;  // known at compile time: the other BSDFs' code is pruned
                 if (KIND == KIND_MF_CONDUCTOR) bsdf.kind = K_MICROFACET_CONDUCTOR;
@@ -415,7 +433,7 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
                         const int j = __ldg(sc.nee_lights + k);
                         if ((j >> 1) != lu_block) {
                             lu_block = j >> 1;
-                            lu = rng_block(key, (uint32_t)pixel, (uint32_t)sample, blk + 1u + (uint32_t)lu_block);
+                            lu = rng_block(key, (uint32_t)pixel, (uint32_t)sample, blk + 1u + (uint32_t)lu_block, node);
                         }
                         const float ux = (j & 1) ? lu.z : lu.x, uy = (j & 1) ? lu.w : lu.y;
                         const long long si = (long long)k * n_vertices + kind_base + qi;  // this (vertex, light)'s slot
@@ -448,31 +466,65 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
                         }
                     }
                 }
-                BsdfSample bs = bsdf_sample_local(bsdf, wo_l, u0.y, u0.z);  // integrator.cc:375
-                bs.wi = to_world(frame, bs.wi);                               // bsdf.h:296-302
-                if (!(is_black(bs.f) || bs.pdf == 0.f)) {
-                    const bool spec = (bs.flags & BSDF_SPECULAR) != 0;
-                    bool survive = true;
-                    if (bounce >= JPBRT_RR_START_BOUNCE) {  // integrator.cc:383-393
-                        const float q = std_max(JPBRT_RR_QMIN, 1 - max_component(bs.f));
-                        if (u0.w < q) survive = false;
-                        else beta = cmul(beta, bs.f * absdot(bs.wi, N) / (bs.pdf * (1 - q)));
-                    } else {
-                        beta = cmul(beta, bs.f * absdot(bs.wi, N) / bs.pdf);  // integrator.cc:397
+                if (!WHITTED) {
+                    BsdfSample bs = bsdf_sample_local(bsdf, wo_l, u0.y, u0.z);  // integrator.cc:375
+                    bs.wi = to_world(frame, bs.wi);                               // bsdf.h:296-302
+                    if (!(is_black(bs.f) || bs.pdf == 0.f)) {
+                        const bool spec = (bs.flags & BSDF_SPECULAR) != 0;
+                        bool survive = true;
+                        if (bounce >= JPBRT_RR_START_BOUNCE) {  // integrator.cc:383-393
+                            const float q = std_max(JPBRT_RR_QMIN, 1 - max_component(bs.f));
+                            if (u0.w < q) survive = false;
+                            else beta = cmul(beta, bs.f * absdot(bs.wi, N) / (bs.pdf * (1 - q)));
+                        } else {
+                            beta = cmul(beta, bs.f * absdot(bs.wi, N) / bs.pdf);  // integrator.cc:397
+                        }
+                        // A non-specular path that would arrive at bounce == maxDepth can add nothing there (no
+                        // emission, integrator.cc:328; loop ends, :340): do not trace it.
+                        if (survive && (spec || bounce + 1 < sc.max_depth)) {
+                            alive = true;
+                            no = make_float4(P.x, P.y, P.z, ro.w);
+                            nd = make_float4(bs.wi.x, bs.wi.y, bs.wi.z,
+                                             __int_as_float(sample | ((bounce + 1) << 24) | (spec ? (int)0x80000000 : 0)));
+                            nbeta = make_float4(beta.x, beta.y, beta.z, 0.f);
+                        }
                     }
-                    // A non-specular path that would arrive at bounce == maxDepth can add nothing there (no
-                    // emission, integrator.cc:328; loop ends, :340): do not trace it.
-                    if (survive && (spec || bounce + 1 < sc.max_depth)) {
+                } else if (KIND == KIND_DELTA && bounce + 1 < sc.max_depth) {
+                    // integrator.cc:157-163: SpecularReflect / SpecularTransmit / SpecularReflectAndTransmit each sample the
+                    // BSDF whose flags are a SUBSET of theirs (bsdf.h:282): a mirror matches the first and the third (two
+                    // rays), FFresnelSpecular only the third; no BSDF of the reference is Specular|Transmission alone.
+                    BsdfSample bs = bsdf_sample_local(bsdf, wo_l, u0.y, u0.z);
+                    bs.wi = to_world(frame, bs.wi);
+                    if (!(is_black(bs.f) || bs.pdf == 0.f)) {
+                        beta = cmul(beta, bs.f * absdot(bs.wi, N) / bs.pdf);  // integrator.cc:181
+                        const bool mirror = bsdf.kind == K_SPECULAR;
                         alive = true;
+                        alive2 = mirror;
                         no = make_float4(P.x, P.y, P.z, ro.w);
-                        nd = make_float4(bs.wi.x, bs.wi.y, bs.wi.z,
-                                         __int_as_float(sample | ((bounce + 1) << 24) | (spec ? (int)0x80000000 : 0)));
-                        nbeta = make_float4(beta.x, beta.y, beta.z, 0.f);
+                        nd = make_float4(bs.wi.x, bs.wi.y, bs.wi.z, __int_as_float(sample | ((bounce + 1) << 24) | (int)0x80000000));
+                        nbeta = make_float4(beta.x, beta.y, beta.z, __uint_as_float(3u * node + (mirror ? 1u : 3u)));
+                        nbeta2 = make_float4(beta.x, beta.y, beta.z, __uint_as_float(3u * node + 3u));
                     }
                 }
             }
-            append_next(p, next_count, nbuf, alive, no, nd, nbeta);
+            append_next<WHITTED>(p, next_count, nbuf, alive, no, nd, nbeta);
+            if (WHITTED && KIND == KIND_DELTA) append_next<true>(p, next_count, nbuf, alive2, no, nd, nbeta2);
         }
+    }
+}
+
+// FDebugIntegrator::Li (integrator.h:47-57): the hit normal as a colour (negative components are summed as they
+// are and clamped by Clamp01 at finalize, exactly like DoRender's L += Li * ratio).
+__global__ void __launch_bounds__(kBlock) k_debug(const __grid_constant__ WfParams p) {
+    const int n = min(p.counters[CNT_RAYS * p.counter_stride + 0], p.queue_capacity);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float2 h = p.hit[i];
+        const int slot = __float_as_int(h.y);
+        if (slot < 0) continue;
+        const float4 ro = p.ray_o[0][i];
+        const f3 d = mk3(p.ray_d[0][i]);
+        const f3 P = mk3(ro) + h.x * d;
+        film_add(p, __float_as_int(ro.w), hit_normal(p.sc, slot, P, d));
     }
 }
 

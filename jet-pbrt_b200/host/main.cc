@@ -1,7 +1,8 @@
 // main.cc -- command line with the reference's arguments (main.cc:113-163): jetpbrt sceneid spp
 //   sceneid 0 = cornell box (create_cornellbox_scene), 1 = bunny scene (create_bunny_scene),
 //   2 = large mesh (C3), 3 = glossy / 16 lights (C4).  Defaults: 1024 x 1024, 50 spp, depth 5, BMP.
-// Extra optional arguments: width height device.
+// Extra optional arguments: width height device integrator  (integrator: 0 path -- what main.cc:154 ships with --
+// 1 recursive path, 2 Whitted, 3 debug: the alternatives main.cc:151-153 keeps commented out).
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -26,8 +27,15 @@ int main(int argc, char* argv[]) {
     printf("current scene: %s\n", scene->Name().c_str());
     Film film(width, height);
     int depth = scene->Desc()->max_depth;
-    PathIntegratorIteration integrator(depth);
-    if (!integrator.Render(scene.get(), samples_per_pixel, &film, device)) return 1;
+    int kind = argc > 6 ? atoi(argv[6]) : 0;
+    std::unique_ptr<Integrator> integrator;
+    switch (kind) {
+    case 1: integrator.reset(new PathIntegratorRecursive(depth)); break;
+    case 2: integrator.reset(new WhittedIntegrator(depth)); break;
+    case 3: integrator.reset(new DebugIntegrator()); break;
+    default: integrator.reset(new PathIntegratorIteration(depth)); break;
+    }
+    if (!integrator->Render(scene.get(), samples_per_pixel, &film, device)) return 1;
     char fullname[256];
     snprintf(fullname, sizeof(fullname), "%s_%d", scene->Name().c_str(), samples_per_pixel);
     film.SaveAsImage(fullname, EImageType::BMP);

@@ -13,8 +13,8 @@ bool Film::SaveAsImage(const std::string& filename, EImageType type) const {
     return jpbrt_save_image(filename.c_str(), (int)type, width_, height_, pixels_.data()) == JPBRT_OK;
 }
 
-bool PathIntegratorIteration::Render(Scene* scene, int spp, Film* film, int device, uint64_t seed) const {
-    scene->SetMaxDepth(maxDepth_);
+bool Integrator::Render(Scene* scene, int spp, Film* film, int device, uint64_t seed) const {
+    if (maxDepth_ >= 0) scene->SetMaxDepth(maxDepth_);
     const jpbrt_scene_desc* desc = scene->Desc();
     if (desc->camera.width != film->Width() || desc->camera.height != film->Height()) {
         fprintf(stdout, "film resolution does not match the camera's\n");
@@ -25,6 +25,7 @@ bool PathIntegratorIteration::Render(Scene* scene, int spp, Film* film, int devi
     jpbrt_ctx* ctx = nullptr;
     int rc = jpbrt_upload_scene(desc, device, &ctx);
     std::vector<float> tmp((size_t)film->Width() * film->Height() * 3);
+    if (rc == 0) rc = jpbrt_set_option(ctx, "integrator", kind_);
     if (rc == 0) rc = jpbrt_render_pass(ctx, 0, spp, seed);
     if (rc == 0) rc = jpbrt_read_film(ctx, tmp.data(), spp, 1);
     if (rc != 0) {

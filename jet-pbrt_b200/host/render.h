@@ -4,6 +4,7 @@
 //   FFilm film(w, h)                                                   jetpbrt::Film film(w, h)
 //   FRandomSampler sampler(spp)                                        (spp argument; sampler is counter based)
 //   FPathIntegratorIteration integrator(5)                             jetpbrt::PathIntegratorIteration integrator(5)
+//   FDebugIntegrator / FWhittedIntegrator(5) / FPathIntegratorRecursive(5)   jetpbrt::DebugIntegrator / WhittedIntegrator(5) / ...
 //   integrator.Render(scene, sampler, &film, 16)                       integrator.Render(scene, spp, &film, device)
 //   film.SaveAsImage(name, EImageType::BMP)                            film.SaveAsImage(name, EImageType::BMP)
 #pragma once
@@ -33,16 +34,36 @@ private:
     std::vector<float> pixels_;  // row-major RGB, row 0 = top (film.h:50-56)
 };
 
-class PathIntegratorIteration {
+// FIntegrator (integrator.h:25-41): Render() is the public entry; the subclass picks the estimator.
+class Integrator {
 public:
-    explicit PathIntegratorIteration(int maxDepth) : maxDepth_(maxDepth) {}
+    virtual ~Integrator() {}
     // Blocks until the film is filled, like FIntegrator::Render (integrator.cc:35-80); adds
     // Clamp01(mean radiance) onto the film (film.h:64-68).  Returns false and prints the C-ABI
     // error on failure (the reference's Render returns void and cannot fail).
     bool Render(Scene* scene, int spp, Film* film, int device = 0, uint64_t seed = 1234) const;
 
-private:
-    int maxDepth_;
+protected:
+    Integrator(int kind, int maxDepth) : kind_(kind), maxDepth_(maxDepth) {}
+    int kind_;      // jpbrt_integrator
+    int maxDepth_;  // < 0: keep the scene's
+};
+
+class PathIntegratorIteration : public Integrator {  // integrator.h:108-121 -- the hot path
+public:
+    explicit PathIntegratorIteration(int maxDepth) : Integrator(0, maxDepth) {}
+};
+class PathIntegratorRecursive : public Integrator {  // integrator.h:87-105
+public:
+    explicit PathIntegratorRecursive(int maxDepth) : Integrator(1, maxDepth) {}
+};
+class WhittedIntegrator : public Integrator {  // integrator.h:62-84
+public:
+    explicit WhittedIntegrator(int maxDepth) : Integrator(2, maxDepth) {}
+};
+class DebugIntegrator : public Integrator {  // integrator.h:44-58
+public:
+    DebugIntegrator() : Integrator(3, -1) {}
 };
 
 }  // namespace jetpbrt

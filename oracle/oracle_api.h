@@ -67,6 +67,11 @@ int ORC(generate_rays)(ORC(scene)* s, int n, const float* posfilm2, float* o3, f
  * reference's 1234.  Returns wall seconds of Render(), or < 0 on error. */
 double ORC(render)(ORC(scene)* s, int spp, int numthreads, int seed, float* film);
 
+/* Same, with the reference's other integrators (main.cc:151-154):
+ * mode 0 FPathIntegratorIteration, 1 FPathIntegratorRecursive (integrator.cc:233-307),
+ * 2 FWhittedIntegrator (integrator.cc:115-220), 3 FDebugIntegrator (integrator.h:44-58). */
+double ORC(render_mode)(ORC(scene)* s, int mode, int spp, int numthreads, int seed, float* film);
+
 /* Scene facts: out[0..2]=world min, [3..5]=world max, [6]=environment-light worldRadius. */
 int ORC(scene_info)(ORC(scene)* s, float* out7);
 

@@ -35,6 +35,9 @@ def _f32(a, shape=None):
     return a.reshape(shape) if shape is not None else a
 
 
+INTEGRATORS = {"path": 0, "path_recursive": 1, "whitted": 2, "debug": 3}  # main.cc:151-154
+
+
 class Oracle:
     def __init__(self, kind: str):
         assert kind in ("ref", "port")
@@ -59,11 +62,15 @@ class Oracle:
         g("generate_rays").argtypes = [P, I, F, F, F]
         g("render").argtypes = [P, I, I, I, F]
         g("render").restype = C.c_double
+        g("render_mode").argtypes = [P, I, I, I, I, F]
+        g("render_mode").restype = C.c_double
         g("scene_info").argtypes = [P, F]
         if kind == "port":
             g("scene_intersect_brute").argtypes = [P, I, F, IP, F, F, F]
             g("render_counter").argtypes = [P, I, I, C.c_uint64, I, F, C.POINTER(C.c_uint64)]
             g("render_counter").restype = C.c_double
+            g("render_counter_mode").argtypes = [P, I, I, I, C.c_uint64, I, F, C.POINTER(C.c_uint64)]
+            g("render_counter_mode").restype = C.c_double
             g("render_counted").argtypes = [P, I, I, I, F, C.POINTER(C.c_uint64)]
             g("render_counted").restype = C.c_double
             g("philox_block").argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, F]
@@ -165,18 +172,19 @@ class OracleScene:
         assert self.o._fn("generate_rays")(self.h, n, _f(posfilm2), _f(o), _f(d)) == 0
         return o, d
 
-    def render(self, spp, numthreads=8, seed=-1):
-        """FIntegrator::Render: returns (film[h,w,3] = Clamp01(mean), seconds)."""
+    def render(self, spp, numthreads=8, seed=-1, mode=0):
+        """FIntegrator::Render: returns (film[h,w,3] = Clamp01(mean), seconds).
+        mode: 0 path (iteration), 1 path (recursive), 2 Whitted, 3 debug -- INTEGRATORS below."""
         film = np.empty((self.height, self.width, 3), np.float32)
-        sec = self.o._fn("render")(self.h, spp, numthreads, seed, _f(film))
+        sec = self.o._fn("render_mode")(self.h, mode, spp, numthreads, seed, _f(film))
         assert sec >= 0
         return film, sec
 
-    def render_counter(self, sample_begin, sample_count, seed, numthreads=8, counters=False):
+    def render_counter(self, sample_begin, sample_count, seed, numthreads=8, counters=False, mode=0):
         """Port only: raw radiance sums with the B200 path's counter-based sampler."""
         film = np.empty((self.height, self.width, 3), np.float32)
         cnt = (C.c_uint64 * 7)()
-        sec = self.o._fn("render_counter")(self.h, sample_begin, sample_count, seed, numthreads, _f(film), cnt if counters else None)
+        sec = self.o._fn("render_counter_mode")(self.h, mode, sample_begin, sample_count, seed, numthreads, _f(film), cnt if counters else None)
         assert sec >= 0
         if counters:
             keys = ["ext_rays", "shadow_rays", "node_tests", "prim_tests", "samples", "rng_draws", "vertices"]

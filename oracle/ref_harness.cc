@@ -269,16 +269,22 @@ int jref_generate_rays(jref_scene* s, int n, const float* posfilm2, float* o3, f
     return 0;
 }
 
-double jref_render(jref_scene* s, int spp, int numthreads, int seed, float* film_out) {
-    if (!s || spp <= 0 || !film_out) return -1.0;
+double jref_render_mode(jref_scene* s, int mode, int spp, int numthreads, int seed, float* film_out) {
+    if (!s || spp <= 0 || !film_out || mode < 0 || mode > 3) return -1.0;
     FFilm film(s->width, s->height);
     film.Clear();
     std::shared_ptr<FSampler> sampler;
     if (seed < 0) sampler = std::make_shared<FRandomSampler>(spp);   // main.cc:149
     else          sampler = std::make_shared<SeededRandomSampler>(spp, seed);
-    FPathIntegratorIteration integrator(s->max_depth);               // main.cc:154
+    std::unique_ptr<FIntegrator> integrator;                          // main.cc:151-154
+    switch (mode) {
+    case 1: integrator = std::make_unique<FPathIntegratorRecursive>(s->max_depth); break;
+    case 2: integrator = std::make_unique<FWhittedIntegrator>(s->max_depth); break;
+    case 3: integrator = std::make_unique<FDebugIntegrator>(); break;
+    default: integrator = std::make_unique<FPathIntegratorIteration>(s->max_depth); break;
+    }
     auto t0 = std::chrono::steady_clock::now();
-    integrator.Render(s->scene.get(), sampler.get(), &film, numthreads);  // main.cc:156
+    integrator->Render(s->scene.get(), sampler.get(), &film, numthreads);  // main.cc:156
     auto t1 = std::chrono::steady_clock::now();
     for (int y = 0; y < s->height; ++y)
         for (int x = 0; x < s->width; ++x) {
@@ -287,6 +293,10 @@ double jref_render(jref_scene* s, int spp, int numthreads, int seed, float* film
             o[0] = c.r; o[1] = c.g; o[2] = c.b;
         }
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+double jref_render(jref_scene* s, int spp, int numthreads, int seed, float* film_out) {
+    return jref_render_mode(s, 0, spp, numthreads, seed, film_out);
 }
 
 int jref_scene_info(jref_scene* s, float* out7) {

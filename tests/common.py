@@ -99,3 +99,27 @@ def shape_rays(rng, n, center, radius):
     d = tgt - o
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     return make_rays(o, d.astype(np.float32))
+
+
+def specular_scene(pkg, res=64, max_depth=5):
+    """A room for the Whitted / recursive / debug integrators: mirror sphere, mirror wall facing
+    it (mirror-mirror chains: the reference traces every mirror vertex twice), glass sphere, plastic box top, matte
+    floor, a null-material pane the rays pass through, a rectangle area light, a point light and a dim environment."""
+    cam = pkg.Camera((0, 3, 11), (0, -0.12, -1), (0, 1, 0), 60.0, res, res)
+    S, M, L, Pm = pkg.Shape, pkg.Material, pkg.Light, pkg.Primitive
+    z3 = (0.0, 0.0, 0.0)
+    shapes = [S(pkg.SHAPE_RECTANGLE, 1, ((-1.5, 7.5, -1.5), (-1.5, 7.5, 1.5), (1.5, 7.5, 1.5), (1.5, 7.5, -1.5))),   # 0 light
+              S(pkg.SHAPE_RECTANGLE, 0, ((-8, 0, -8), (-8, 0, 8), (8, 0, 8), (8, 0, -8))),                           # 1 floor
+              S(pkg.SHAPE_SPHERE, 0, ((-2.2, 1.5, 0), (1.5, 0, 0), z3, z3)),                                          # 2 mirror ball
+              S(pkg.SHAPE_SPHERE, 0, ((2.0, 1.2, 1.5), (1.2, 0, 0), z3, z3)),                                         # 3 glass ball
+              S(pkg.SHAPE_RECTANGLE, 0, ((-6, 0, -4), (-6, 6, -4), (4, 6, -5), (4, 0, -5))),                          # 4 mirror wall
+              S(pkg.SHAPE_RECTANGLE, 0, ((3.5, 0.8, -2), (3.5, 0.8, 0), (5.5, 0.8, 0), (5.5, 0.8, -2))),             # 5 plastic slab
+              S(pkg.SHAPE_RECTANGLE, 0, ((-1, 0, 5), (-1, 4, 5), (1, 4, 5), (1, 0, 5))),                              # 6 null pane
+              S(pkg.SHAPE_TRIANGLE, 0, ((5, 0, -4.5), (7, 0, -3), (6, 4, -4), z3))]                                   # 7 metal fin
+    mats = [M(pkg.MAT_MATTE, 0, (.6, .55, .5), z3, 0, 0), M(pkg.MAT_MIRROR, 0, (.9, .85, .8), z3, 0, 0),
+            M(pkg.MAT_GLASS, 0, (.95, .95, .95), (.95, .95, .95), 1.5, 0), M(pkg.MAT_PLASTIC, 0, (.3, .1, .4), (.7, .9, .6), 0.15, 0),
+            M(pkg.MAT_METAL, 0, (.18, .15, .81), (.11, .11, .11), 0.2, 0.2)]
+    lights = [L(pkg.LIGHT_ENVIRONMENT, -1, (.08, .08, .2), z3, z3), L(pkg.LIGHT_AREA, 0, (14, 13, 12), z3, z3),
+              L(pkg.LIGHT_POINT, -1, (20, 20, 20), (5, 6, 4), z3)]
+    prims = [Pm(0, 0, 1), Pm(1, 0, -1), Pm(2, 1, -1), Pm(3, 2, -1), Pm(4, 1, -1), Pm(5, 3, -1), Pm(6, -1, -1), Pm(7, 4, -1)]
+    return pkg.HostScene.from_arrays(cam, shapes, mats, lights, prims, max_depth=max_depth, name="specular")
