@@ -93,6 +93,7 @@ struct jpbrt_ctx {
     bool opt_stage_timing = false;
     bool opt_count_traversal = false;
     int opt_refill_min = 16;
+    long long opt_band_pixels = 0;  // pixels per band of a wavefront (0 = default 2^20); >= the frame: no banding
     int opt_integrator = JPBRT_INTEGRATOR_PATH;  // jpbrt_integrator: which FIntegrator::Li the passes evaluate
     bool has_mirror = false;                     // Whitted traces a mirror vertex twice: the ray tree can grow
     int opt_trav_blocks = 6;  // resident blocks per SM the traversal kernels are compiled for: 6 (40 registers, default) or 5 (48)
@@ -416,6 +417,7 @@ int jpbrt_set_option(jpbrt_ctx* c, const char* name, long long value) {
     if (!strcmp(name, "count_traversal")) { c->opt_count_traversal = value != 0; return 0; }
     if (!strcmp(name, "trav_blocks")) { c->opt_trav_blocks = (int)value; return 0; }
     if (!strcmp(name, "use_graph")) { c->opt_use_graph = value != 0; return 0; }
+    if (!strcmp(name, "band_pixels")) { c->opt_band_pixels = std::max(0ll, value); return 0; }
     if (!strcmp(name, "integrator")) {
         if (value < JPBRT_INTEGRATOR_PATH || value > JPBRT_INTEGRATOR_DEBUG) return set_error(c, JPBRT_ERR_INVALID, "unknown integrator %lld", value);
         c->opt_integrator = (int)value;
@@ -502,7 +504,14 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
     int rc = ensure_pool(c);
     if (rc != 0) return rc;
     const long long npix = (long long)c->hs.width * c->hs.height;
-    int chunk_max = (int)(c->paths_in_flight / npix);
+    // Bands: a wavefront covers a contiguous range of the Morton pixel order (a compact region of the frame) times as
+    // many samples as the pool holds, not the whole frame times a few samples.  Every radiance contribution is a float
+    // atomic on the film; a band's film (<= 12 MB) stays in the 126 MB L2 next to the streamed wavefront state, a 4K
+    // frame's (99.5 MB) does not -- measured on the 3840x2160 Cornell config: k_connect 222 -> see DESIGN.md.
+    const long long band_target = c->opt_band_pixels > 0 ? c->opt_band_pixels : (1ll << 20);
+    const int n_bands = (int)std::max(1ll, (npix + band_target - 1) / band_target);
+    const long long band_pixels = (npix + n_bands - 1) / n_bands;
+    int chunk_max = (int)std::max(1ll, c->paths_in_flight / band_pixels);
     if (c->opt_integrator == JPBRT_INTEGRATOR_WHITTED && c->has_mirror)  // room for the ray tree: x2 per mirror bounce, at most x8
         chunk_max = std::max(1, chunk_max >> std::min(3, std::max(0, c->hs.max_depth - 1)));
     // equal wavefronts: 50 spp with room for 32 run as 25 + 25, not 32 + 18 (short wavefronts are less efficient)
@@ -528,24 +537,30 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
         if (ce != cudaSuccess) { c->wave_graph = nullptr; return set_error(c, JPBRT_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
         c->wave_graph_key = graph_key;
     }
-    for (int done = 0; done < sample_count;) {
-        const int spp = std::min(chunk, sample_count - done);
-        PassArgs a;
-        a.k0 = (uint32_t)seed;
-        a.k1 = (uint32_t)(seed >> 32);
-        a.sample_begin = sample_begin + done;
-        a.n_paths = (int)(npix * spp);
-        k_set_args<<<1, 1, 0, c->stream>>>(c->pass_args.ptr, a);
-        c->kernel_launches++;
-        if (use_graph) {
-            CU_CHECK(c, cudaGraphLaunch(c->wave_graph, c->stream));
-            c->kernel_launches += c->wave_graph_launches;
-        } else {
-            int qrc = queue_wavefront(c, count);
-            if (qrc != 0) return qrc;
+    for (int band = 0; band < n_bands; ++band) {
+        const long long pix0 = band * band_pixels, pix1 = std::min(npix, pix0 + band_pixels);
+        if (pix1 <= pix0) break;
+        for (int done = 0; done < sample_count;) {
+            const int spp = std::min(chunk, sample_count - done);
+            PassArgs a;
+            a.k0 = (uint32_t)seed;
+            a.k1 = (uint32_t)(seed >> 32);
+            a.sample_begin = sample_begin + done;
+            a.pixel_begin = (int)pix0;
+            a.pixel_count = (int)(pix1 - pix0);
+            a.n_paths = (int)((pix1 - pix0) * spp);
+            k_set_args<<<1, 1, 0, c->stream>>>(c->pass_args.ptr, a);
+            c->kernel_launches++;
+            if (use_graph) {
+                CU_CHECK(c, cudaGraphLaunch(c->wave_graph, c->stream));
+                c->kernel_launches += c->wave_graph_launches;
+            } else {
+                int qrc = queue_wavefront(c, count);
+                if (qrc != 0) return qrc;
+            }
+            CU_CHECK(c, cudaGetLastError());
+            done += spp;
         }
-        CU_CHECK(c, cudaGetLastError());
-        done += spp;
     }
     return 0;
 }

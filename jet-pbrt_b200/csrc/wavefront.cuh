@@ -53,6 +53,8 @@ struct PassArgs {
     uint32_t k0, k1;   // sampler key (seed)
     int sample_begin;  // first sample index of this wavefront
     int n_paths;       // pixels x samples of this wavefront
+    int pixel_begin;   // the wavefront covers pixel_order[pixel_begin .. pixel_begin + pixel_count): a BAND of the frame
+    int pixel_count;   //   whose film (12 bytes per pixel) stays L2-resident while its samples accumulate
 };
 
 __global__ void k_set_args(PassArgs* dst, PassArgs v) { *dst = v; }
@@ -91,6 +93,10 @@ __device__ __forceinline__ void film_add(const WfParams& p, int pixel, const f3&
         return;
     }
     float* px = p.film + 3 * (size_t)pixel;
+#ifdef JPB_EXPERIMENT_FILM_X_ONLY  // timing experiment only (wrong image): how much of a stage is the float atomics?
+    if (c.x != 0.f) atomicAdd(px + 0, c.x + c.y + c.z);
+    return;
+#endif
     if (c.x != 0.f) atomicAdd(px + 0, c.x);
     if (c.y != 0.f) atomicAdd(px + 1, c.y);
     if (c.z != 0.f) atomicAdd(px + 2, c.z);
@@ -115,8 +121,8 @@ __global__ void __launch_bounds__(kBlock) k_generate(const __grid_constant__ WfP
     const f3 up = mk3(cam.up[0], cam.up[1], cam.up[2]);
     const int W = p.sc.width;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_paths; i += gridDim.x * blockDim.x) {
-        const int pixel = __ldg(p.sc.pixel_order + i % p.npix);
-        const int sample = a.sample_begin + i / p.npix;
+        const int pixel = __ldg(p.sc.pixel_order + a.pixel_begin + i % a.pixel_count);
+        const int sample = a.sample_begin + i / a.pixel_count;
         const int x = pixel % W, y = pixel / W;
         const float4 u = rng_block(key, (uint32_t)pixel, (uint32_t)sample, 0u);
         const float fx = (float)x + u.x, fy = (float)y + u.y;  // sampler.h:152
@@ -267,8 +273,11 @@ __device__ __forceinline__ int warp_fetch_n(int* counter, int amount) {
     return __shfl_sync(kFull, base, 0);
 }
 
+#ifndef JPB_LOGIC_MIN_BLOCKS
+#define JPB_LOGIC_MIN_BLOCKS 1
+#endif
 template <bool WHITTED>
-__global__ void __launch_bounds__(kBlock) k_logic(const __grid_constant__ WfParams p, int it) {
+__global__ void __launch_bounds__(kBlock, JPB_LOGIC_MIN_BLOCKS) k_logic(const __grid_constant__ WfParams p, int it) {
     const DevScene& sc = p.sc;
     const int n = min(p.counters[CNT_RAYS * p.counter_stride + it], p.queue_capacity);
     int* work = p.counters + CNT_W_SHADE * p.counter_stride + it;
@@ -369,9 +378,10 @@ __global__ void __launch_bounds__(kBlock) k_logic(const __grid_constant__ WfPara
     }
 }
 
-// 3 resident blocks per SM (80 registers, ~150 bytes of spills) measured 5-9 % faster than 2 (111 registers)
+// Resident blocks per SM: 2 (111 registers) -> 3 (80) measured 5-9 % faster, 3 -> 4 (64 registers, the same ~150 bytes
+// of spills, which come from the out-of-line calls) another 3 % (gpurun_out/ab_shade.log)
 #ifndef JPB_SHADE_MIN_BLOCKS
-#define JPB_SHADE_MIN_BLOCKS 3
+#define JPB_SHADE_MIN_BLOCKS 4
 #endif
 template <int KIND, bool WHITTED = false>
 __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ WfParams p, int it) {
