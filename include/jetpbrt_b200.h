@@ -56,6 +56,13 @@ typedef enum jpbrt_integrator {
  * The description is copied; the caller may free it afterwards. */
 int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out_ctx);
 
+/* Same with flags.  JPBRT_UPLOAD_GPU_BVH: build the BVH on the device (linear BVH: Morton sort + radix tree +
+ * bottom-up refit, csrc/bvh_build.cuh) instead of the host's binned-SAH build -- replaces the recursive build of
+ * FBVH_Node (bvh.h:59-92) for scenes whose build time matters; ~100x faster to build, slower to traverse.  Hits do
+ * not depend on the tree.  jpbrt_upload_scene reads the default from the environment (JPBRT_BVH_BUILDER=gpu). */
+#define JPBRT_UPLOAD_GPU_BVH 1u
+int jpbrt_upload_scene_ex(const jpbrt_scene_desc* desc, int device, unsigned flags, jpbrt_ctx** out_ctx);
+
 /* Replaces FIntegrator::DoRender (integrator.cc:82-111) for sample indices
  * [sample_begin, sample_begin + sample_count) of EVERY pixel: adds the raw radiance of each
  * sample (FPathIntegratorIteration::Li, integrator.cc:316-403) into the device film.
@@ -121,6 +128,8 @@ typedef struct jpbrt_stats {
     uint64_t n_nodes, n_prim_slots, scene_bytes;
     double   bvh_build_seconds;
     uint64_t paths_in_flight;  /* capacity of the path pool (paths per wavefront), 0 before the first pass */
+    uint64_t bvh_builder;      /* 0 host binned SAH, 1 GPU linear BVH (JPBRT_UPLOAD_GPU_BVH) */
+    double   bvh_device_seconds; /* GPU builder: box upload + sort/tree/refit kernels + tree download (part of bvh_build_seconds) */
 } jpbrt_stats;
 int jpbrt_get_stats(jpbrt_ctx* ctx, jpbrt_stats* out);
 
@@ -175,6 +184,10 @@ int jpbrt_device_count(void);
  * 4 prim_slot (int); 5 materials, 6 lights (float4 records).  Copies up to `capacity` 32-bit words
  * into `out` (may be NULL) and returns the total number of 32-bit words, or a negative status. */
 long long jpbrt_debug_flatten(const jpbrt_scene_desc* desc, int what, void* out, long long capacity);
+
+/* The same tables (0 nodes, 1 slots, 2 slot_nrm, 3 slot_ml, 4 prim_slot) as a CONTEXT holds them -- i.e. of the tree
+ * its builder (host SAH or GPU LBVH) actually produced; for validating a device-built BVH. */
+long long jpbrt_debug_ctx_table(jpbrt_ctx* ctx, int what, void* out, long long capacity);
 
 const char* jpbrt_version(void);
 

@@ -52,6 +52,7 @@ class SceneDesc(C.Structure):
 
 
 SHAPE_TRIANGLE, SHAPE_RECTANGLE, SHAPE_SPHERE, SHAPE_DISK = 0, 1, 2, 3
+UPLOAD_GPU_BVH = 1  # jpbrt_upload_scene_ex flag
 MAT_MATTE, MAT_MIRROR, MAT_GLASS, MAT_PLASTIC, MAT_METAL = 0, 1, 2, 3, 4
 LIGHT_ENVIRONMENT, LIGHT_AREA, LIGHT_POINT, LIGHT_DIRECTION = 0, 1, 2, 3
 
@@ -64,7 +65,8 @@ class Stats(C.Structure):
                 ("ms_generate", C.c_double), ("ms_extend", C.c_double), ("ms_shade", C.c_double),
                 ("ms_connect", C.c_double), ("ms_finalize", C.c_double),
                 ("n_nodes", C.c_uint64), ("n_prim_slots", C.c_uint64), ("scene_bytes", C.c_uint64),
-                ("bvh_build_seconds", C.c_double), ("paths_in_flight", C.c_uint64)]
+                ("bvh_build_seconds", C.c_double), ("paths_in_flight", C.c_uint64), ("bvh_builder", C.c_uint64),
+                ("bvh_device_seconds", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -72,13 +74,13 @@ class Stats(C.Structure):
 
 # Every symbol include/jetpbrt_b200.h declares (tests check the library exports them all).
 EXPORTS = [
-    "jpbrt_upload_scene", "jpbrt_render_pass", "jpbrt_read_film", "jpbrt_clear_film", "jpbrt_reset_stats", "jpbrt_destroy",
+    "jpbrt_upload_scene", "jpbrt_upload_scene_ex", "jpbrt_render_pass", "jpbrt_read_film", "jpbrt_clear_film", "jpbrt_reset_stats", "jpbrt_destroy",
     "jpbrt_last_error", "jpbrt_render", "jpbrt_render_integrator", "jpbrt_film_device_ptr", "jpbrt_film_num_floats", "jpbrt_stream",
     "jpbrt_synchronize", "jpbrt_finalize_film_device", "jpbrt_reupload_scene", "jpbrt_set_option",
     "jpbrt_get_stats", "jpbrt_unit_intersect_shape", "jpbrt_unit_scene_intersect", "jpbrt_unit_scene_occluded",
     "jpbrt_unit_bsdf", "jpbrt_unit_light_sample", "jpbrt_unit_emitted", "jpbrt_unit_generate_rays",
     "jpbrt_unit_rng_block", "jpbrt_scene_info", "jpbrt_scene_builtin", "jpbrt_scene_get_desc",
-    "jpbrt_scene_free", "jpbrt_save_image", "jpbrt_version", "jpbrt_device_count", "jpbrt_debug_flatten",
+    "jpbrt_scene_free", "jpbrt_save_image", "jpbrt_version", "jpbrt_device_count", "jpbrt_debug_flatten", "jpbrt_debug_ctx_table",
 ]
 
 
@@ -97,6 +99,7 @@ def _load():
     lib.jpbrt_last_error.restype = C.c_char_p
     lib.jpbrt_last_error.argtypes = [P]
     lib.jpbrt_upload_scene.argtypes = [C.POINTER(SceneDesc), I, C.POINTER(P)]
+    lib.jpbrt_upload_scene_ex.argtypes = [C.POINTER(SceneDesc), I, C.c_uint, C.POINTER(P)]
     lib.jpbrt_render_pass.argtypes = [P, I, I, C.c_uint64]
     lib.jpbrt_read_film.argtypes = [P, F, I, I]
     lib.jpbrt_clear_film.argtypes = [P]
@@ -136,6 +139,8 @@ def _load():
     lib.jpbrt_device_count.restype = I
     lib.jpbrt_debug_flatten.argtypes = [C.POINTER(SceneDesc), I, P, C.c_longlong]
     lib.jpbrt_debug_flatten.restype = C.c_longlong
+    lib.jpbrt_debug_ctx_table.argtypes = [P, I, P, C.c_longlong]
+    lib.jpbrt_debug_ctx_table.restype = C.c_longlong
     return lib
 
 
@@ -223,10 +228,15 @@ class HostScene:
 class Context:
     """jpbrt_ctx: a scene uploaded to one GPU plus its film and wavefront buffers."""
 
-    def __init__(self, scene: HostScene, device: int = 0):
+    def __init__(self, scene: HostScene, device: int = 0, gpu_bvh: bool | None = None):
+        """gpu_bvh: True = build the BVH on the device (JPBRT_UPLOAD_GPU_BVH), False = host binned SAH,
+        None = the library default (host, unless JPBRT_BVH_BUILDER=gpu is set)."""
         self._ctx = C.c_void_p()
         self.scene = scene
-        rc = lib.jpbrt_upload_scene(scene.desc, device, C.byref(self._ctx))
+        if gpu_bvh is None:
+            rc = lib.jpbrt_upload_scene(scene.desc, device, C.byref(self._ctx))
+        else:
+            rc = lib.jpbrt_upload_scene_ex(scene.desc, device, UPLOAD_GPU_BVH if gpu_bvh else 0, C.byref(self._ctx))
         _check(rc, None)
         self.width = scene.d.camera.width
         self.height = scene.d.camera.height
@@ -287,6 +297,15 @@ class Context:
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
 
         return torch.as_tensor(_Arr(), device=f"cuda:{self.device}")
+
+    def table(self, name: str) -> np.ndarray:
+        """The flattened table `name` (nodes, slots, slot_nrm, slot_ml, prim_slot) of the tree this context's builder produced."""
+        what, dtype = _TABLES[name]
+        n = lib.jpbrt_debug_ctx_table(self._ctx, what, None, 0)
+        _check(min(n, 0), self._ctx)
+        out = np.empty(n, dtype=dtype)
+        lib.jpbrt_debug_ctx_table(self._ctx, what, out.ctypes.data_as(C.c_void_p), n)
+        return out
 
     def scene_info(self) -> np.ndarray:
         o = np.zeros(7, dtype=np.float32)

@@ -16,6 +16,7 @@
 
 #include "../../include/jetpbrt_b200.h"
 #include "scene_flatten.h"
+#include "bvh_build.cuh"
 #include "wavefront.cuh"
 
 using namespace jpbrt;
@@ -291,24 +292,63 @@ long long jpbrt_debug_flatten(const jpbrt_scene_desc* desc, int what, void* out,
     return words;
 }
 
+long long jpbrt_debug_ctx_table(jpbrt_ctx* c, int what, void* out, long long capacity) {
+    if (!c) return set_error(nullptr, JPBRT_ERR_INVALID, "ctx is null");
+    const HostScene& hs = c->hs;
+    const void* src = nullptr;
+    long long words = 0;
+    switch (what) {
+    case 0: src = hs.nodes.data(); words = (long long)hs.nodes.size() * 4; break;
+    case 1: src = hs.slots.data(); words = (long long)hs.slots.size() * 4; break;
+    case 2: src = hs.slot_nrm.data(); words = (long long)hs.slot_nrm.size() * 4; break;
+    case 3: src = hs.slot_ml.data(); words = (long long)hs.slot_ml.size() * 2; break;
+    case 4: src = hs.prim_slot.data(); words = (long long)hs.prim_slot.size(); break;
+    default: return set_error(c, JPBRT_ERR_INVALID, "unknown table %d", what);
+    }
+    if (out && capacity > 0) memcpy(out, src, (size_t)std::min(words, capacity) * 4);
+    return words;
+}
+
 const char* jpbrt_version(void) { return "jet-pbrt_b200 0.1 (sm_100a wavefront path tracer)"; }
 
 const char* jpbrt_last_error(const jpbrt_ctx* ctx) { return ctx ? ctx->error.c_str() : g_last_error.c_str(); }
 
 int jpbrt_upload_scene(const jpbrt_scene_desc* desc, int device, jpbrt_ctx** out_ctx) {
+    unsigned flags = 0;
+    if (const char* v = getenv("JPBRT_BVH_BUILDER")) flags |= (!strcmp(v, "gpu") || !strcmp(v, "lbvh")) ? JPBRT_UPLOAD_GPU_BVH : 0u;
+    return jpbrt_upload_scene_ex(desc, device, flags, out_ctx);
+}
+
+int jpbrt_upload_scene_ex(const jpbrt_scene_desc* desc, int device, unsigned flags, jpbrt_ctx** out_ctx) {
     if (!out_ctx) return set_error(nullptr, JPBRT_ERR_INVALID, "out_ctx is null");
     *out_ctx = nullptr;
+    if (flags & ~(unsigned)JPBRT_UPLOAD_GPU_BVH) return set_error(nullptr, JPBRT_ERR_INVALID, "unknown upload flags 0x%x", flags);
     jpbrt_ctx* c = new jpbrt_ctx();
     std::string err;
-    int rc = FlattenScene(desc, &c->hs, &err);
-    if (rc != 0) { set_error(nullptr, rc, "%s", err.c_str()); delete c; return rc; }
-    rc = select_device(nullptr, device);
-    if (rc != 0) { delete c; return rc; }
+    int rc;
+    if (flags & JPBRT_UPLOAD_GPU_BVH) {
+        // the BVH is built on the device (csrc/bvh_build.cuh): the device comes first
+        rc = select_device(nullptr, device);
+        if (rc != 0) { delete c; return rc; }
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            rc = set_error(nullptr, JPBRT_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+            delete c;
+            return rc;
+        }
+        rc = FlattenScene(desc, &c->hs, &err, lbvh::build_on_device, (void*)c->stream);
+        if (rc != 0) { set_error(nullptr, rc, "%s", err.c_str()); cudaStreamDestroy(c->stream); delete c; return rc; }
+    } else {
+        // validate and flatten first: a malformed description is reported even where no device exists
+        rc = FlattenScene(desc, &c->hs, &err);
+        if (rc != 0) { set_error(nullptr, rc, "%s", err.c_str()); delete c; return rc; }
+        rc = select_device(nullptr, device);
+        if (rc != 0) { delete c; return rc; }
+    }
     c->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     auto fail = [&](int code) { jpbrt_destroy(c); return code; };
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
+    if (!c->stream && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
         return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError())));
     HostScene& hs = c->hs;
     cudaError_t e = cudaSuccess;
@@ -633,6 +673,8 @@ int jpbrt_get_stats(jpbrt_ctx* c, jpbrt_stats* out) {
     out->n_prim_slots = c->dsc.n_slots;
     out->scene_bytes = c->hs.Bytes();
     out->bvh_build_seconds = c->hs.bvh_build_seconds;
+    out->bvh_builder = (uint64_t)c->hs.bvh_builder;
+    out->bvh_device_seconds = c->hs.bvh_device_seconds;
     out->paths_in_flight = (uint64_t)c->paths_in_flight;
     return 0;
 }

@@ -321,7 +321,7 @@ int LeafRef(int first, int count) { return ~((first << kLeafCountBits) | count);
 
 }  // namespace
 
-int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err) {
+int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, BvhBuildFn build, void* build_user) {
     auto fail = [&](int code, const char* msg) { if (err) *err = msg; return code; };
     if (!d || !out) return fail(JPBRT_ERR_INVALID, "null scene description");
     if (d->n_primitives <= 0 || !d->primitives || !d->shapes) return fail(JPBRT_ERR_INVALID, "scene has no primitives");
@@ -457,8 +457,67 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err) {
     const float pad = 4e-6f * maxabs + 1e-30f;
     int nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
     Builder bld(boxes, nthreads);
-    int root = bld.Alloc();
-    bld.Build(root, 0, N);
+    int root = -1;
+    if (build && N >= 2) {
+        // external (GPU) builder: a binary radix tree over the Morton-sorted primitives; cut it into our leaves here
+        static_assert(sizeof(Box) == 6 * sizeof(float), "Box must be 6 packed floats");
+        BuiltBvh built;
+        std::string berr;
+        if (build(build_user, reinterpret_cast<const float*>(boxes.data()), N, &built, &berr) && (int)built.order.size() == N &&
+            (int)built.nodes.size() == N - 1) {
+            bld.idx = built.order;
+            bld.nodes.clear();
+            bld.nodes.reserve((size_t)2 * N);
+            struct Todo { int built_ref; int tmp; int depth; };
+            int max_depth = 0;
+            std::vector<Todo> todo;
+            auto new_tmp = [&]() { bld.nodes.emplace_back(); return (int)bld.nodes.size() - 1; };
+            root = new_tmp();
+            todo.push_back(Todo{0, root, 0});
+            while (!todo.empty()) {
+                Todo t = todo.back();
+                todo.pop_back();
+                max_depth = std::max(max_depth, t.depth);
+                if (t.built_ref < 0) {  // a single primitive
+                    const int pos = ~t.built_ref;
+                    TmpNode& T = bld.nodes[t.tmp];
+                    T.box = boxes[built.order[pos]];
+                    T.first = pos;
+                    T.count = 1;
+                    continue;
+                }
+                const BuiltNode& b = built.nodes[t.built_ref];
+                for (int a = 0; a < 3; ++a) { bld.nodes[t.tmp].box.mn[a] = b.mn[a]; bld.nodes[t.tmp].box.mx[a] = b.mx[a]; }
+                const int count = b.last - b.first + 1;
+                if (count <= bld.max_leaf && count <= kMaxLeafPrims) {
+                    bld.nodes[t.tmp].first = b.first;
+                    bld.nodes[t.tmp].count = count;
+                    continue;
+                }
+                const int l = new_tmp(), r = new_tmp();
+                bld.nodes[t.tmp].left = l;
+                bld.nodes[t.tmp].right = r;
+                bld.nodes[t.tmp].count = 0;
+                todo.push_back(Todo{b.right, r, t.depth + 1});
+                todo.push_back(Todo{b.left, l, t.depth + 1});
+            }
+            hs.bvh_builder = 1;
+            hs.bvh_device_seconds = built.seconds;
+            if (max_depth > 60) {  // deeper than the traversal stack (pathological duplicate centroids): use the SAH builder
+                hs.bvh_builder = 0;
+                root = -1;
+                bld.nodes.assign(std::max<size_t>(2 * (size_t)N, 2), TmpNode());
+                for (int i = 0; i < N; ++i) bld.idx[i] = i;
+                bld.next = 0;
+            }
+        } else if (!berr.empty()) {
+            return fail(JPBRT_ERR_CUDA, berr.c_str());
+        }
+    }
+    if (root < 0) {
+        root = bld.Alloc();
+        bld.Build(root, 0, N);
+    }
 
     // flatten: inner nodes depth-first, leaves reference idx ranges (== slot ranges)
     std::vector<Float4>& fn = hs.nodes;

@@ -28,14 +28,33 @@ struct HostScene {
     int n_prims = 0;
     bool has_null_material = false;
     double bvh_build_seconds = 0;
+    int bvh_builder = 0;  // 0 host binned SAH, 1 GPU LBVH
+    double bvh_device_seconds = 0;  // GPU builder only: upload of the boxes + kernels + download of the tree
     size_t Bytes() const {
         return (nodes.size() + slots.size() + slot_nrm.size() + materials.size() + lights.size() + slot_frame.size()) * sizeof(Float4) +
                slot_ml.size() * sizeof(Int2) + (inf_lights.size() + prim_slot.size() + nee_lights.size()) * sizeof(int);  // pixel_order is film state, not scene
     }
 };
 
-// Returns 0 or a negative jpbrt_status; *err receives a message.
-int FlattenScene(const jpbrt_scene_desc* desc, HostScene* out, std::string* err);
+// BVH topology handed to the flattener by an external builder (the GPU LBVH builder, csrc/bvh_build.cuh): a binary
+// radix tree over the primitives in `order`.  Inner node i covers order[first..last]; a child reference >= 0 is an
+// inner node, < 0 is the single primitive at position ~ref of `order`.  Boxes are UNPADDED primitive-bounds unions.
+struct BuiltNode {
+    float mn[3], mx[3];
+    int left, right;
+    int first, last;
+};
+struct BuiltBvh {
+    std::vector<BuiltNode> nodes;  // n_prims - 1 inner nodes, root = 0
+    std::vector<int> order;        // sorted position -> primitive index
+    double seconds = 0;            // device time + transfers
+};
+// prim_boxes: 6 floats per primitive (min xyz, max xyz).  Returns false to fall back to the host builder.
+typedef bool (*BvhBuildFn)(void* user, const float* prim_boxes, int n_prims, BuiltBvh* out, std::string* err);
+
+// Returns 0 or a negative jpbrt_status; *err receives a message.  With `build` the BVH topology comes from that
+// builder (leaves are cut where a subtree holds <= kMaxLeafPrims primitives); without, from the host's binned-SAH builder.
+int FlattenScene(const jpbrt_scene_desc* desc, HostScene* out, std::string* err, BvhBuildFn build = nullptr, void* build_user = nullptr);
 
 // One shape -> one slot (+ normal/tag), as used by the unit kernels.  Returns false on a bad type.
 bool MakeSlot(const jpbrt_shape& shape, int prim_index, Float4 slot[4], Float4* nrm, float bounds_min[3], float bounds_max[3]);

@@ -33,21 +33,20 @@ def slot_bounds(slots, nrm):
     return lo, hi, tag >> 2
 
 
-@pytest.mark.parametrize("name,scale", [("cornell", 1.0), ("bunny", 0.3), ("glossy", 1.0), ("large", 0.03)])
-def test_bvh_is_a_partition_with_containing_boxes(pkg, name, scale):
-    sc = pkg.HostScene.builtin(name, 32, 32, scale)
-    nodes, refs, slots, nrm = decode(pkg, sc)
-    n_prims = sc.d.n_primitives
+def check_tree(nodes, refs, slots, nrm, prim_slot, n_prims):
+    """The flattened BVH is a partition of the primitives into leaves of <= 4 whose boxes nest (any builder)."""
     assert len(slots) == n_prims == len(nrm)
     lo, hi, prim_of_slot = slot_bounds(slots, nrm)
     assert sorted(prim_of_slot.tolist()) == list(range(n_prims))  # every primitive in exactly one slot
-    prim_slot = pkg.debug_flatten(sc, "prim_slot")
     assert np.array_equal(prim_of_slot[prim_slot], np.arange(n_prims))
     seen = np.zeros(n_prims, int)
     visited = np.zeros(len(nodes), int)
-
-    def walk(ref, blo, bhi, depth):
+    max_depth = 0
+    todo = [(0, -np.full(3, 1e30), np.full(3, 1e30), 0)]
+    while todo:
+        ref, blo, bhi, depth = todo.pop()
         assert depth < 64, "tree deeper than the traversal stack"
+        max_depth = max(max_depth, depth)
         if ref < 0:
             bits = ~ref
             first, cnt = bits >> 4, bits & 15
@@ -55,7 +54,7 @@ def test_bvh_is_a_partition_with_containing_boxes(pkg, name, scale):
             for s in range(first, first + cnt):
                 seen[s] += 1
                 assert (lo[s] >= blo - 1e-6).all() and (hi[s] <= bhi + 1e-6).all(), "leaf box does not contain its primitive"
-            return (lo[first:first + cnt].min(0), hi[first:first + cnt].max(0)) if cnt else (blo, bhi)
+            continue
         visited[ref] += 1
         nd = nodes[ref]
         lmin, lmax = nd[[0, 1, 2]], nd[[3, 4, 5]]
@@ -63,15 +62,18 @@ def test_bvh_is_a_partition_with_containing_boxes(pkg, name, scale):
         for (cmin, cmax) in ((lmin, lmax), (rmin, rmax)):
             if np.isfinite(cmin).all():
                 assert (cmin >= blo - 1e-6).all() and (cmax <= bhi + 1e-6).all(), "child box escapes its parent"
-        walk(int(refs[ref, 0]), lmin, lmax, depth + 1)
-        walk(int(refs[ref, 1]), rmin, rmax, depth + 1)
-
-    import sys
-    sys.setrecursionlimit(10000)
-    big = np.full(3, 1e30)
-    walk(0, -big, big, 0)
+        todo.append((int(refs[ref, 0]), lmin, lmax, depth + 1))
+        todo.append((int(refs[ref, 1]), rmin, rmax, depth + 1))
     assert (seen == 1).all(), "a primitive is missing from, or duplicated in, the leaves"
     assert (visited == 1).all(), "an inner node is unreachable or shared"
+    return max_depth
+
+
+@pytest.mark.parametrize("name,scale", [("cornell", 1.0), ("bunny", 0.3), ("glossy", 1.0), ("large", 0.03)])
+def test_bvh_is_a_partition_with_containing_boxes(pkg, name, scale):
+    sc = pkg.HostScene.builtin(name, 32, 32, scale)
+    nodes, refs, slots, nrm = decode(pkg, sc)
+    check_tree(nodes, refs, slots, nrm, pkg.debug_flatten(sc, "prim_slot"), sc.d.n_primitives)
 
 
 def test_single_primitive_scene_gets_a_wrapped_root(pkg):
