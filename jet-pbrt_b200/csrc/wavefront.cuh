@@ -86,6 +86,29 @@ constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Wavefront state (path / hit / shadow records, kind queues) is written once and read once or twice, GBs per pass:
+// it is loaded and stored with the streaming (evict-first) cache policy so that it does not push the scene's
+// nodes and primitives -- and the film band -- out of L1/L2.  JPB_STREAM_HINTS=0 builds the plain-policy variant.
+#ifndef JPB_STREAM_HINTS
+#define JPB_STREAM_HINTS 1
+#endif
+template <typename T>
+__device__ __forceinline__ T ld_stream(const T* p) {
+#if JPB_STREAM_HINTS
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <typename T>
+__device__ __forceinline__ void st_stream(T* p, const T& v) {
+#if JPB_STREAM_HINTS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 // accumulate: film[pixel] += c   (radiance sums; FFilm::AddColor happens at finalize)
 __device__ __forceinline__ void film_add(const WfParams& p, int pixel, const f3& c) {
     if (!(isfinite(c.x) && isfinite(c.y) && isfinite(c.z))) {  // the reference only logs these (integrator.cc:104)
@@ -93,10 +116,6 @@ __device__ __forceinline__ void film_add(const WfParams& p, int pixel, const f3&
         return;
     }
     float* px = p.film + 3 * (size_t)pixel;
-#ifdef JPB_EXPERIMENT_FILM_X_ONLY  // timing experiment only (wrong image): how much of a stage is the float atomics?
-    if (c.x != 0.f) atomicAdd(px + 0, c.x + c.y + c.z);
-    return;
-#endif
     if (c.x != 0.f) atomicAdd(px + 0, c.x);
     if (c.y != 0.f) atomicAdd(px + 1, c.y);
     if (c.z != 0.f) atomicAdd(px + 2, c.z);
@@ -128,9 +147,9 @@ __global__ void __launch_bounds__(kBlock) k_generate(const __grid_constant__ WfP
         const float fx = (float)x + u.x, fy = (float)y + u.y;  // sampler.h:152
         const f3 dir = front + right * (fx / cam.res_x - 0.5f) + up * (0.5f - fy / cam.res_y);  // camera.h:54-55
         const f3 d = normalize(dir);
-        p.ray_o[0][i] = make_float4(pos.x, pos.y, pos.z, __int_as_float(pixel));
-        p.ray_d[0][i] = make_float4(d.x, d.y, d.z, __int_as_float(sample & 0xffffff));
-        p.ray_b[0][i] = make_float4(1.f, 1.f, 1.f, 0.f);
+        st_stream(&p.ray_o[0][i], make_float4(pos.x, pos.y, pos.z, __int_as_float(pixel)));
+        st_stream(&p.ray_d[0][i], make_float4(d.x, d.y, d.z, __int_as_float(sample & 0xffffff)));
+        st_stream(&p.ray_b[0][i], make_float4(1.f, 1.f, 1.f, 0.f));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.counters[CNT_RAYS * p.counter_stride + 0] = n_paths;
@@ -146,13 +165,13 @@ struct ExtendIO {
     const float4* rd;
     float2* hit;
     __device__ __forceinline__ bool load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
-        o = mk3(ro[i]);
-        d = mk3(rd[i]);
+        o = mk3(ld_stream(&ro[i]));
+        d = mk3(ld_stream(&rd[i]));
         tmin = JPBRT_RAY_TMIN;                 // FRay default min_t, geometry.h:395
         tmax = __int_as_float(0x7f800000);     // kInfinity
         return true;
     }
-    __device__ __forceinline__ void store(int i, int slot, float t) const { hit[i] = make_float2(t, __int_as_float(slot)); }
+    __device__ __forceinline__ void store(int i, int slot, float t) const { st_stream(&hit[i], make_float2(t, __int_as_float(slot))); }
 };
 
 // MINB = resident blocks per SM the register allocation must allow (5: 48 registers, 6: 40; measured on B200:
@@ -183,17 +202,17 @@ struct ConnectIO {
     const WfParams* p;
     unsigned* n_traced;
     __device__ __forceinline__ bool load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
-        const float4 so = p->sh_o[i];
+        const float4 so = ld_stream(&p->sh_o[i]);
         if (so.w < 0.f) return false;
         o = mk3(so);
-        d = mk3(p->sh_d[i]);
+        d = mk3(ld_stream(&p->sh_d[i]));
         tmin = JPBRT_RAY_TMIN;  // scene.h:38
         tmax = so.w;            // dist - 0.001
         ++*n_traced;
         return true;
     }
     __device__ __forceinline__ void store(int i, int slot, float) const {
-        if (slot < 0) film_add(*p, __float_as_int(p->sh_d[i].w), mk3(p->sh_c[i]));  // integrator.cc:367-370
+        if (slot < 0) film_add(*p, __float_as_int(ld_stream(&p->sh_d[i]).w), mk3(ld_stream(&p->sh_c[i])));  // integrator.cc:367-370
     }
 };
 
@@ -251,9 +270,9 @@ __device__ __forceinline__ void append_next(const WfParams& p, int* next_count, 
                 atomicAdd(p.stats + ST_DROPPED, 1ull);
                 return;
             }
-            p.ray_o[nbuf][dst] = no;
-            p.ray_d[nbuf][dst] = nd;
-            p.ray_b[nbuf][dst] = nbeta;
+            st_stream(&p.ray_o[nbuf][dst], no);
+            st_stream(&p.ray_d[nbuf][dst], nd);
+            st_stream(&p.ray_b[nbuf][dst], nbeta);
         }
     }
 }
@@ -274,7 +293,7 @@ __device__ __forceinline__ int warp_fetch_n(int* counter, int amount) {
 }
 
 #ifndef JPB_LOGIC_MIN_BLOCKS
-#define JPB_LOGIC_MIN_BLOCKS 1
+#define JPB_LOGIC_MIN_BLOCKS 4  // 64 registers; 5-6 blocks (48 / 40 registers) measured equal (gpurun_out/ab_shade.log)
 #endif
 template <bool WHITTED>
 __global__ void __launch_bounds__(kBlock, JPB_LOGIC_MIN_BLOCKS) k_logic(const __grid_constant__ WfParams p, int it) {
@@ -297,8 +316,8 @@ __global__ void __launch_bounds__(kBlock, JPB_LOGIC_MIN_BLOCKS) k_logic(const __
             int kind = -1;
             float4 no = make_float4(0, 0, 0, 0), nd = no, nbeta = no;
             if (c < nchunks && i < n) {
-                const float4 rd = p.ray_d[buf][i];
-                const float2 h = p.hit[i];
+                const float4 rd = ld_stream(&p.ray_d[buf][i]);
+                const float2 h = ld_stream(&p.hit[i]);
                 const int fl = __float_as_int(rd.w);
                 const int bounce = (fl >> 24) & 0x7f;
                 const bool specular = fl < 0;
@@ -307,8 +326,8 @@ __global__ void __launch_bounds__(kBlock, JPB_LOGIC_MIN_BLOCKS) k_logic(const __
                 const bool in_depth = WHITTED || bounce < sc.max_depth;           // Whitted bounds the depth where it spawns (:157)
                 if (slot < 0) {
                     if (add_emission && sc.n_inf_lights > 0) {
-                        const int pixel = __float_as_int(p.ray_o[buf][i].w);
-                        const f3 beta = mk3(p.ray_b[buf][i]);
+                        const int pixel = __float_as_int(ld_stream(&p.ray_o[buf][i]).w);
+                        const f3 beta = mk3(ld_stream(&p.ray_b[buf][i]));
                         for (int k = 0; k < sc.n_inf_lights; ++k)  // integrator.cc:334-335
                             film_add(p, pixel, cmul(beta, mk3(ldg4(sc.lights + (size_t)sc.inf_lights[k] * kLightStride))));
                     }
@@ -317,8 +336,8 @@ __global__ void __launch_bounds__(kBlock, JPB_LOGIC_MIN_BLOCKS) k_logic(const __
                     const bool emits = add_emission && ml.y >= 0 && !(WHITTED && ml.x < 0);  // Whitted: null material returns first (:136)
                     const bool pass = in_depth && ml.x < 0;
                     if (emits || pass) {
-                        const float4 ro = p.ray_o[buf][i];
-                        const float4 rb = p.ray_b[buf][i];
+                        const float4 ro = ld_stream(&p.ray_o[buf][i]);
+                        const float4 rb = ld_stream(&p.ray_b[buf][i]);
                         const f3 o = mk3(ro), d = mk3(rd);
                         const f3 P = o + h.x * d;  // FRay::operator(), geometry.h:413-417
                         if (emits) {
@@ -338,9 +357,9 @@ __global__ void __launch_bounds__(kBlock, JPB_LOGIC_MIN_BLOCKS) k_logic(const __
                         const Float4* mat = sc.materials + (size_t)ml.x * kMaterialStride;
                         const int type = __float_as_int(ldg4(mat).w);
                         if (type == MAT_PLASTIC) {  // the lobe pick is the first number of the bounce's block (material.cc:14)
-                            const int pixel = __float_as_int(p.ray_o[buf][i].w);
+                            const int pixel = __float_as_int(ld_stream(&p.ray_o[buf][i]).w);
                             const uint32_t blk = 1u + (uint32_t)bounce * (uint32_t)p.blocks_per_bounce;
-                            const uint32_t node = WHITTED ? __float_as_uint(p.ray_b[buf][i].w) : 0u;
+                            const uint32_t node = WHITTED ? __float_as_uint(ld_stream(&p.ray_b[buf][i]).w) : 0u;
                             const float4 u0 = rng_block(key, (uint32_t)pixel, (uint32_t)(fl & 0xffffff), blk, node);
                             kind = (u0.x < ldg4(mat + 2).y) ? KIND_LAMBERT : KIND_MF_DIELECTRIC;
                         } else {
@@ -371,7 +390,7 @@ __global__ void __launch_bounds__(kBlock, JPB_LOGIC_MIN_BLOCKS) k_logic(const __
 #pragma unroll
             for (int k = 0; k < NUM_KINDS; ++k) {
                 if (kinds[c] == k)
-                    p.kind_queue[(size_t)k * p.queue_capacity + bases[k] + __popc(masks[c][k] & ((1u << lane_id()) - 1))] = base + 32 * c + lane_id();
+                    st_stream(&p.kind_queue[(size_t)k * p.queue_capacity + bases[k] + __popc(masks[c][k] & ((1u << lane_id()) - 1))], base + 32 * c + lane_id());
                 bases[k] += __popc(masks[c][k]);
             }
         }
@@ -410,11 +429,11 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
             bool alive = false, alive2 = false;  // alive2: a mirror's second ray in the Whitted mode
             float4 no = make_float4(0, 0, 0, 0), nd = no, nbeta = no, nbeta2 = no;
             if (qi < n) {
-                const int i = queue[qi];
-                const float4 ro = p.ray_o[buf][i];
-                const float4 rd = p.ray_d[buf][i];
-                const float4 rb = p.ray_b[buf][i];
-                const float2 h = p.hit[i];
+                const int i = ld_stream(&queue[qi]);
+                const float4 ro = ld_stream(&p.ray_o[buf][i]);
+                const float4 rd = ld_stream(&p.ray_d[buf][i]);
+                const float4 rb = ld_stream(&p.ray_b[buf][i]);
+                const float2 h = ld_stream(&p.hit[i]);
                 const f3 o = mk3(ro), d = mk3(rd);
                 f3 beta = mk3(rb);
                 const int pixel = __float_as_int(ro.w);
@@ -464,15 +483,15 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
                             // a degenerate distance (tmax <= 0 or NaN) can hit nothing: the sample is unoccluded
                             const float tmax = dist - 0.001f;
                             if (tmax > 0.f) {
-                                p.sh_o[si] = make_float4(P.x, P.y, P.z, tmax);
-                                p.sh_d[si] = make_float4(sdir.x, sdir.y, sdir.z, ro.w);
-                                p.sh_c[si] = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
+                                st_stream(&p.sh_o[si], make_float4(P.x, P.y, P.z, tmax));
+                                st_stream(&p.sh_d[si], make_float4(sdir.x, sdir.y, sdir.z, ro.w));
+                                st_stream(&p.sh_c[si], make_float4(contrib.x, contrib.y, contrib.z, 0.f));
                             } else {
-                                p.sh_o[si] = make_float4(0.f, 0.f, 0.f, -1.f);
+                                st_stream(&p.sh_o[si], make_float4(0.f, 0.f, 0.f, -1.f));
                                 film_add(p, pixel, contrib);
                             }
                         } else if (fits) {
-                            p.sh_o[si] = make_float4(0.f, 0.f, 0.f, -1.f);
+                            st_stream(&p.sh_o[si], make_float4(0.f, 0.f, 0.f, -1.f));
                         }
                     }
                 }
@@ -528,11 +547,11 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
 __global__ void __launch_bounds__(kBlock) k_debug(const __grid_constant__ WfParams p) {
     const int n = min(p.counters[CNT_RAYS * p.counter_stride + 0], p.queue_capacity);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float2 h = p.hit[i];
+        const float2 h = ld_stream(&p.hit[i]);
         const int slot = __float_as_int(h.y);
         if (slot < 0) continue;
-        const float4 ro = p.ray_o[0][i];
-        const f3 d = mk3(p.ray_d[0][i]);
+        const float4 ro = ld_stream(&p.ray_o[0][i]);
+        const f3 d = mk3(ld_stream(&p.ray_d[0][i]));
         const f3 P = mk3(ro) + h.x * d;
         film_add(p, __float_as_int(ro.w), hit_normal(p.sc, slot, P, d));
     }
