@@ -69,7 +69,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device: int):
-        self.rows, self.proc, self.device = [], None, device
+        self.rows, self.proc, self.device, self.seen = [], None, device, 0
 
     def start(self):
         try:
@@ -83,6 +83,12 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
+            self.seen += 1
+
+    def wait_first_sample(self, timeout_s: float):
+        t0 = time.time()
+        while self.proc and self.seen == 0 and time.time() - t0 < timeout_s:
+            time.sleep(0.01)
 
     def stop(self):
         if not self.proc:
@@ -279,8 +285,18 @@ def main():
         clocks = ClockSampler(local)
         if rank == 0 and not args.no_clocks:
             clocks.start()
+            clocks.wait_first_sample(5.0)  # nvidia-smi's start-up (NVML init, driver locks) stays OUT of the timed region
         barrier()
+        step_resident()                    # one more untimed step (every rank: it holds the reduce) with the sampler polling
+        barrier()
+        ctx.clear_film()
+        ctx.reset_stats()
+        clocks.rows.clear()                # only samples taken during the timed region count
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # Hold the stream for ~100 ms (untimed: before ev0) while the host queues the first steps' launches, so that a
+        # stalled host driver call (seen on these boxes while nvidia-smi polls) cannot leave the GPU idle inside the
+        # timed region: from then on the host stays several steps ahead of the device.
+        torch.cuda._sleep(int(0.1 * 1.9e9))
         ev0.record(stream)
         for _ in range(args.steps):
             step_resident()

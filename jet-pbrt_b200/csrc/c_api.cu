@@ -200,9 +200,10 @@ size_t bytes_per_path(int n_nee_lights) { return 2 * 48 + 8 + 4 * NUM_KINDS + (s
 int ensure_pool(jpbrt_ctx* c) {
     const long long npix = (long long)c->hs.width * c->hs.height;
     const int n_lights = std::max(1, (int)c->hs.nee_lights.size());  // one shadow slot per (vertex, non-black light)
-    // Default pool: 2^25 paths (measured on B200: 8 M -> 32 M paths in flight is +13 % on the bunny scene, +6 % on
-    // Cornell: longer launches, shorter tails), but never more than a quarter of the device's free memory.
-    long long want = c->opt_paths_in_flight > 0 ? c->opt_paths_in_flight : (1ll << 25);
+    // Default pool: 2^26 paths (measured on B200: 8 M -> 32 M paths in flight is +13 % on the bunny scene, +6 % on
+    // Cornell, 32 M -> 52 M -- the 50-spp pass as ONE wavefront instead of two -- another +3.5 %: longer launches,
+    // shorter tails; 14.5 GB of the 180 GB at two lights), but never more than a quarter of the device's free memory.
+    long long want = c->opt_paths_in_flight > 0 ? c->opt_paths_in_flight : (1ll << 26);
     if (c->opt_paths_in_flight <= 0) {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && c->paths_in_flight == 0) {
