@@ -73,6 +73,8 @@ struct jpbrt_ctx {
     DevScene dsc{};
     // wavefront state
     long long paths_in_flight = 0;  // capacity of the path pool
+    long long pool_limit = 0;       // default upper bound of the pool, fixed at the first pass
+    bool pool_explicit = false;     // the pool was sized by the "paths_in_flight" option
     DevBuf<float4> ray_o[2], ray_d[2], ray_b[2], sh_o, sh_d, sh_c;
     DevBuf<float2> hit;
     DevBuf<int> kind_queue;
@@ -197,21 +199,29 @@ int upload_arrays(jpbrt_ctx* c, size_t* bytes) {
 // 48 B shadow slot per non-black light.
 size_t bytes_per_path(int n_nee_lights) { return 2 * 48 + 8 + 4 * NUM_KINDS + (size_t)48 * std::max(1, n_nee_lights); }
 
-int ensure_pool(jpbrt_ctx* c) {
+// Size the path pool for a pass of `paths_needed` camera paths.  An explicit "paths_in_flight" option is honoured
+// exactly; otherwise the pool grows on demand up to the default limit and is never shrunk.
+int ensure_pool(jpbrt_ctx* c, long long paths_needed) {
     const long long npix = (long long)c->hs.width * c->hs.height;
     const int n_lights = std::max(1, (int)c->hs.nee_lights.size());  // one shadow slot per (vertex, non-black light)
-    // Default pool: 2^26 paths (measured on B200: 8 M -> 32 M paths in flight is +13 % on the bunny scene, +6 % on
-    // Cornell, 32 M -> 52 M -- the 50-spp pass as ONE wavefront instead of two -- another +3.5 %: longer launches,
-    // shorter tails; 14.5 GB of the 180 GB at two lights), but never more than a quarter of the device's free memory.
-    long long want = c->opt_paths_in_flight > 0 ? c->opt_paths_in_flight : (1ll << 26);
-    if (c->opt_paths_in_flight <= 0) {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && c->paths_in_flight == 0) {
-            long long fit = (long long)(free_b / 4 / bytes_per_path(n_lights));
-            want = std::min(want, std::max(fit, npix));
-        } else if (c->paths_in_flight > 0) {
-            want = c->paths_in_flight;  // keep what was sized at the first pass
+    long long want;
+    if (c->opt_paths_in_flight > 0) {
+        want = c->opt_paths_in_flight;
+        c->pool_explicit = true;
+    } else {
+        // Default limit: 2^26 paths (measured on B200: 8 M -> 32 M paths in flight is +13 % on the bunny scene, +6 % on
+        // Cornell, 32 M -> 52 M -- the 50-spp pass as ONE wavefront instead of two -- another +3.5 %: longer launches,
+        // shorter tails; 14.5 GB of the 180 GB at two lights), but never more than a quarter of the device's free memory
+        // as it was at the first pass.  A pass that needs fewer paths gets a pool of its own size.
+        if (c->pool_limit == 0) {
+            c->pool_limit = 1ll << 26;
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+                c->pool_limit = std::min(c->pool_limit, std::max((long long)(free_b / 4 / bytes_per_path(n_lights)), npix));
         }
+        want = std::min(c->pool_limit, std::max(paths_needed, npix));
+        if (!c->pool_explicit && c->paths_in_flight >= want) return 0;  // large enough already
+        c->pool_explicit = false;
     }
     // whole samples only: the pool holds k full-frame samples
     long long k = std::max(1ll, want / npix);
@@ -542,7 +552,9 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
     if (sample_begin < 0 || sample_count < 0 || (long long)sample_begin + sample_count > 0xffffff)
         return set_error(c, JPBRT_ERR_INVALID, "sample range [%d, %d) outside [0, 2^24)", sample_begin, sample_begin + sample_count);
     CU_CHECK(c, cudaSetDevice(c->device));
-    int rc = ensure_pool(c);
+    // Whitted traces a mirror vertex twice (bsdf.h:282): leave room for the ray tree, x2 per mirror bounce, at most x8
+    const int tree_growth = (c->opt_integrator == JPBRT_INTEGRATOR_WHITTED && c->has_mirror) ? 1 << std::min(3, std::max(0, c->hs.max_depth - 1)) : 1;
+    int rc = ensure_pool(c, (long long)c->hs.width * c->hs.height * std::max(1, sample_count) * tree_growth);
     if (rc != 0) return rc;
     const long long npix = (long long)c->hs.width * c->hs.height;
     // Bands: a wavefront covers a contiguous range of the Morton pixel order (a compact region of the frame) times as
@@ -553,8 +565,7 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
     const int n_bands = (int)std::max(1ll, (npix + band_target - 1) / band_target);
     const long long band_pixels = (npix + n_bands - 1) / n_bands;
     int chunk_max = (int)std::max(1ll, c->paths_in_flight / band_pixels);
-    if (c->opt_integrator == JPBRT_INTEGRATOR_WHITTED && c->has_mirror)  // room for the ray tree: x2 per mirror bounce, at most x8
-        chunk_max = std::max(1, chunk_max >> std::min(3, std::max(0, c->hs.max_depth - 1)));
+    chunk_max = std::max(1, chunk_max / tree_growth);
     // equal wavefronts: 50 spp with room for 32 run as 25 + 25, not 32 + 18 (short wavefronts are less efficient)
     const int n_waves = (sample_count + chunk_max - 1) / std::max(1, chunk_max);
     const int chunk = n_waves > 0 ? (sample_count + n_waves - 1) / n_waves : chunk_max;
