@@ -192,6 +192,12 @@ static int EnvInt(const char* name, int def) {
 struct Builder {
     int max_leaf = std::max(1, std::min(15, EnvInt("JPBRT_BVH_LEAF", kMaxLeafPrims)));
     float trav_cost = EnvInt("JPBRT_BVH_TRAV", 100) * 0.01f;
+    // Split search by set size (B200 sweep, gpurun_out/bvh_quality*.log): <= 1,024 primitives: 16 bins (an exact sweep
+    // changes nothing on the bunny scene, helps Cornell by 4 % and costs the glossy scene 15 %); 1,025 .. sweep_hi: exact
+    // sweep SAH (bunny scene: box tests per ray 34.3 -> 28.1, k_extend -6 %, for 70 ms of build); above: bins_big bins.
+    int bins_big = EnvInt("JPBRT_BVH_BINS_BIG", 256);
+    int sweep_hi = EnvInt("JPBRT_BVH_SWEEP_HI", 65536);  // (scenes of more than 2^18 primitives: bins only -- the sweep doubles a 5 M build for < 2 %)
+    int sweep_max = EnvInt("JPBRT_BVH_SWEEP", 0);  // experiments: also sweep sets of at most this many primitives
     const std::vector<Box>& pb;
     std::vector<float> cx, cy, cz;
     std::vector<int> idx;
@@ -209,6 +215,7 @@ struct Builder {
             idx[i] = (int)i;
         }
         nodes.resize(std::max<size_t>(2 * n, 2));
+        if (n > (size_t)1 << 18) sweep_hi = 0;
     }
     float C(int axis, int i) const { return axis == 0 ? cx[i] : (axis == 1 ? cy[i] : cz[i]); }
     int Alloc() { return next.fetch_add(1); }
@@ -258,11 +265,46 @@ struct Builder {
         }
     }
 
+    // Exact SAH for small sets: every split position of the centroid-sorted order on every axis.
+    float SweepSplitCost(int first, int last, const Box& box, int* out_axis, int* out_mid) {
+        const int count = last - first;
+        float best = std::numeric_limits<float>::infinity();
+        int best_axis = -1, best_k = -1;
+        const float parent_area = std::max(box.HalfArea(), 1e-30f);
+        std::vector<int> order(idx.begin() + first, idx.begin() + last), best_order;
+        std::vector<float> right_area(count);
+        for (int a = 0; a < 3; ++a) {
+            std::sort(order.begin(), order.end(), [&](int l, int r) { return C(a, l) < C(a, r) || (C(a, l) == C(a, r) && l < r); });
+            Box acc;
+            for (int k = count - 1; k > 0; --k) { acc.Add(pb[order[k]]); right_area[k] = acc.HalfArea(); }
+            Box accl;
+            for (int k = 1; k < count; ++k) {  // left = order[0..k), right = order[k..count)
+                accl.Add(pb[order[k - 1]]);
+                float cost = trav_cost + (accl.HalfArea() * k + right_area[k] * (count - k)) / parent_area;
+                if (cost < best) { best = cost; best_axis = a; best_k = k; if (out_axis) best_order = order; }
+            }
+            if (out_axis && best_axis == a) best_order = order;
+        }
+        if (out_axis) {
+            if (best_axis >= 0) {
+                std::copy(best_order.begin(), best_order.end(), idx.begin() + first);
+                *out_axis = best_axis;
+                *out_mid = first + best_k;
+            } else {
+                *out_axis = -1;
+                *out_mid = -1;
+            }
+        }
+        return best;
+    }
+
     // Binned SAH over the three axes.  Returns the best cost (in primitive-test units, traversal
     // step = 1); if axis/mid are given, partitions idx[first,last) and reports the split.
     float BestSplitCost(int first, int last, const Box& box, const Box& cbox, int* out_axis, int* out_mid) {
-        constexpr int NB = 16;
+        constexpr int kMaxBins = 256;
+        const int NB = (last - first) > 1024 ? std::min(kMaxBins, std::max(2, bins_big)) : 16;
         int count = last - first;
+        if (count <= sweep_max || (count > 1024 && count <= sweep_hi)) return SweepSplitCost(first, last, box, out_axis, out_mid);
         float best = std::numeric_limits<float>::infinity();
         int best_axis = -1, best_bin = -1;
         float parent_area = std::max(box.HalfArea(), 1e-30f);
@@ -270,16 +312,16 @@ struct Builder {
             float lo = cbox.mn[a], ext = cbox.mx[a] - cbox.mn[a];
             if (!(ext > 0)) continue;
             float scale = (float)NB / ext;
-            Box bb[NB];
-            int bc[NB] = {0};
+            Box bb[kMaxBins];
+            int bc[kMaxBins] = {0};
             for (int i = first; i < last; ++i) {
                 int p = idx[i];
                 int b = std::min(NB - 1, std::max(0, (int)((C(a, p) - lo) * scale)));
                 bb[b].Add(pb[p]);
                 bc[b]++;
             }
-            float right_area[NB];
-            int right_cnt[NB];
+            float right_area[kMaxBins];
+            int right_cnt[kMaxBins];
             Box acc;
             int c = 0;
             for (int b = NB - 1; b > 0; --b) {
