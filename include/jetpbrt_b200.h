@@ -149,6 +149,11 @@ int jpbrt_unit_scene_occluded(jpbrt_ctx* ctx, int n, const float* pos3, const fl
 int jpbrt_unit_bsdf(const jpbrt_material* mat, int device, int n,
                     const float* nrm3, const float* wo3, const float* wi3, const float* u2, const float* ulobe,
                     float* f_eval3, float* pdf_eval, float* s_wi3, float* s_f3, float* s_pdf, int* s_flags, int* is_delta);
+/* The BSDF classes no FMaterial of the reference builds (jpbrt_bsdf_desc): FPhongSpecularReflection
+ * (bsdf.h:557-633), FMicrofacetReflection with Beckmann / Trowbridge-Reitz and any Fresnel (bsdf.cc:35-78,
+ * microfacet.cc:11-254), FMicrofacetTransmission (bsdf.cc:80-145): Evalf / Pdf / Sample in world space, frame = FFrame(nrm). */
+int jpbrt_unit_bsdf_ex(const jpbrt_bsdf_desc* desc, int device, int n, const float* nrm3, const float* wo3, const float* wi3,
+                       const float* u2, float* f_eval3, float* pdf_eval, float* s_wi3, float* s_f3, float* s_pdf, int* s_flags);
 /* FLight::Sample_Li (light.h): the `shade` stage's next-event sampling. */
 int jpbrt_unit_light_sample(jpbrt_ctx* ctx, int light, int n, const float* pos3, const float* nrm3, const float* u2,
                             float* lpos3, float* wi3, float* pdf, float* Li3);

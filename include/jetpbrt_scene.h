@@ -100,6 +100,34 @@ typedef struct jpbrt_scene_desc {
     const char*             name;           /* FScene name (scene.h:27), used for "<name>_<spp>" output files */
 } jpbrt_scene_desc;
 
+/* ---- BSDFs the reference implements but no FMaterial builds: reachable only through the
+ * unit entry point jpbrt_unit_bsdf_ex, constructed exactly as their C++ constructors are. ---- */
+typedef enum jpbrt_bsdf_kind {
+    JPBRT_BSDF_PHONG = 0,                    /* FPhongSpecularReflection(frame, Ks, exponent)            bsdf.h:557-633 */
+    JPBRT_BSDF_MICROFACET_REFLECTION = 1,    /* FMicrofacetReflection(frame, R, distribution, fresnel)   bsdf.cc:35-78 */
+    JPBRT_BSDF_MICROFACET_TRANSMISSION = 2   /* FMicrofacetTransmission(frame, T, distribution, etaA, etaB) bsdf.cc:80-145 */
+} jpbrt_bsdf_kind;
+typedef enum jpbrt_distribution {
+    JPBRT_DIST_BECKMANN = 0,                 /* BeckmannDistribution(alphax, alphay, samplevis)          microfacet.cc:11-254 */
+    JPBRT_DIST_TROWBRIDGE_REITZ = 1          /* TrowbridgeReitzDistribution(alphax, alphay, samplevis)   microfacet.cc:181-357 */
+} jpbrt_distribution;
+typedef enum jpbrt_fresnel {
+    JPBRT_FRESNEL_NOOP = 0,                  /* FresnelNoOp                       bsdf.h:666-669 */
+    JPBRT_FRESNEL_DIELECTRIC = 1,            /* FresnelDielectric(eta_a, eta_b)   bsdf.h:656-664 */
+    JPBRT_FRESNEL_CONDUCTOR = 2              /* FresnelConductor(c_eta_i, c_eta_t, c_k) bsdf.h:644-654 */
+} jpbrt_fresnel;
+typedef struct jpbrt_bsdf_desc {
+    int   kind;                 /* jpbrt_bsdf_kind */
+    int   distribution;         /* jpbrt_distribution (microfacet kinds) */
+    int   sample_visible_area;  /* the distributions' samplevis flag */
+    int   fresnel;              /* jpbrt_fresnel (microfacet reflection) */
+    float color[3];             /* Ks | R | T */
+    float exponent;             /* Phong */
+    float alphax, alphay;
+    float eta_a, eta_b;         /* dielectric Fresnel (etaI, etaT) | transmission (etaA, etaB) */
+    float c_eta_i[3], c_eta_t[3], c_k[3];
+} jpbrt_bsdf_desc;
+
 /* Constants the reference hard-codes on the hot path (kept as constants, not knobs, so that the
  * compiled reference, the oracle and the CUDA path can never disagree about them). */
 #define JPBRT_RAY_TMIN        0.001f  /* geometry.h:395,399 ; scene.h:38 */

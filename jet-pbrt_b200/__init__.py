@@ -35,6 +35,18 @@ class Material(C.Structure):
                 ("f0", C.c_float), ("f1", C.c_float)]
 
 
+class BsdfDesc(C.Structure):
+    """jpbrt_bsdf_desc (include/jetpbrt_scene.h): the BSDF classes of the reference that no material builds."""
+    _fields_ = [("kind", C.c_int), ("distribution", C.c_int), ("sample_visible_area", C.c_int), ("fresnel", C.c_int),
+                ("color", C.c_float * 3), ("exponent", C.c_float), ("alphax", C.c_float), ("alphay", C.c_float),
+                ("eta_a", C.c_float), ("eta_b", C.c_float), ("c_eta_i", C.c_float * 3), ("c_eta_t", C.c_float * 3), ("c_k", C.c_float * 3)]
+
+
+BSDF_PHONG, BSDF_MICROFACET_REFLECTION, BSDF_MICROFACET_TRANSMISSION = 0, 1, 2
+DIST_BECKMANN, DIST_TROWBRIDGE_REITZ = 0, 1
+FRESNEL_NOOP, FRESNEL_DIELECTRIC, FRESNEL_CONDUCTOR = 0, 1, 2
+
+
 class Light(C.Structure):
     _fields_ = [("type", C.c_int), ("shape", C.c_int), ("color", C.c_float * 3), ("pos", C.c_float * 3),
                 ("dir", C.c_float * 3)]
@@ -78,7 +90,7 @@ EXPORTS = [
     "jpbrt_last_error", "jpbrt_render", "jpbrt_render_integrator", "jpbrt_film_device_ptr", "jpbrt_film_num_floats", "jpbrt_stream",
     "jpbrt_synchronize", "jpbrt_finalize_film_device", "jpbrt_reupload_scene", "jpbrt_set_option",
     "jpbrt_get_stats", "jpbrt_unit_intersect_shape", "jpbrt_unit_scene_intersect", "jpbrt_unit_scene_occluded",
-    "jpbrt_unit_bsdf", "jpbrt_unit_light_sample", "jpbrt_unit_emitted", "jpbrt_unit_generate_rays",
+    "jpbrt_unit_bsdf", "jpbrt_unit_bsdf_ex", "jpbrt_unit_light_sample", "jpbrt_unit_emitted", "jpbrt_unit_generate_rays",
     "jpbrt_unit_rng_block", "jpbrt_scene_info", "jpbrt_scene_builtin", "jpbrt_scene_get_desc",
     "jpbrt_scene_free", "jpbrt_save_image", "jpbrt_version", "jpbrt_device_count", "jpbrt_debug_flatten", "jpbrt_debug_ctx_table",
 ]
@@ -123,6 +135,7 @@ def _load():
     lib.jpbrt_unit_scene_intersect.argtypes = [P, I, F, IP, F, F, F]
     lib.jpbrt_unit_scene_occluded.argtypes = [P, I, F, F, IP]
     lib.jpbrt_unit_bsdf.argtypes = [C.POINTER(Material), I, I, F, F, F, F, F, F, F, F, F, F, IP, IP]
+    lib.jpbrt_unit_bsdf_ex.argtypes = [C.POINTER(BsdfDesc), I, I, F, F, F, F, F, F, F, F, F, IP]
     lib.jpbrt_unit_light_sample.argtypes = [P, I, I, F, F, F, F, F, F, F]
     lib.jpbrt_unit_emitted.argtypes = [P, I, IP, F, F, F]
     lib.jpbrt_unit_generate_rays.argtypes = [P, I, F, F, F]
@@ -379,6 +392,16 @@ def unit_bsdf(mat: Material, nrm3, wo3, wi3, u2, ulobe, device: int = 0):
     _check(lib.jpbrt_unit_bsdf(C.byref(mat), device, n, _f(nrm3), _f(wo3), _f(wi3), _f(u2), _f(ulobe), _f(fe), _f(pe),
                                _f(swi), _f(sf), _f(sp), _i(fl), _i(dl)))
     return dict(f_eval=fe, pdf_eval=pe, s_wi=swi, s_f=sf, s_pdf=sp, s_flags=fl, is_delta=dl)
+
+
+def unit_bsdf_ex(desc: BsdfDesc, nrm3, wo3, wi3, u2, device: int = 0):
+    """jpbrt_unit_bsdf_ex: Evalf / Pdf / Sample of the BSDF classes no material builds."""
+    nrm3 = _f32(nrm3, (-1, 3)); wo3 = _f32(wo3, (-1, 3)); wi3 = _f32(wi3, (-1, 3)); u2 = _f32(u2, (-1, 2))
+    n = len(nrm3)
+    fe = np.empty((n, 3), np.float32); pe = np.empty(n, np.float32); swi = np.empty((n, 3), np.float32)
+    sf = np.empty((n, 3), np.float32); sp = np.empty(n, np.float32); fl = np.empty(n, np.int32)
+    _check(lib.jpbrt_unit_bsdf_ex(C.byref(desc), device, n, _f(nrm3), _f(wo3), _f(wi3), _f(u2), _f(fe), _f(pe), _f(swi), _f(sf), _f(sp), _i(fl)))
+    return dict(f_eval=fe, pdf_eval=pe, s_wi=swi, s_f=sf, s_pdf=sp, s_flags=fl)
 
 
 def unit_rng_block(pixel, sample, block, seed: int, device: int = 0):

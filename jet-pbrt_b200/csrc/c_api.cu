@@ -16,6 +16,7 @@
 
 #include "../../include/jetpbrt_b200.h"
 #include "scene_flatten.h"
+#include "bsdf_ex.cuh"
 #include "bvh_build.cuh"
 #include "wavefront.cuh"
 
@@ -837,6 +838,22 @@ __global__ void k_unit_bsdf(const Float4* mat, int n, const float* nrm3, const f
     }
 }
 
+__global__ void k_unit_bsdf_ex(jpbrt_bsdf_desc desc, int n, const float* nrm3, const float* wo3, const float* wi3, const float* u2,
+                               float* f_eval3, float* pdf_eval, float* s_wi3, float* s_f3, float* s_pdf, int* s_flags) {
+    const BsdfEx b = make_bsdf_ex(desc);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Frame fr = make_frame(ld3(nrm3, i));
+        const f3 wo = to_local(fr, ld3(wo3, i)), wi = to_local(fr, ld3(wi3, i));
+        st3(f_eval3, i, bsdf_ex_eval_local(b, wo, wi));
+        pdf_eval[i] = bsdf_ex_pdf_local(b, wo, wi);
+        BsdfSample s = bsdf_ex_sample_local(b, fr, wo, u2[2 * i], u2[2 * i + 1]);
+        st3(s_wi3, i, to_world(fr, s.wi));
+        st3(s_f3, i, s.f);
+        s_pdf[i] = s.pdf;
+        s_flags[i] = s.flags;
+    }
+}
+
 __global__ void k_unit_light_sample(DevScene sc, int light, int n, const float* pos3, const float* nrm3, const float* u2,
                                     float* lpos3, float* wi3, float* pdf, float* Li3) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -999,6 +1016,29 @@ int jpbrt_unit_bsdf(const jpbrt_material* mat, int device, int n, const float* n
     if (rc != 0) return rc;
     a.Back(f_eval3, d_fe, (size_t)n * 3); a.Back(pdf_eval, d_pe, n); a.Back(s_wi3, d_swi, (size_t)n * 3);
     a.Back(s_f3, d_sf, (size_t)n * 3); a.Back(s_pdf, d_sp, n); a.Back(s_flags, d_fl, n); a.Back(is_delta, d_dl, n);
+    return a.err == cudaSuccess ? 0 : set_error(nullptr, JPBRT_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(a.err));
+}
+
+int jpbrt_unit_bsdf_ex(const jpbrt_bsdf_desc* desc, int device, int n, const float* nrm3, const float* wo3, const float* wi3,
+                       const float* u2, float* f_eval3, float* pdf_eval, float* s_wi3, float* s_f3, float* s_pdf, int* s_flags) {
+    if (!desc || n < 0 || !nrm3 || !wo3 || !wi3 || !u2) return set_error(nullptr, JPBRT_ERR_INVALID, "null argument");
+    if (desc->kind < JPBRT_BSDF_PHONG || desc->kind > JPBRT_BSDF_MICROFACET_TRANSMISSION || desc->distribution < 0 ||
+        desc->distribution > JPBRT_DIST_TROWBRIDGE_REITZ || desc->fresnel < 0 || desc->fresnel > JPBRT_FRESNEL_CONDUCTOR)
+        return set_error(nullptr, JPBRT_ERR_INVALID, "unknown BSDF kind / distribution / Fresnel");
+    int rc = select_device(nullptr, device);
+    if (rc != 0) return rc;
+    Arena a;
+    const float *d_n = a.In(nrm3, (size_t)n * 3), *d_wo = a.In(wo3, (size_t)n * 3), *d_wi = a.In(wi3, (size_t)n * 3);
+    const float* d_u = a.In(u2, (size_t)n * 2);
+    float *d_fe = a.Out<float>((size_t)n * 3), *d_pe = a.Out<float>(n), *d_swi = a.Out<float>((size_t)n * 3);
+    float *d_sf = a.Out<float>((size_t)n * 3), *d_sp = a.Out<float>(n);
+    int* d_fl = a.Out<int>(n);
+    if (a.err == cudaSuccess && n > 0)
+        k_unit_bsdf_ex<<<unit_grid(n), kBlock>>>(*desc, n, d_n, d_wo, d_wi, d_u, d_fe, d_pe, d_swi, d_sf, d_sp, d_fl);
+    rc = finish_unit(nullptr, a);
+    if (rc != 0) return rc;
+    a.Back(f_eval3, d_fe, (size_t)n * 3); a.Back(pdf_eval, d_pe, n); a.Back(s_wi3, d_swi, (size_t)n * 3);
+    a.Back(s_f3, d_sf, (size_t)n * 3); a.Back(s_pdf, d_sp, n); a.Back(s_flags, d_fl, n);
     return a.err == cudaSuccess ? 0 : set_error(nullptr, JPBRT_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(a.err));
 }
 

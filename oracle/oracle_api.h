@@ -51,6 +51,11 @@ int ORC(bsdf)(const jpbrt_material* mat, int n,
               float* f_eval3, float* pdf_eval,
               float* s_wi3, float* s_f3, float* s_pdf, int* s_flags, int* is_delta);
 
+/* The BSDF classes no material builds (jpbrt_bsdf_desc): constructed directly with FFrame(nrm) and the described
+ * distribution / Fresnel objects, then Evalf(wo,wi), Pdf(wo,wi), Sample(wo,u) as above. */
+int ORC(bsdf_ex)(const jpbrt_bsdf_desc* desc, int n, const float* nrm3, const float* wo3, const float* wi3, const float* u2,
+                 float* f_eval3, float* pdf_eval, float* s_wi3, float* s_f3, float* s_pdf, int* s_flags);
+
 /* light->Sample_Li(isect{position,normal}, u) for desc->lights[light]  (light.h). */
 int ORC(light_sample)(ORC(scene)* s, int light, int n, const float* pos3, const float* nrm3, const float* u2,
                       float* lpos3, float* wi3, float* pdf, float* Li3);

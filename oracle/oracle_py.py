@@ -57,6 +57,7 @@ class Oracle:
         g("scene_intersect").argtypes = [P, I, F, IP, F, F, F]
         g("scene_occluded").argtypes = [P, I, F, F, IP]
         g("bsdf").argtypes = [P, I, F, F, F, F, F, F, F, F, F, F, IP, IP]
+        g("bsdf_ex").argtypes = [P, I, F, F, F, F, F, F, F, F, F, IP]
         g("light_sample").argtypes = [P, I, I, F, F, F, F, F, F, F]
         g("emitted").argtypes = [P, I, IP, F, F, F]
         g("generate_rays").argtypes = [P, I, F, F, F]
@@ -100,6 +101,16 @@ class Oracle:
                               _f(sf), _f(sp), _i(fl), _i(dl))
         assert rc == 0
         return dict(f_eval=fe, pdf_eval=pe, s_wi=swi, s_f=sf, s_pdf=sp, s_flags=fl, is_delta=dl)
+
+    def bsdf_ex(self, desc, nrm3, wo3, wi3, u2):
+        """The BSDF classes no material builds (jpbrt_bsdf_desc): Evalf / Pdf / Sample in world space."""
+        nrm3 = _f32(nrm3, (-1, 3)); wo3 = _f32(wo3, (-1, 3)); wi3 = _f32(wi3, (-1, 3)); u2 = _f32(u2, (-1, 2))
+        n = len(nrm3)
+        fe = np.empty((n, 3), np.float32); pe = np.empty(n, np.float32); swi = np.empty((n, 3), np.float32)
+        sf = np.empty((n, 3), np.float32); sp = np.empty(n, np.float32); fl = np.empty(n, np.int32)
+        rc = self._fn("bsdf_ex")(C.addressof(desc), n, _f(nrm3), _f(wo3), _f(wi3), _f(u2), _f(fe), _f(pe), _f(swi), _f(sf), _f(sp), _i(fl))
+        assert rc == 0
+        return dict(f_eval=fe, pdf_eval=pe, s_wi=swi, s_f=sf, s_pdf=sp, s_flags=fl)
 
     def philox_block(self, pixel, sample, block, seed):
         o = np.empty(4, np.float32)

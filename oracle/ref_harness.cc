@@ -231,6 +231,43 @@ int jref_bsdf(const jpbrt_material* mat, int n, const float* nrm3, const float* 
     return 0;
 }
 
+int jref_bsdf_ex(const jpbrt_bsdf_desc* d, int n, const float* nrm3, const float* wo3, const float* wi3, const float* u2,
+                 float* f_eval3, float* pdf_eval, float* s_wi3, float* s_f3, float* s_pdf, int* s_flags) {
+    if (!d) return -1;
+    for (int i = 0; i < n; ++i) {
+        FFrame frame(V3(nrm3 + 3 * i));
+        std::unique_ptr<FBSDF> bsdf;
+        auto make_dist = [&]() -> MicrofacetDistribution* {  // owned (and deleted) by the BSDF, bsdf.cc:29-33,80-83
+            if (d->distribution == JPBRT_DIST_BECKMANN) return new BeckmannDistribution(d->alphax, d->alphay, d->sample_visible_area != 0);
+            return new TrowbridgeReitzDistribution(d->alphax, d->alphay, d->sample_visible_area != 0);
+        };
+        switch (d->kind) {
+        case JPBRT_BSDF_PHONG: bsdf = std::make_unique<FPhongSpecularReflection>(frame, C3(d->color), d->exponent); break;
+        case JPBRT_BSDF_MICROFACET_REFLECTION: {
+            Fresnel* fr = nullptr;
+            if (d->fresnel == JPBRT_FRESNEL_DIELECTRIC) fr = new FresnelDielectric(d->eta_a, d->eta_b);
+            else if (d->fresnel == JPBRT_FRESNEL_CONDUCTOR) fr = new FresnelConductor(C3(d->c_eta_i), C3(d->c_eta_t), C3(d->c_k));
+            else fr = new FresnelNoOp();
+            bsdf = std::make_unique<FMicrofacetReflection>(frame, C3(d->color), make_dist(), fr);
+            break;
+        }
+        case JPBRT_BSDF_MICROFACET_TRANSMISSION:
+            bsdf = std::make_unique<FMicrofacetTransmission>(frame, C3(d->color), make_dist(), d->eta_a, d->eta_b);
+            break;
+        default: return -1;
+        }
+        FVector3 wo = V3(wo3 + 3 * i), wi = V3(wi3 + 3 * i);
+        putcol(f_eval3 + 3 * i, bsdf->Evalf(wo, wi));
+        pdf_eval[i] = bsdf->Pdf(wo, wi);
+        FBSDFSample smp = bsdf->Sample(wo, FFloat2(u2[2 * i], u2[2 * i + 1]));
+        put3(s_wi3 + 3 * i, smp.wi);
+        putcol(s_f3 + 3 * i, smp.f);
+        s_pdf[i] = smp.pdf;
+        s_flags[i] = smp.ebsdf;
+    }
+    return 0;
+}
+
 int jref_light_sample(jref_scene* s, int light, int n, const float* pos3, const float* nrm3, const float* u2,
                       float* lpos3, float* wi3, float* pdf, float* Li3) {
     if (light < 0 || light >= (int)s->lights.size()) return -1;

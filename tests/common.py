@@ -123,3 +123,29 @@ def specular_scene(pkg, res=64, max_depth=5):
               L(pkg.LIGHT_POINT, -1, (20, 20, 20), (5, 6, 4), z3)]
     prims = [Pm(0, 0, 1), Pm(1, 0, -1), Pm(2, 1, -1), Pm(3, 2, -1), Pm(4, 1, -1), Pm(5, 3, -1), Pm(6, -1, -1), Pm(7, 4, -1)]
     return pkg.HostScene.from_arrays(cam, shapes, mats, lights, prims, max_depth=max_depth, name="specular")
+
+
+def bsdf_ex_cases(pkg):
+    """The BSDF classes no material of the reference builds (jpbrt_bsdf_desc)."""
+    def D(**k):
+        d = pkg.BsdfDesc()
+        for a, v in k.items():
+            setattr(d, a, (pkg.C.c_float * 3)(*v) if isinstance(v, (tuple, list)) else v)
+        return d
+    P, MR, MT = pkg.BSDF_PHONG, pkg.BSDF_MICROFACET_REFLECTION, pkg.BSDF_MICROFACET_TRANSMISSION
+    BK, TR = pkg.DIST_BECKMANN, pkg.DIST_TROWBRIDGE_REITZ
+    return {
+        "phong": D(kind=P, color=(.8, .7, .6), exponent=20.0),
+        "phong_soft": D(kind=P, color=(.5, .5, .5), exponent=3.0),
+        "refl_beckmann_visible_dielectric": D(kind=MR, distribution=BK, sample_visible_area=1, fresnel=pkg.FRESNEL_DIELECTRIC, color=(.9, .9, .9),
+                                              alphax=.2, alphay=.2, eta_a=1.0, eta_b=1.5),
+        "refl_beckmann_visible_aniso_conductor": D(kind=MR, distribution=BK, sample_visible_area=1, fresnel=pkg.FRESNEL_CONDUCTOR, color=(1, 1, 1),
+                                                   alphax=.3, alphay=.1, c_eta_i=(1, 1, 1), c_eta_t=(.2, .92, 1.1), c_k=(3.9, 2.45, 2.14)),
+        "refl_beckmann_full": D(kind=MR, distribution=BK, sample_visible_area=0, fresnel=pkg.FRESNEL_NOOP, color=(1, 1, 1), alphax=.25, alphay=.25),
+        "refl_beckmann_full_aniso": D(kind=MR, distribution=BK, sample_visible_area=0, fresnel=pkg.FRESNEL_NOOP, color=(1, 1, 1), alphax=.4, alphay=.15),
+        "refl_tr_full": D(kind=MR, distribution=TR, sample_visible_area=0, fresnel=pkg.FRESNEL_DIELECTRIC, color=(1, 1, 1), alphax=.3, alphay=.3,
+                          eta_a=1.0, eta_b=1.5),
+        "refl_tr_full_aniso": D(kind=MR, distribution=TR, sample_visible_area=0, fresnel=pkg.FRESNEL_NOOP, color=(1, 1, 1), alphax=.3, alphay=.12),
+        "trans_tr": D(kind=MT, distribution=TR, sample_visible_area=1, color=(.95, .95, .95), alphax=.2, alphay=.2, eta_a=1.0, eta_b=1.5),
+        "trans_beckmann_aniso": D(kind=MT, distribution=BK, sample_visible_area=1, color=(.9, .95, .9), alphax=.15, alphay=.3, eta_a=1.0, eta_b=1.33),
+    }
