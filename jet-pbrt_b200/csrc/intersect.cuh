@@ -19,15 +19,37 @@ enum { SHAPE_TRI = 0, SHAPE_RECT = 1, SHAPE_SPHERE = 2, SHAPE_DISK = 3 };
 
 __device__ __forceinline__ float4 ldg4(const Float4* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// 256-bit read-only load (sm_100: LDG.E.256): two float4 of a 32-byte-aligned record in ONE load instruction.
+// A 64-byte BVH node is then 2 loads instead of 4, a triangle slot 2 instead of 3.
+#ifndef JPB_LDG256
+#define JPB_LDG256 1
+#endif
+// JPB_LDG256: 0 off, 1 nodes and slots, 2 nodes only, 3 slots only (A/B builds)
+template <bool WIDE>
+__device__ __forceinline__ void ldg8(const Float4* p, float4& a, float4& b) {
+    if (WIDE) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+    } else {
+        a = ldg4(p);
+        b = ldg4(p + 1);
+    }
+}
+constexpr bool kWideNodeLoads = JPB_LDG256 == 1 || JPB_LDG256 == 2;
+constexpr bool kWideSlotLoads = JPB_LDG256 == 1 || JPB_LDG256 == 3;
+
 // One primitive slot against one ray.  Returns true and shrinks tmax on an accepted hit.
 // `nrm_lookup` is the slot's (normal, tag) record, fetched only after the edge tests pass.
 __device__ __forceinline__ bool intersect_slot(const Float4* __restrict__ slot, const Float4* __restrict__ nrm_rec,
                                                const f3& o, const f3& d, float tmin, float& tmax) {
-    const float4 q0 = ldg4(slot);
+    float4 q0, q1, q2, q3;
+    ldg8<kWideSlotLoads>(slot, q0, q1);
     const int type = __float_as_int(q0.w) & ((1 << kTypeBits) - 1);
     const f3 p0 = mk3(q0);
     if (type == SHAPE_TRI) {  // shape.h:291-327
-        const f3 p1 = mk3(ldg4(slot + 1)), p2 = mk3(ldg4(slot + 2));
+        ldg8<kWideSlotLoads>(slot + 2, q2, q3);
+        const f3 p1 = mk3(q1), p2 = mk3(q2);
         const f3 oa = p0 - o, ob = p1 - o, oc = p2 - o;
         const f3 v0 = cross(oc, ob), v1 = cross(ob, oa), v2 = cross(oa, oc);
         const float v0d = dot(v0, d), v1d = dot(v1, d), v2d = dot(v2, d);
@@ -39,7 +61,8 @@ __device__ __forceinline__ bool intersect_slot(const Float4* __restrict__ slot, 
         return false;
     }
     if (type == SHAPE_RECT) {  // shape.h:399-435
-        const f3 p1 = mk3(ldg4(slot + 1)), p2 = mk3(ldg4(slot + 2)), p3 = mk3(ldg4(slot + 3));
+        ldg8<kWideSlotLoads>(slot + 2, q2, q3);
+        const f3 p1 = mk3(q1), p2 = mk3(q2), p3 = mk3(q3);
         const f3 oa = p0 - o, ob = p1 - o, oc = p2 - o, od = p3 - o;
         const f3 v0 = cross(oc, ob), v1 = cross(ob, oa), v2 = cross(oa, od), v3 = cross(od, oc);
         const float v0d = dot(v0, d), v1d = dot(v1, d), v2d = dot(v2, d), v3d = dot(v3, d);
@@ -51,7 +74,7 @@ __device__ __forceinline__ bool intersect_slot(const Float4* __restrict__ slot, 
         return false;
     }
     if (type == SHAPE_SPHERE) {  // shape.h:487-526
-        const float radius = ldg4(slot + 1).x;
+        const float radius = q1.x;
         const f3 oc = o - p0;
         const float a = length2(d);
         const float half_b = dot(oc, d);
@@ -73,7 +96,6 @@ __device__ __forceinline__ bool intersect_slot(const Float4* __restrict__ slot, 
         return false;
     }
     {  // SHAPE_DISK, shape.h:199-221; isEqual(x, 0) is |x| <= eps * max(1, |x|)  (pbrt.h:97-104)
-        const float4 q1 = ldg4(slot + 1);
         const f3 n = mk3(q1);
         const float radius = q1.w;
         const float dn = dot(d, n);
@@ -152,7 +174,9 @@ template <bool COUNT>
 __device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, int* stack, unsigned& n_box) {
     const float widen = 1.0000004f;  // 1 + 2*gamma(3): pbrt's conservative slab bound
     const Float4* np = sc.nodes + (size_t)t.cur * kNodeStride;
-    const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
+    float4 n0, n1, n2, n3;
+    ldg8<kWideNodeLoads>(np, n0, n1);
+    ldg8<kWideNodeLoads>(np + 2, n2, n3);
     if (COUNT) n_box += 2;
     // left box: min = (n0.x n0.y n0.z), max = (n0.w n1.x n1.y)
     float a0 = __fmaf_rn(n0.x, t.inv.x, t.oi.x), a1 = __fmaf_rn(n0.w, t.inv.x, t.oi.x);
