@@ -46,10 +46,10 @@ CONFIGS = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of k_extend per ray, from the committed `ncu --set full` captures
-# (profiles/r01_ncu_bunny_v2.md launch #0: 272.53 + 59.30 MB for 8,388,608 rays; profiles/r01_ncu_cornell_v2.md
-# launch #0: 268.52 + 52.58 MB for 8,388,608 rays).  The scene itself is cache-resident: DRAM only sees the
-# 32-byte ray read and the 8-byte hit write.
-NCU_EXTEND_DRAM_BYTES_PER_RAY = {"bunny": 39.55, "cornell": 38.28}
+# (profiles/r01_ncu_bunny_v7.md launch #0: 273.08 + 42.40 MB for 8,388,608 rays; profiles/r01_ncu_cornell_v2.md
+# launch #0: 268.52 + 52.58 MB for 8,388,608 rays; profiles/r01_ncu_large_v7.md launch #0: 760 + 44.5 MB for 4,194,304
+# rays).  Where the scene is cache-resident DRAM only sees the 32-byte ray read and the 8-byte hit write.
+NCU_EXTEND_DRAM_BYTES_PER_RAY = {"bunny": 37.61, "cornell": 38.28, "large": 191.8}
 
 
 def peaks():
