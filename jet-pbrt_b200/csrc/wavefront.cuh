@@ -277,9 +277,14 @@ __device__ __forceinline__ void append_next(const WfParams& p, int* next_count, 
     }
 }
 
-constexpr int kChunksPerFetch = 4;  // work is fetched up to 128 items at a time: fewer atomics on the hot queue cursors
+// (measured on B200, gpurun_out/ab_chunks.log: 2 -> 4 -> 8 chunks per fetch = shade stage 6.28 -> 5.73 -> 5.50 ms on Cornell,
+// 3.36 -> 3.02 -> 2.84 ms on the bunny scene: the same-address atomics of the cursors are a real cost there)
+#ifndef JPB_CHUNKS_PER_FETCH
+#define JPB_CHUNKS_PER_FETCH 8
+#endif
+constexpr int kChunksPerFetch = JPB_CHUNKS_PER_FETCH;  // work is fetched up to 256 items at a time: fewer atomics on the hot queue cursors
 
-// Items per fetch: 128 while the queue is long, shrinking to 32 when it is short relative to the number of
+// Items per fetch: 256 while the queue is long, shrinking to 32 when it is short relative to the number of
 // resident warps, so that late, small iterations still spread over the whole chip.
 __device__ __forceinline__ int chunks_for(int n) {
     const int total_warps = (gridDim.x * blockDim.x) >> 5;
