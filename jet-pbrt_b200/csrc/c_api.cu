@@ -96,7 +96,8 @@ struct jpbrt_ctx {
     long long opt_paths_in_flight = 0;
     bool opt_stage_timing = false;
     bool opt_count_traversal = false;
-    int opt_refill_min = 16;
+    int opt_refill_min = -1;  // < 0: automatic (16, or 20 for trees of at most 64 nodes)
+    int opt_min_inner = -1;  // < 0: automatic (8, or 4 for trees of at most 64 nodes); 0 or 1: wait for every lane
     long long opt_band_pixels = 0;  // pixels per band of a wavefront (0 = default 2^20); >= the frame: no banding
     int opt_integrator = JPBRT_INTEGRATOR_PATH;  // jpbrt_integrator: which FIntegrator::Li the passes evaluate
     bool has_mirror = false;                     // Whitted traces a mirror vertex twice: the ray tree can grow
@@ -269,7 +270,11 @@ WfParams make_params(jpbrt_ctx* c) {
     p.npix = c->hs.width * c->hs.height;
     p.blocks_per_bounce = rng_blocks_per_bounce(c->dsc.n_lights);
     p.shadow_capacity = (int)std::min<size_t>(c->sh_o.count, 0x7fffffff);
-    p.refill_min = c->opt_refill_min;
+    // B200 sweep (gpurun_out/sweep_mininner.log): trees of thousands of nodes want min_inner 8 / refill 16 (bunny scene +14 %,
+    // 5 M triangles +22 % over waiting for every lane); the 16- and 33-node trees of Cornell / glossy want 4 / 20 (+1 %).
+    const bool tiny_tree = c->dsc.n_nodes <= 64;
+    p.refill_min = c->opt_refill_min > 0 ? c->opt_refill_min : (tiny_tree ? 20 : 16);
+    p.min_inner = c->opt_min_inner >= 0 ? c->opt_min_inner : (tiny_tree ? 4 : 8);
     return p;
 }
 
@@ -475,7 +480,8 @@ int jpbrt_set_option(jpbrt_ctx* c, const char* name, long long value) {
         c->opt_integrator = (int)value;
         return 0;
     }
-    if (!strcmp(name, "refill_min")) { c->opt_refill_min = (int)std::max(1ll, std::min(32ll, value)); return 0; }
+    if (!strcmp(name, "min_inner")) { c->opt_min_inner = (int)std::max(-1ll, std::min(32ll, value)); return 0; }
+    if (!strcmp(name, "refill_min")) { c->opt_refill_min = (int)std::max(-1ll, std::min(32ll, value)); return 0; }
     return set_error(c, JPBRT_ERR_INVALID, "unknown option '%s'", name);
 }
 
@@ -573,7 +579,7 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
     const bool count = c->opt_count_traversal;
     // Graph replay needs a launch sequence that never changes: no per-launch events, no counting variant.
     const bool use_graph = c->opt_use_graph && !c->opt_stage_timing && !count;
-    const int graph_key = (c->opt_integrator * 16 + c->opt_trav_blocks) * 64 + c->opt_refill_min;
+    const int graph_key = ((c->opt_integrator * 16 + c->opt_trav_blocks) * 64 + (c->opt_refill_min + 1)) * 64 + (c->opt_min_inner + 1);
     if (use_graph && (c->wave_graph == nullptr || c->wave_graph_key != graph_key)) {
         if (c->wave_graph) { cudaGraphExecDestroy(c->wave_graph); c->wave_graph = nullptr; }
         cudaGraph_t graph = nullptr;
@@ -794,7 +800,7 @@ struct UnitRayIO {
 __global__ void __launch_bounds__(kBlock) k_unit_scene_intersect(DevScene sc, int n, int* work, const float* rays8, int* prim, float* t, float* pos3, float* nrm3) {
     unsigned a = 0, b = 0;
     UnitRayIO io{rays8, prim, t, pos3, nrm3, &sc};
-    traverse_queue<false, false>(sc, n, work, io, 8, a, b);
+    traverse_queue<false, false>(sc, n, work, io, 8, 8, a, b);
 }
 
 struct UnitOccIO {
@@ -817,7 +823,7 @@ struct UnitOccIO {
 __global__ void __launch_bounds__(kBlock) k_unit_scene_occluded(DevScene sc, int n, int* work, const float* pos3, const float* target3, int* occ) {
     unsigned a = 0, b = 0;
     UnitOccIO io{pos3, target3, occ};
-    traverse_queue<true, false>(sc, n, work, io, 8, a, b);
+    traverse_queue<true, false>(sc, n, work, io, 8, 8, a, b);
 }
 
 __global__ void k_unit_bsdf(const Float4* mat, int n, const float* nrm3, const float* wo3, const float* wi3, const float* u2,

@@ -79,6 +79,7 @@ struct WfParams {
     int blocks_per_bounce;
     int shadow_capacity;
     int refill_min;  // ray replacement threshold of the traversal kernels (idle lanes per warp)
+    int min_inner;   // the node phase of a warp ends when fewer lanes than this are still at inner nodes (intersect.cuh)
 };
 
 constexpr int kBlock = 256;
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_extend(const __grid_constant__
     unsigned nb = 0, np = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.stats + ST_EXT_RAYS, (unsigned long long)n);
     ExtendIO io{p.ray_o[buf], p.ray_d[buf], p.hit};
-    traverse_queue<false, COUNT>(p.sc, n, work, io, p.refill_min, nb, np);
+    traverse_queue<false, COUNT>(p.sc, n, work, io, p.refill_min, p.min_inner, nb, np);
     if (COUNT) {
         warp_stat_add(p.stats + ST_BOX, nb);
         warp_stat_add(p.stats + ST_PRIM, np);
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_connect(const __grid_constant_
     int* work = p.counters + CNT_W_CONNECT * p.counter_stride + it;
     unsigned nb = 0, np = 0, traced = 0;
     ConnectIO io{&p, &traced};
-    traverse_queue<true, COUNT>(p.sc, n, work, io, p.refill_min, nb, np);
+    traverse_queue<true, COUNT>(p.sc, n, work, io, p.refill_min, p.min_inner, nb, np);
     warp_stat_add(p.stats + ST_SHADOW_RAYS, traced);
     if (COUNT) {
         warp_stat_add(p.stats + ST_SH_BOX, nb);
