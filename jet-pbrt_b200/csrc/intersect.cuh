@@ -137,12 +137,6 @@ __device__ __forceinline__ Frame hit_frame(const DevScene& sc, int slot, const f
     return f;
 }
 
-#ifndef JPB_LEAF_BREAK
-#define JPB_LEAF_BREAK 0
-#endif
-#ifndef JPB_LEAF_LOOP
-#define JPB_LEAF_LOOP 0
-#endif
 constexpr int kTraversalStack = 64;
 constexpr int kTravDone = 0x7fffffff;  // `cur` value of a lane whose stack is empty (or that found an any-hit)
 
@@ -280,18 +274,9 @@ __device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* w
             const unsigned m_inner = __ballot_sync(full, inner);
             if (m_inner == 0) break;
             if (__popc(m_inner) < min_inner && __any_sync(full, idx >= 0 && trav_at_leaf(t))) break;
-#if JPB_LEAF_BREAK > 0
-            if (__popc(__ballot_sync(full, idx >= 0 && trav_at_leaf(t))) >= JPB_LEAF_BREAK) break;
-#endif
             if (inner) trav_node_step<COUNT>(sc, t, stack, n_box);
         }
-#if JPB_LEAF_LOOP > 0
-        do {
-            if (idx >= 0 && trav_at_leaf(t)) trav_leaf_step<ANY_HIT, COUNT>(sc, t, stack, n_prim);
-        } while (__popc(__ballot_sync(full, idx >= 0 && trav_at_leaf(t))) >= JPB_LEAF_LOOP);
-#else
         if (idx >= 0 && trav_at_leaf(t)) trav_leaf_step<ANY_HIT, COUNT>(sc, t, stack, n_prim);
-#endif
         if (idx >= 0 && trav_done(t)) {
             io.store(idx, t.hit, t.tmax);
             idx = -1;
