@@ -120,3 +120,22 @@ def test_cli_binary_exists_and_prints_usage(pkg):
     assert exe.exists(), "run make -C jet-pbrt_b200"
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=30)
     assert r.returncode == 0 and "pbrt.exe  sceneid   spp" in r.stdout
+
+
+def test_new_entry_points_validate_before_touching_a_device(pkg):
+    """jpbrt_upload_scene_ex / jpbrt_unit_bsdf_ex / jpbrt_render_integrator reject bad arguments on any machine."""
+    sc = pkg.HostScene.builtin("cornell", 16, 16)
+    ctx = C.c_void_p()
+    assert pkg.lib.jpbrt_upload_scene_ex(sc.desc, 0, 0x80, C.byref(ctx)) == -1 and not ctx.value  # unknown flag
+    assert b"flags" in pkg.lib.jpbrt_last_error(None)
+    assert pkg.lib.jpbrt_upload_scene_ex(sc.desc, 0, 0, None) == -1
+    d = pkg.BsdfDesc()
+    d.kind = 7
+    z = np.zeros(3, np.float32)
+    f = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))  # noqa: E731
+    o3, o1, oi = np.zeros(3, np.float32), np.zeros(1, np.float32), np.zeros(1, np.int32)
+    rc = pkg.lib.jpbrt_unit_bsdf_ex(C.byref(d), 0, 1, f(z), f(z), f(z), f(z), f(o3), f(o1), f(o3), f(o3), f(o1), oi.ctypes.data_as(C.POINTER(C.c_int)))
+    assert rc == -1 and b"BSDF" in pkg.lib.jpbrt_last_error(None)
+    out = np.zeros((16, 16, 3), np.float32)
+    assert pkg.lib.jpbrt_render_integrator(sc.desc, 0, 0, 1, 0, f(out), None) == -1  # spp must be positive
+    assert set(pkg.INTEGRATORS) == {"path", "path_recursive", "whitted", "debug"}
