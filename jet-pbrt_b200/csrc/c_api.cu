@@ -270,7 +270,7 @@ WfParams make_params(jpbrt_ctx* c) {
     p.npix = c->hs.width * c->hs.height;
     p.blocks_per_bounce = rng_blocks_per_bounce(c->dsc.n_lights);
     p.shadow_capacity = (int)std::min<size_t>(c->sh_o.count, 0x7fffffff);
-    // B200 sweep (gpurun_out/sweep_mininner.log): trees of thousands of nodes want min_inner 8 / refill 16 (bunny scene +14 %,
+    // B200 sweep (profiles/r01_sweep_min_inner.txt): trees of thousands of nodes want min_inner 8 / refill 16 (bunny scene +14 %,
     // 5 M triangles +22 % over waiting for every lane); the 16- and 33-node trees of Cornell / glossy want 4 / 20 (+1 %).
     const bool tiny_tree = c->dsc.n_nodes <= 64;
     p.refill_min = c->opt_refill_min > 0 ? c->opt_refill_min : (tiny_tree ? 20 : 16);

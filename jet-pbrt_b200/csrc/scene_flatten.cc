@@ -192,7 +192,7 @@ static int EnvInt(const char* name, int def) {
 struct Builder {
     int max_leaf = std::max(1, std::min(15, EnvInt("JPBRT_BVH_LEAF", kMaxLeafPrims)));
     float trav_cost = EnvInt("JPBRT_BVH_TRAV", 100) * 0.01f;
-    // Split search by set size (B200 sweep, gpurun_out/bvh_quality*.log): <= 1,024 primitives: 16 bins (an exact sweep
+    // Split search by set size (B200 sweep, profiles/r01_bvh_quality_sweep.txt): <= 1,024 primitives: 16 bins (an exact sweep
     // changes nothing on the bunny scene, helps Cornell by 4 % and costs the glossy scene 15 %); 1,025 .. sweep_hi: exact
     // sweep SAH (bunny scene: box tests per ray 34.3 -> 28.1, k_extend -6 %, for 70 ms of build); above: bins_big bins.
     int bins_big = EnvInt("JPBRT_BVH_BINS_BIG", 256);

@@ -278,7 +278,7 @@ __device__ __forceinline__ void append_next(const WfParams& p, int* next_count, 
     }
 }
 
-// (measured on B200, gpurun_out/ab_chunks.log: 2 -> 4 -> 8 chunks per fetch = shade stage 6.28 -> 5.73 -> 5.50 ms on Cornell,
+// (measured on B200, profiles/ab/r01_ab_chunks.log: 2 -> 4 -> 8 chunks per fetch = shade stage 6.28 -> 5.73 -> 5.50 ms on Cornell,
 // 3.36 -> 3.02 -> 2.84 ms on the bunny scene: the same-address atomics of the cursors are a real cost there)
 #ifndef JPB_CHUNKS_PER_FETCH
 #define JPB_CHUNKS_PER_FETCH 8
@@ -299,7 +299,7 @@ __device__ __forceinline__ int warp_fetch_n(int* counter, int amount) {
 }
 
 #ifndef JPB_LOGIC_MIN_BLOCKS
-#define JPB_LOGIC_MIN_BLOCKS 4  // 64 registers; 5-6 blocks (48 / 40 registers) measured equal (gpurun_out/ab_shade.log)
+#define JPB_LOGIC_MIN_BLOCKS 4  // 64 registers; 5-6 blocks (48 / 40 registers) measured equal (profiles/ab/r01_ab_shade.log)
 #endif
 template <bool WHITTED>
 __global__ void __launch_bounds__(kBlock, JPB_LOGIC_MIN_BLOCKS) k_logic(const __grid_constant__ WfParams p, int it) {
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(kBlock, JPB_LOGIC_MIN_BLOCKS) k_logic(const __
 }
 
 // Resident blocks per SM: 2 (111 registers) -> 3 (80) measured 5-9 % faster, 3 -> 4 (64 registers, the same ~150 bytes
-// of spills, which come from the out-of-line calls) another 3 % (gpurun_out/ab_shade.log)
+// of spills, which come from the out-of-line calls) another 3 % (profiles/ab/r01_ab_shade.log)
 #ifndef JPB_SHADE_MIN_BLOCKS
 #define JPB_SHADE_MIN_BLOCKS 4
 #endif
