@@ -144,3 +144,18 @@ def test_sweep_sah_builds_a_cheaper_tree_than_16_bins(pkg, monkeypatch):
     c_sweep, c_bins = sah_cost(nodes, refs), sah_cost(nodes16, refs16)
     assert c_sweep < c_bins, (c_sweep, c_bins)
     print("SAH cost: sweep", c_sweep, "16 bins", c_bins)
+
+
+def test_reinsertion_lowers_the_cost_and_keeps_the_tree_valid(pkg, monkeypatch):
+    """Insertion-based optimisation (default for 1,025..131,072 primitives): a valid partition with a lower SAH cost."""
+    sc = pkg.HostScene.builtin("bunny", 32, 32, 0.5)
+    monkeypatch.setenv("JPBRT_BVH_REINSERT", "0")
+    n0, r0, s0, m0 = decode(pkg, sc)
+    monkeypatch.setenv("JPBRT_BVH_REINSERT", "2")
+    n2, r2, s2, m2 = decode(pkg, sc)
+    depth = check_tree(n2, r2, s2, m2, pkg.debug_flatten(sc, "prim_slot"), sc.d.n_primitives)
+    assert np.array_equal(s0, s2) and np.array_equal(m0, m2)  # leaves and slot order untouched
+    assert sah_cost(n2, r2) < 0.95 * sah_cost(n0, r0) and depth < 56
+    monkeypatch.delenv("JPBRT_BVH_REINSERT")
+    nd, rd, _, _ = decode(pkg, sc)
+    assert np.array_equal(nd, n2)  # the default for a scene of this size
