@@ -158,4 +158,4 @@ def test_reinsertion_lowers_the_cost_and_keeps_the_tree_valid(pkg, monkeypatch):
     assert sah_cost(n2, r2) < 0.95 * sah_cost(n0, r0) and depth < 56
     monkeypatch.delenv("JPBRT_BVH_REINSERT")
     nd, rd, _, _ = decode(pkg, sc)
-    assert np.array_equal(nd, n2)  # the default for a scene of this size
+    assert np.array_equal(nd.view(np.int32), n2.view(np.int32))  # the default for a scene of this size (bit compare: child refs are ints)
