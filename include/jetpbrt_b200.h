@@ -108,9 +108,20 @@ int    jpbrt_finalize_film_device(jpbrt_ctx* ctx, void* out_device, int spp_tota
  * caller pays for a changed scene); returns bytes copied through *bytes. */
 int    jpbrt_reupload_scene(jpbrt_ctx* ctx, size_t* bytes);
 
-/* Options: "integrator" (jpbrt_integrator), "paths_in_flight" per wavefront (0 = default), "stage_timing"
- * (per-stage CUDA events) on/off, "count_traversal" (node/primitive test counters) on/off, "use_graph",
- * "trav_blocks", "refill_min" (traversal kernel tunables). */
+/* Options (value 0 / 1 unless noted):
+ *   "integrator"       jpbrt_integrator
+ *   "paths_in_flight"  capacity of the path pool = paths per wavefront (0 = automatic: the pass, at most 2^26)
+ *   "band_pixels"      pixels per band of a wavefront (0 = 2^20); >= the frame disables banding
+ *   "stage_timing"     per-stage CUDA events (jpbrt_stats.ms_*); disables CUDA-graph replay
+ *   "count_traversal"  node / primitive test counters (jpbrt_stats.box_tests ...); uses the counting kernel variants
+ *   "use_graph"        replay a wavefront as one CUDA graph (default 1)
+ *   "sort_rays"        reorder the rays of bounces >= 1 by (origin cell, direction octant) before they are traced:
+ *                      0 off, else cell bits per axis 1..6, +16 to include the octant
+ *   traversal tunables "trav_blocks" (5 or 6 resident blocks per SM; other values are clamped), "refill_min" (idle lanes
+ *                      that trigger a refill, 1..32, -1 automatic), "min_inner" (lanes at inner nodes below which a warp's
+ *                      node phase ends, 0..32, -1 automatic)
+ * The film is accumulated with float atomics: a render is reproducible up to float summation order (<= 1e-6 relative),
+ * not bit for bit; the PATHS depend only on (seed, pixel, sample index). */
 int jpbrt_set_option(jpbrt_ctx* ctx, const char* name, long long value);
 
 typedef struct jpbrt_stats {
@@ -128,8 +139,13 @@ typedef struct jpbrt_stats {
     uint64_t n_nodes, n_prim_slots, scene_bytes;
     double   bvh_build_seconds;
     uint64_t paths_in_flight;  /* capacity of the path pool (paths per wavefront), 0 before the first pass */
-    uint64_t bvh_builder;      /* 0 host binned SAH, 1 GPU linear BVH (JPBRT_UPLOAD_GPU_BVH) */
+    uint64_t bvh_builder;      /* 0 host binned SAH, 1 GPU linear BVH (JPBRT_UPLOAD_GPU_BVH), 2 host object-median rebuild (tree too deep) */
     double   bvh_device_seconds; /* GPU builder: box upload + sort/tree/refit kernels + tree download (part of bvh_build_seconds) */
+    /* What the pipeline had to drop -- each is also part of invalid_contributions; all are 0 in a healthy render: */
+    uint64_t dropped_rays;     /* rays that found the next wavefront queue full (Whitted ray trees), or were still queued after the last bounce */
+    uint64_t stack_overflows;  /* far BVH children lost to a full traversal stack (tree deeper than 63 levels of pending subtrees) */
+    uint64_t nee_dropped;      /* light samples that found no shadow-ray slot (pool smaller than vertices x lights) */
+    uint64_t bvh_depth;        /* levels of the BVH (root = 1); trees deeper than 62 are rebuilt with median splits at upload */
 } jpbrt_stats;
 int jpbrt_get_stats(jpbrt_ctx* ctx, jpbrt_stats* out);
 
@@ -164,6 +180,9 @@ int jpbrt_unit_generate_rays(jpbrt_ctx* ctx, int n, const float* posfilm2, float
 /* The counter-based sampler's block (pixel, sample, block) -> 4 floats in [0,1). */
 int jpbrt_unit_rng_block(int device, int n, const uint32_t* pixel, const uint32_t* sample, const uint32_t* block,
                          uint64_t seed, float* out4);
+/* The raw generator under it: Philox4x32-10 on n (counter[4], key[2]) pairs -> 4 words each (for the published
+ * known-answer vectors). */
+int jpbrt_unit_philox_raw(int device, int n, const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4);
 /* Scene facts computed at upload: out[0..2] world min, [3..5] world max, [6] environment radius. */
 int jpbrt_scene_info(jpbrt_ctx* ctx, float* out7);
 

@@ -78,7 +78,8 @@ class Stats(C.Structure):
                 ("ms_connect", C.c_double), ("ms_finalize", C.c_double),
                 ("n_nodes", C.c_uint64), ("n_prim_slots", C.c_uint64), ("scene_bytes", C.c_uint64),
                 ("bvh_build_seconds", C.c_double), ("paths_in_flight", C.c_uint64), ("bvh_builder", C.c_uint64),
-                ("bvh_device_seconds", C.c_double)]
+                ("bvh_device_seconds", C.c_double), ("dropped_rays", C.c_uint64), ("stack_overflows", C.c_uint64),
+                ("nee_dropped", C.c_uint64), ("bvh_depth", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -91,7 +92,7 @@ EXPORTS = [
     "jpbrt_synchronize", "jpbrt_finalize_film_device", "jpbrt_reupload_scene", "jpbrt_set_option",
     "jpbrt_get_stats", "jpbrt_unit_intersect_shape", "jpbrt_unit_scene_intersect", "jpbrt_unit_scene_occluded",
     "jpbrt_unit_bsdf", "jpbrt_unit_bsdf_ex", "jpbrt_unit_light_sample", "jpbrt_unit_emitted", "jpbrt_unit_generate_rays",
-    "jpbrt_unit_rng_block", "jpbrt_scene_info", "jpbrt_scene_builtin", "jpbrt_scene_get_desc",
+    "jpbrt_unit_rng_block", "jpbrt_unit_philox_raw", "jpbrt_scene_info", "jpbrt_scene_builtin", "jpbrt_scene_get_desc",
     "jpbrt_scene_free", "jpbrt_save_image", "jpbrt_version", "jpbrt_device_count", "jpbrt_debug_flatten", "jpbrt_debug_ctx_table",
 ]
 
@@ -141,6 +142,7 @@ def _load():
     lib.jpbrt_unit_generate_rays.argtypes = [P, I, F, F, F]
     lib.jpbrt_unit_rng_block.argtypes = [I, I, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                          C.c_uint64, F]
+    lib.jpbrt_unit_philox_raw.argtypes = [I, I, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.jpbrt_scene_info.argtypes = [P, F]
     lib.jpbrt_scene_builtin.argtypes = [C.c_char_p, I, I, C.c_float]
     lib.jpbrt_scene_builtin.restype = P
@@ -412,6 +414,15 @@ def unit_rng_block(pixel, sample, block, seed: int, device: int = 0):
     u32p = C.POINTER(C.c_uint32)
     _check(lib.jpbrt_unit_rng_block(device, n, pixel.ctypes.data_as(u32p), sample.ctypes.data_as(u32p),
                                     block.ctypes.data_as(u32p), seed, _f(out)))
+    return out
+
+
+def unit_philox_raw(ctr4, key2, device: int = 0):
+    """Philox4x32-10 on (counter[4], key[2]) rows -> uint32[n, 4] (known-answer tests)."""
+    ctr4 = np.ascontiguousarray(ctr4, np.uint32).reshape(-1, 4); key2 = np.ascontiguousarray(key2, np.uint32).reshape(-1, 2)
+    out = np.empty_like(ctr4)
+    u32p = C.POINTER(C.c_uint32)
+    _check(lib.jpbrt_unit_philox_raw(device, len(ctr4), ctr4.ctypes.data_as(u32p), key2.ctypes.data_as(u32p), out.ctypes.data_as(u32p)))
     return out
 
 

@@ -20,6 +20,8 @@
 #include "bvh_build.cuh"
 #include "wavefront.cuh"
 
+#include <cub/device/device_scan.cuh>
+
 using namespace jpbrt;
 
 namespace {
@@ -79,6 +81,11 @@ struct jpbrt_ctx {
     DevBuf<float4> ray_o[2], ray_d[2], ray_b[2], sh_o, sh_d, sh_c;
     DevBuf<float2> hit;
     DevBuf<int> kind_queue;
+    // ray reordering (option "sort_rays"): bin counters, their prefix sums, (bin, rank) per ray, the permutation, cub's scratch
+    DevBuf<unsigned> sort_bins, sort_start;
+    DevBuf<uint2> sort_kr;
+    DevBuf<int> perm;
+    DevBuf<unsigned char> scan_tmp;
     DevBuf<int> counters;
     int counter_stride = 0;
     int n_iters = 0;
@@ -101,6 +108,7 @@ struct jpbrt_ctx {
     long long opt_band_pixels = 0;  // pixels per band of a wavefront (0 = default 2^20); >= the frame: no banding
     int opt_integrator = JPBRT_INTEGRATOR_PATH;  // jpbrt_integrator: which FIntegrator::Li the passes evaluate
     bool has_mirror = false;                     // Whitted traces a mirror vertex twice: the ray tree can grow
+    int opt_sort_rays = 0;    // 0 off; else cell bits per axis (1..6) + 16 x (direction octant in the key)
     int opt_trav_blocks = 6;  // resident blocks per SM the traversal kernels are compiled for: 6 (40 registers, default) or 5 (48)
     unsigned kinds_present = 0;  // bit k set: some material of the scene can build BSDF kind k
     // launch geometry
@@ -201,6 +209,12 @@ int upload_arrays(jpbrt_ctx* c, size_t* bytes) {
 // 48 B shadow slot per non-black light.
 size_t bytes_per_path(int n_nee_lights) { return 2 * 48 + 8 + 4 * NUM_KINDS + (size_t)48 * std::max(1, n_nee_lights); }
 
+void free_pool(jpbrt_ctx* c) {
+    for (int b = 0; b < 2; ++b) { c->ray_o[b].Free(); c->ray_d[b].Free(); c->ray_b[b].Free(); }
+    c->hit.Free(); c->kind_queue.Free(); c->sh_o.Free(); c->sh_d.Free(); c->sh_c.Free();
+    c->sort_kr.Free(); c->perm.Free();
+}
+
 // Size the path pool for a pass of `paths_needed` camera paths.  An explicit "paths_in_flight" option is honoured
 // exactly; otherwise the pool grows on demand up to the default limit and is never shrunk.
 int ensure_pool(jpbrt_ctx* c, long long paths_needed) {
@@ -238,17 +252,47 @@ int ensure_pool(jpbrt_ctx* c, long long paths_needed) {
     }
     if (cap == c->paths_in_flight) return 0;
     if (c->wave_graph) { cudaGraphExecDestroy(c->wave_graph); c->wave_graph = nullptr; }  // it holds the old buffers' addresses
-    for (int b = 0; b < 2; ++b) {
-        CU_CHECK(c, c->ray_o[b].Alloc(cap));
-        CU_CHECK(c, c->ray_d[b].Alloc(cap));
-        CU_CHECK(c, c->ray_b[b].Alloc(cap));
+    // The pool is reallocated as a whole: while that is under way the context owns NO pool (capacity 0), and a failed
+    // allocation releases everything, so that the next pass starts from scratch instead of trusting a stale capacity.
+    c->paths_in_flight = 0;
+    free_pool(c);
+    cudaError_t e = cudaSuccess;
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+        if ((e = c->ray_o[b].Alloc(cap)) == cudaSuccess && (e = c->ray_d[b].Alloc(cap)) == cudaSuccess) e = c->ray_b[b].Alloc(cap);
     }
-    CU_CHECK(c, c->hit.Alloc(cap));
-    CU_CHECK(c, c->kind_queue.Alloc((size_t)cap * NUM_KINDS));
-    CU_CHECK(c, c->sh_o.Alloc(shadow_cap));
-    CU_CHECK(c, c->sh_d.Alloc(shadow_cap));
-    CU_CHECK(c, c->sh_c.Alloc(shadow_cap));
+    if (e == cudaSuccess) e = c->hit.Alloc(cap);
+    if (e == cudaSuccess) e = c->kind_queue.Alloc((size_t)cap * NUM_KINDS);
+    if (e == cudaSuccess) e = c->sh_o.Alloc(shadow_cap);
+    if (e == cudaSuccess) e = c->sh_d.Alloc(shadow_cap);
+    if (e == cudaSuccess) e = c->sh_c.Alloc(shadow_cap);
+    if (e != cudaSuccess) {
+        free_pool(c);
+        cudaGetLastError();
+        return set_error(c, JPBRT_ERR_CUDA, "allocating a pool of %lld paths failed: %s", cap, cudaGetErrorString(e));
+    }
     c->paths_in_flight = cap;
+    return 0;
+}
+
+// Buffers of the ray reordering ("sort_rays"): sized with the pool, allocated on first use.
+constexpr int kSortMaxKeyBits = 21;  // 6 cell bits per axis + 3 direction bits
+int ensure_sort_buffers(jpbrt_ctx* c) {
+    if (c->opt_sort_rays == 0) return 0;
+    const size_t cap = (size_t)c->paths_in_flight;
+    if (c->sort_kr.ptr && c->sort_kr.count == cap) return 0;
+    if (c->wave_graph) { cudaGraphExecDestroy(c->wave_graph); c->wave_graph = nullptr; }
+    const size_t nbins = (size_t)1 << kSortMaxKeyBits;
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (const unsigned*)nullptr, (unsigned*)nullptr, (int)nbins, c->stream);
+    cudaError_t e;
+    if ((e = c->sort_kr.Alloc(cap)) != cudaSuccess || (e = c->perm.Alloc(cap)) != cudaSuccess ||
+        (e = c->sort_bins.Alloc(nbins)) != cudaSuccess || (e = c->sort_start.Alloc(nbins)) != cudaSuccess ||
+        (e = c->scan_tmp.Alloc(tmp_bytes)) != cudaSuccess) {
+        c->sort_kr.Free(); c->perm.Free(); c->sort_bins.Free(); c->sort_start.Free(); c->scan_tmp.Free();
+        cudaGetLastError();
+        return set_error(c, JPBRT_ERR_CUDA, "allocating the reordering buffers failed: %s", cudaGetErrorString(e));
+    }
+    CU_CHECK(c, cudaMemsetAsync(c->sort_bins.ptr, 0, nbins * sizeof(unsigned), c->stream));
     return 0;
 }
 
@@ -275,6 +319,20 @@ WfParams make_params(jpbrt_ctx* c) {
     const bool tiny_tree = c->dsc.n_nodes <= 64;
     p.refill_min = c->opt_refill_min > 0 ? c->opt_refill_min : (tiny_tree ? 20 : 16);
     p.min_inner = c->opt_min_inner >= 0 ? c->opt_min_inner : (tiny_tree ? 4 : 8);
+    const bool sorting = c->opt_sort_rays != 0 && c->sort_kr.ptr && (c->opt_integrator == JPBRT_INTEGRATOR_PATH || c->opt_integrator == JPBRT_INTEGRATOR_PATH_RECURSIVE);
+    if (sorting) {
+        p.sort_bins = c->sort_bins.ptr;
+        p.sort_start = c->sort_start.ptr;
+        p.sort_kr = c->sort_kr.ptr;
+        p.perm = c->perm.ptr;
+        p.sort_cell_bits = c->opt_sort_rays & 15;
+        p.sort_dir = (c->opt_sort_rays >> 4) & 1;
+        for (int a = 0; a < 3; ++a) {
+            const float ext = c->hs.world_max[a] - c->hs.world_min[a];
+            p.sort_min[a] = c->hs.world_min[a];
+            p.sort_scale[a] = ext > 0.f ? (float)(1 << p.sort_cell_bits) / ext : 0.f;
+        }
+    }
     return p;
 }
 
@@ -472,7 +530,12 @@ int jpbrt_set_option(jpbrt_ctx* c, const char* name, long long value) {
     if (!strcmp(name, "paths_in_flight")) { c->opt_paths_in_flight = value; return 0; }
     if (!strcmp(name, "stage_timing")) { c->opt_stage_timing = value != 0; return 0; }
     if (!strcmp(name, "count_traversal")) { c->opt_count_traversal = value != 0; return 0; }
-    if (!strcmp(name, "trav_blocks")) { c->opt_trav_blocks = (int)value; return 0; }
+    if (!strcmp(name, "trav_blocks")) { c->opt_trav_blocks = value >= 6 ? 6 : 5; return 0; }
+    if (!strcmp(name, "sort_rays")) {
+        if (value != 0 && ((value & 15) < 1 || (value & 15) > 6 || (value >> 5) != 0)) return set_error(c, JPBRT_ERR_INVALID, "sort_rays: cell bits 1..6 (+16 for the direction octant), got %lld", value);
+        c->opt_sort_rays = (int)value;
+        return 0;
+    }
     if (!strcmp(name, "use_graph")) { c->opt_use_graph = value != 0; return 0; }
     if (!strcmp(name, "band_pixels")) { c->opt_band_pixels = std::max(0ll, value); return 0; }
     if (!strcmp(name, "integrator")) {
@@ -490,6 +553,8 @@ int jpbrt_set_option(jpbrt_ctx* c, const char* name, long long value) {
 static int queue_wavefront(jpbrt_ctx* c, bool count) {
     WfParams p = make_params(c);
     CU_CHECK(c, cudaMemsetAsync(c->counters.ptr, 0, c->counters.count * sizeof(int), c->stream));
+    if (p.sort_bins)  // (a null-material pass-through at the last bounce can leave counts behind)
+        CU_CHECK(c, cudaMemsetAsync(c->sort_bins.ptr, 0, sizeof(unsigned) << (3 * p.sort_cell_bits + 3 * p.sort_dir), c->stream));
     {
         StageTimer t(c, 0);
         k_generate<<<c->grid_generate, kBlock, 0, c->stream>>>(p);
@@ -497,10 +562,22 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
     }
     const bool whitted = c->opt_integrator == JPBRT_INTEGRATOR_WHITTED;
     const bool debug = c->opt_integrator == JPBRT_INTEGRATOR_DEBUG;
+    const bool sorting = p.sort_bins != nullptr;
     for (int it = 0; it < (debug ? 1 : c->n_iters); ++it) {
+        if (sorting && it > 0) {
+            // reordering: bins were counted while bounce it-1 appended its rays; prefix-sum them, place every ray, clear the bins
+            StageTimer t(c, 1);
+            size_t tmp_bytes = c->scan_tmp.count;
+            CU_CHECK(c, cub::DeviceScan::ExclusiveSum(c->scan_tmp.ptr, tmp_bytes, c->sort_bins.ptr, c->sort_start.ptr,
+                                                      1 << (3 * p.sort_cell_bits + 3 * p.sort_dir), c->stream));
+            k_permute<<<c->grid_generate, kBlock, 0, c->stream>>>(p, it);
+            CU_CHECK(c, cudaMemsetAsync(c->sort_bins.ptr, 0, sizeof(unsigned) << (3 * p.sort_cell_bits + 3 * p.sort_dir), c->stream));
+            c->kernel_launches += 2;
+        }
         {
             StageTimer t(c, 1);
             if (count) k_extend<true, 5><<<c->grid_extend_c, kBlock, 0, c->stream>>>(p, it);
+            else if (sorting && it > 0) k_extend<false, 6, true><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
             else if (c->opt_trav_blocks >= 6) k_extend<false, 6><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
             else k_extend<false, 5><<<c->grid_extend, kBlock, 0, c->stream>>>(p, it);
             c->kernel_launches++;
@@ -562,6 +639,7 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
     // Whitted traces a mirror vertex twice (bsdf.h:282): leave room for the ray tree, x2 per mirror bounce, at most x8
     const int tree_growth = (c->opt_integrator == JPBRT_INTEGRATOR_WHITTED && c->has_mirror) ? 1 << std::min(3, std::max(0, c->hs.max_depth - 1)) : 1;
     int rc = ensure_pool(c, (long long)c->hs.width * c->hs.height * std::max(1, sample_count) * tree_growth);
+    if (rc == 0) rc = ensure_sort_buffers(c);
     if (rc != 0) return rc;
     const long long npix = (long long)c->hs.width * c->hs.height;
     // Bands: a wavefront covers a contiguous range of the Morton pixel order (a compact region of the frame) times as
@@ -579,7 +657,7 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
     const bool count = c->opt_count_traversal;
     // Graph replay needs a launch sequence that never changes: no per-launch events, no counting variant.
     const bool use_graph = c->opt_use_graph && !c->opt_stage_timing && !count;
-    const int graph_key = ((c->opt_integrator * 16 + c->opt_trav_blocks) * 64 + (c->opt_refill_min + 1)) * 64 + (c->opt_min_inner + 1);
+    const int graph_key = (((c->opt_integrator * 16 + c->opt_trav_blocks) * 64 + (c->opt_refill_min + 1)) * 64 + (c->opt_min_inner + 1)) * 64 + c->opt_sort_rays;
     if (use_graph && (c->wave_graph == nullptr || c->wave_graph_key != graph_key)) {
         if (c->wave_graph) { cudaGraphExecDestroy(c->wave_graph); c->wave_graph = nullptr; }
         cudaGraph_t graph = nullptr;
@@ -681,7 +759,11 @@ int jpbrt_get_stats(jpbrt_ctx* c, jpbrt_stats* out) {
     out->prim_tests = h[ST_PRIM];
     out->shadow_box_tests = h[ST_SH_BOX];
     out->shadow_prim_tests = h[ST_SH_PRIM];
-    out->invalid_contributions = h[ST_INVALID] + h[ST_DROPPED];
+    out->invalid_contributions = h[ST_INVALID] + h[ST_DROPPED] + h[ST_STACK_DROPPED] + h[ST_NEE_DROPPED];
+    out->dropped_rays = h[ST_DROPPED];
+    out->stack_overflows = h[ST_STACK_DROPPED];
+    out->nee_dropped = h[ST_NEE_DROPPED];
+    out->bvh_depth = (uint64_t)c->hs.bvh_depth;
     out->kernel_launches = c->kernel_launches;
     out->ms_generate = c->ms_stage[0];
     out->ms_extend = c->ms_stage[1];
@@ -904,6 +986,13 @@ __global__ void k_unit_rng_block(int n, const uint32_t* pixel, const uint32_t* s
     }
 }
 
+__global__ void k_unit_philox_raw(int n, const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 r = philox4x32_10(ctr4[4 * i], ctr4[4 * i + 1], ctr4[4 * i + 2], ctr4[4 * i + 3], key2[2 * i], key2[2 * i + 1]);
+        out4[4 * i] = r.x; out4[4 * i + 1] = r.y; out4[4 * i + 2] = r.z; out4[4 * i + 3] = r.w;
+    }
+}
+
 // host <-> device marshalling for the unit entry points
 struct Arena {
     std::vector<void*> ptrs;
@@ -1099,6 +1188,20 @@ int jpbrt_unit_rng_block(int device, int n, const uint32_t* pixel, const uint32_
     float* d_o = a.Out<float>((size_t)n * 4);
     RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32)};
     if (a.err == cudaSuccess && n > 0) k_unit_rng_block<<<unit_grid(n), kBlock>>>(n, d_p, d_s, d_b, key, d_o);
+    rc = finish_unit(nullptr, a);
+    if (rc != 0) return rc;
+    a.Back(out4, d_o, (size_t)n * 4);
+    return a.err == cudaSuccess ? 0 : set_error(nullptr, JPBRT_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(a.err));
+}
+
+int jpbrt_unit_philox_raw(int device, int n, const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4) {
+    if (n < 0 || !ctr4 || !key2 || !out4) return set_error(nullptr, JPBRT_ERR_INVALID, "null argument");
+    int rc = select_device(nullptr, device);
+    if (rc != 0) return rc;
+    Arena a;
+    const uint32_t *d_c = a.In(ctr4, (size_t)n * 4), *d_k = a.In(key2, (size_t)n * 2);
+    uint32_t* d_o = a.Out<uint32_t>((size_t)n * 4);
+    if (a.err == cudaSuccess && n > 0) k_unit_philox_raw<<<unit_grid(n), kBlock>>>(n, d_c, d_k, d_o);
     rc = finish_unit(nullptr, a);
     if (rc != 0) return rc;
     a.Back(out4, d_o, (size_t)n * 4);

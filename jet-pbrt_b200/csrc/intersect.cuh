@@ -137,8 +137,21 @@ __device__ __forceinline__ Frame hit_frame(const DevScene& sc, int slot, const f
     return f;
 }
 
-constexpr int kTraversalStack = 64;
+constexpr int kTraversalStack = 64;     // deepest node stack a ray can use (entries, the sentinel included)
 constexpr int kTravDone = 0x7fffffff;  // `cur` value of a lane whose stack is empty (or that found an any-hit)
+constexpr int kTravBlock = 256;        // threads per block of every kernel that traverses (wavefront.cuh: kBlock)
+
+// The first JPB_SMEM_STACK entries of every lane's node stack live in SHARED memory, laid out [entry][thread]: lane l of a
+// warp always hits bank l whatever its stack depth, so a push or pop is ONE conflict-free wavefront even when the 32 lanes
+// sit at 32 different depths (the local-memory stack of round 1 cost one L1 wavefront per distinct depth, was a quarter of
+// the kernel's load/store instructions and ran its push / pop branches at 5.5 / 1.9 of 32 lanes: profiles/
+// r01_lane_profile_bunny_v8.txt).  Deeper entries spill to a local array, which only trees deeper than the shared part
+// ever touch.  0 = the whole stack in local memory (A/B builds).
+#ifndef JPB_SMEM_STACK
+#define JPB_SMEM_STACK 8
+#endif
+constexpr int kSmemStack = JPB_SMEM_STACK;
+static_assert(kSmemStack >= 0 && kSmemStack < kTraversalStack, "JPB_SMEM_STACK out of range");
 
 // Per-lane traversal state.  The BVH walk is a state machine so that a warp can (a) run the inner-node
 // step and the leaf step in separate, converged phases (while-while traversal) and (b) hand a finished
@@ -147,7 +160,34 @@ struct Trav {
     f3 o, d, inv, oi;
     float tmin, tmax;
     int cur, sp, hit;
-};  // the node stack is a separate local array so that these scalars stay in registers
+};  // the node stack is separate (shared + local arrays) so that these scalars stay in registers
+
+// This lane's node stack.  Entry 0 is a sentinel (kTravDone) that is never overwritten: popping an empty stack yields
+// "done" without a compare.
+struct TravStack {
+    int* sm;  // &shared[0][threadIdx.x]; entry e is sm[e * kTravBlock]
+    int* lm;  // local spill, entries kSmemStack .. kTraversalStack-1
+    unsigned long long* dropped;  // stats counter of pushes that found the stack full (never in the five configs)
+    __device__ __forceinline__ void init() const {
+        if (kSmemStack > 0) sm[0] = kTravDone; else lm[0] = kTravDone;
+    }
+    __device__ __forceinline__ void push(int& sp, int v) const {
+        if (kSmemStack > 0 && sp < kSmemStack) {
+            sm[sp * kTravBlock] = v;
+            ++sp;
+        } else if (sp < kTraversalStack) {
+            lm[sp - kSmemStack] = v;
+            ++sp;
+        } else if (dropped) {
+            atomicAdd(dropped, 1ull);  // the far child is lost: counted, reported as invalid_contributions / stack_overflows
+        }
+    }
+    __device__ __forceinline__ int pop(int& sp) const {
+        --sp;
+        if (kSmemStack > 0 && sp < kSmemStack) return sm[sp * kTravBlock];
+        return lm[sp - kSmemStack];
+    }
+};
 
 __device__ __forceinline__ void trav_init(Trav& t, const f3& o, const f3& d, float tmin, float tmax) {
     t.o = o;
@@ -160,18 +200,18 @@ __device__ __forceinline__ void trav_init(Trav& t, const f3& o, const f3& d, flo
     t.tmin = tmin;
     t.tmax = tmax;
     t.cur = 0;  // root (always an inner node, scene_flatten.cc)
-    t.sp = 0;
+    t.sp = 1;   // above the sentinel
     t.hit = -1;
 }
 
 __device__ __forceinline__ bool trav_at_inner(const Trav& t) { return (unsigned)t.cur < (unsigned)kTravDone; }
 __device__ __forceinline__ bool trav_at_leaf(const Trav& t) { return t.cur < 0; }
 __device__ __forceinline__ bool trav_done(const Trav& t) { return t.cur == kTravDone; }
-__device__ __forceinline__ void trav_pop(Trav& t, const int* stack) { t.cur = t.sp ? stack[--t.sp] : kTravDone; }
 
-// One inner node: fetch 64 bytes, test both child boxes, descend into the nearer hit child.
+// One inner node: fetch 64 bytes, test both child boxes, descend into the nearer hit child.  Written without
+// divergent branches: the push (both children hit) and the pop (none hit) are short predicated sequences.
 template <bool COUNT>
-__device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, int* stack, unsigned& n_box) {
+__device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, const TravStack& stk, unsigned& n_box) {
     const float widen = 1.0000004f;  // 1 + 2*gamma(3): pbrt's conservative slab bound
     const Float4* np = sc.nodes + (size_t)t.cur * kNodeStride;
     float4 n0, n1, n2, n3;
@@ -193,22 +233,17 @@ __device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, int*
     const bool hl = ltn <= ltf * widen;
     const bool hr = rtn <= rtf * widen;
     const int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
-    if (hl && hr) {
-        const bool left_first = ltn <= rtn;
-        t.cur = left_first ? cl : cr;
-        if (t.sp < kTraversalStack) stack[t.sp++] = left_first ? cr : cl;  // (prefetching the far child measured 3-6 % slower)
-    } else if (hl) {
-        t.cur = cl;
-    } else if (hr) {
-        t.cur = cr;
-    } else {
-        trav_pop(t, stack);
-    }
+    const bool both = hl && hr;
+    const bool right_first = both ? !(ltn <= rtn) : hr;  // the nearer child first; left on ties (the reference's order, bvh.h:99-100)
+    const int near = right_first ? cr : cl;
+    const int far = right_first ? cl : cr;
+    if (both) stk.push(t.sp, far);  // (prefetching the far child measured 3-6 % slower)
+    t.cur = (hl || hr) ? near : stk.pop(t.sp);
 }
 
 // One leaf: test its (<= 4) primitives, then pop.
 template <bool ANY_HIT, bool COUNT>
-__device__ __forceinline__ void trav_leaf_step(const DevScene& sc, Trav& t, const int* stack, unsigned& n_prim) {
+__device__ __forceinline__ void trav_leaf_step(const DevScene& sc, Trav& t, const TravStack& stk, unsigned& n_prim) {
     const int bits = ~t.cur;
     const int first = bits >> kLeafCountBits;
     const int cnt = bits & ((1 << kLeafCountBits) - 1);
@@ -220,7 +255,7 @@ __device__ __forceinline__ void trav_leaf_step(const DevScene& sc, Trav& t, cons
             if (ANY_HIT) { t.cur = kTravDone; return; }
         }
     }
-    trav_pop(t, stack);
+    t.cur = stk.pop(t.sp);
 }
 
 // Warp-cooperative traversal of a whole ray queue.
@@ -231,14 +266,23 @@ __device__ __forceinline__ void trav_leaf_step(const DevScene& sc, Trav& t, cons
 //            slowest ray of the warp is done;
 //   nodes  : lanes at an inner node step until (almost, see min_inner) every active lane sits on a leaf or is done;
 //   leaves : lanes at a leaf test its primitives and pop; finished lanes store their result.
+// Invariant: a lane without a ray (idx < 0) has t.cur == kTravDone, so "at an inner node" / "at a leaf" need no idx test.
+// Must be called by every thread of a kTravBlock-thread block (static shared memory).
+#ifndef JPB_NODE_UNROLL
+#define JPB_NODE_UNROLL 1  // node steps per warp vote of the node phase (A/B builds)
+#endif
 template <bool ANY_HIT, bool COUNT, typename IO>
 __device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* work, const IO& io, int refill_min, int min_inner,
-                                               unsigned& n_box, unsigned& n_prim) {
+                                               unsigned& n_box, unsigned& n_prim, unsigned long long* dropped = nullptr) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    __shared__ int s_stack[(kSmemStack > 0 ? kSmemStack : 1) * kTravBlock];
+    int l_stack[kTraversalStack - kSmemStack];
+    const TravStack stk{s_stack + threadIdx.x, l_stack, dropped};
+    stk.init();
     Trav t;
-    int stack[kTraversalStack];
     t.cur = kTravDone;
+    t.sp = 1;
     int idx = -1;
     bool exhausted = false;
     for (;;) {
@@ -270,13 +314,14 @@ __device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* w
         // `min_inner` lanes are still walking inner nodes and some lane has a leaf to test; the stragglers resume after the
         // (short) leaf phase.  Measured on B200: min_inner 8 = +12 % on the bunny scene, +20 % on the 5 M-triangle scene.
         for (;;) {
-            const bool inner = idx >= 0 && trav_at_inner(t);
-            const unsigned m_inner = __ballot_sync(full, inner);
+            const unsigned m_inner = __ballot_sync(full, trav_at_inner(t));
             if (m_inner == 0) break;
-            if (__popc(m_inner) < min_inner && __any_sync(full, idx >= 0 && trav_at_leaf(t))) break;
-            if (inner) trav_node_step<COUNT>(sc, t, stack, n_box);
+            if (__popc(m_inner) < min_inner && __any_sync(full, trav_at_leaf(t))) break;
+#pragma unroll
+            for (int u = 0; u < JPB_NODE_UNROLL; ++u)
+                if (trav_at_inner(t)) trav_node_step<COUNT>(sc, t, stk, n_box);
         }
-        if (idx >= 0 && trav_at_leaf(t)) trav_leaf_step<ANY_HIT, COUNT>(sc, t, stack, n_prim);
+        if (trav_at_leaf(t)) trav_leaf_step<ANY_HIT, COUNT>(sc, t, stk, n_prim);
         if (idx >= 0 && trav_done(t)) {
             io.store(idx, t.hit, t.tmax);
             idx = -1;

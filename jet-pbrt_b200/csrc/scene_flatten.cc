@@ -204,6 +204,9 @@ struct Builder {
     std::vector<TmpNode> nodes;
     std::atomic<int> next{0};
     std::atomic<int> threads_left;
+    bool force_median = false;  // object-median splits only: the fallback for trees SAH leaves deeper than the traversal stack
+    bool chain_test = EnvInt("JPBRT_TEST_CHAIN_BVH", 0) != 0;  // TEST HOOK: one primitive peeled off per level (a tree as deep
+                                                               // as the scene is large), to exercise the kernels' stack-overflow counter
 
     explicit Builder(const std::vector<Box>& prim_boxes, int nthreads) : pb(prim_boxes), threads_left(nthreads) {
         size_t n = pb.size();
@@ -230,17 +233,25 @@ struct Builder {
         }
         N.box = box;
         int count = last - first;
+        if (chain_test && !force_median) {
+            if (count == 1) { N.first = first; N.count = 1; return; }
+            int l = Alloc(), r = Alloc();
+            N.left = l; N.right = r; N.count = 0;
+            Build(l, first, last - 1);
+            Build(r, last - 1, last);
+            return;
+        }
         if (count <= max_leaf) {
             // a small set becomes a leaf unless SAH says that splitting it is clearly cheaper
             bool leaf = true;
-            if (count > 1) {
+            if (count > 1 && !force_median) {
                 float best = BestSplitCost(first, last, box, cbox, nullptr, nullptr);
                 leaf = !(best < (float)count);
             }
             if (leaf) { N.first = first; N.count = count; return; }
         }
         int axis = -1, mid = -1;
-        BestSplitCost(first, last, box, cbox, &axis, &mid);
+        if (!force_median) BestSplitCost(first, last, box, cbox, &axis, &mid);
         if (mid <= first || mid >= last) {  // degenerate (coincident centroids): median by index
             int a = 0;
             float ext = -1;
@@ -281,9 +292,9 @@ struct Builder {
             for (int k = 1; k < count; ++k) {  // left = order[0..k), right = order[k..count)
                 accl.Add(pb[order[k - 1]]);
                 float cost = trav_cost + (accl.HalfArea() * k + right_area[k] * (count - k)) / parent_area;
-                if (cost < best) { best = cost; best_axis = a; best_k = k; if (out_axis) best_order = order; }
+                if (cost < best) { best = cost; best_axis = a; best_k = k; }
             }
-            if (out_axis && best_axis == a) best_order = order;
+            if (out_axis && best_axis == a) best_order = order;  // one copy per winning axis (not per improvement)
         }
         if (out_axis) {
             if (best_axis >= 0) {
@@ -697,6 +708,36 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, Bv
             bld.nodes = backup;
             root = root_backup;
         }
+    }
+
+    // The traversal kernels keep at most kMaxBvhDepth pending subtrees per ray (csrc/intersect.cuh: kTraversalStack minus the
+    // sentinel); a deeper tree would silently lose far children.  SAH on skewed input (long chains of nested or
+    // near-coincident primitives) can exceed that: such a tree is rebuilt with object-median splits, whose depth is
+    // ceil(log2(N / leaf)) <= 31.  The kernels additionally COUNT any push that finds the stack full (stack_overflows).
+    auto tree_depth = [&](int r) {
+        int deepest = 0;
+        std::vector<std::pair<int, int>> st{{r, 1}};
+        while (!st.empty()) {
+            auto [n, dep] = st.back();
+            st.pop_back();
+            deepest = std::max(deepest, dep);
+            if (bld.nodes[n].count == 0) { st.push_back({bld.nodes[n].left, dep + 1}); st.push_back({bld.nodes[n].right, dep + 1}); }
+        }
+        return deepest;
+    };
+    hs.bvh_depth = tree_depth(root);
+    const int depth_limit = std::max(1, std::min(kMaxBvhDepth, EnvInt("JPBRT_BVH_MAX_DEPTH", kMaxBvhDepth)));  // (lowered by tests)
+    const bool allow_deep = EnvInt("JPBRT_TEST_ALLOW_DEEP_BVH", 0) != 0;  // tests of the kernels' overflow counter only
+    if (hs.bvh_depth > depth_limit && !allow_deep) {
+        bld.nodes.assign(std::max<size_t>(2 * (size_t)N, 2), TmpNode());
+        for (int i = 0; i < N; ++i) bld.idx[i] = i;
+        bld.next = 0;
+        bld.force_median = true;
+        root = bld.Alloc();
+        bld.Build(root, 0, N);
+        hs.bvh_depth = tree_depth(root);
+        hs.bvh_builder = 2;
+        if (hs.bvh_depth > kMaxBvhDepth) return fail(JPBRT_ERR_UNSUPPORTED, "BVH deeper than the traversal stack even with median splits");
     }
 
     // flatten: inner nodes depth-first, leaves reference idx ranges (== slot ranges)

@@ -28,13 +28,18 @@ struct HostScene {
     int n_prims = 0;
     bool has_null_material = false;
     double bvh_build_seconds = 0;
-    int bvh_builder = 0;  // 0 host binned SAH, 1 GPU LBVH
+    int bvh_builder = 0;  // 0 host binned SAH, 1 GPU LBVH, 2 host object-median rebuild (the SAH/LBVH tree was too deep)
+    int bvh_depth = 0;    // levels of the tree (root = 1); at most kMaxBvhDepth
     double bvh_device_seconds = 0;  // GPU builder only: upload of the boxes + kernels + download of the tree
     size_t Bytes() const {
         return (nodes.size() + slots.size() + slot_nrm.size() + materials.size() + lights.size() + slot_frame.size()) * sizeof(Float4) +
                slot_ml.size() * sizeof(Int2) + (inf_lights.size() + prim_slot.size() + nee_lights.size()) * sizeof(int);  // pixel_order is film state, not scene
     }
 };
+
+// Deepest tree the traversal kernels can walk without losing a subtree: their node stack holds 64 entries, one of them
+// the sentinel (csrc/intersect.cuh), and a ray has at most one pending subtree per level below the root.
+constexpr int kMaxBvhDepth = 62;
 
 // BVH topology handed to the flattener by an external builder (the GPU LBVH builder, csrc/bvh_build.cuh): a binary
 // radix tree over the primitives in `order`.  Inner node i covers order[first..last]; a child reference >= 0 is an

@@ -42,7 +42,10 @@ namespace jpbrt {
 enum { CNT_RAYS = 0, CNT_UNUSED = 1, CNT_W_EXTEND = 2, CNT_W_SHADE = 3, CNT_W_CONNECT = 4,
        CNT_Q0 = 5 /* 4 kinds */, CNT_WQ0 = 9 /* 4 kinds */, CNT_KINDS = 13 };
 enum {
-    ST_SAMPLES = 0, ST_EXT_RAYS, ST_SHADOW_RAYS, ST_VERTICES, ST_BOX, ST_PRIM, ST_SH_BOX, ST_SH_PRIM, ST_INVALID, ST_DROPPED, ST_COUNT
+    ST_SAMPLES = 0, ST_EXT_RAYS, ST_SHADOW_RAYS, ST_VERTICES, ST_BOX, ST_PRIM, ST_SH_BOX, ST_SH_PRIM, ST_INVALID, ST_DROPPED,
+    ST_STACK_DROPPED,  // far children lost to a full traversal stack (intersect.cuh: kTraversalStack)
+    ST_NEE_DROPPED,    // light samples that found no shadow slot (pool smaller than vertices x lights)
+    ST_COUNT
 };
 
 // The only values that change from one wavefront to the next.  They live in device memory (written by
@@ -80,6 +83,15 @@ struct WfParams {
     int shadow_capacity;
     int refill_min;  // ray replacement threshold of the traversal kernels (idle lanes per warp)
     int min_inner;   // the node phase of a warp ends when fewer lanes than this are still at inner nodes (intersect.cuh)
+    // Ray reordering (option "sort_rays"): the rays a bounce emits are binned by (origin cell, direction octant) while they
+    // are appended, and k_extend of the next bounce walks them in bin order through `perm` (see k_permute).
+    unsigned* sort_bins;   // [1 << sort_key_bits] per-bin counters; null = reordering off
+    unsigned* sort_start;  // exclusive prefix sums of the counters
+    uint2* sort_kr;        // (bin, rank within the bin) of every queued ray
+    int* perm;             // sorted position -> queue index
+    int sort_cell_bits;    // origin grid: 2^bits cells per axis
+    int sort_dir;          // 1: the direction octant is the low 3 bits of the key
+    float sort_min[3], sort_scale[3];
 };
 
 constexpr int kBlock = 256;
@@ -161,31 +173,37 @@ __global__ void __launch_bounds__(kBlock) k_generate(const __grid_constant__ WfP
 // ---------------------------------------------------------------------------------------------
 // extend: closest hit for every ray of iteration `it`
 // ---------------------------------------------------------------------------------------------
+template <bool PERM>
 struct ExtendIO {
     const float4* ro;
     const float4* rd;
     float2* hit;
-    __device__ __forceinline__ bool load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
+    const int* perm;  // PERM: queue position -> ray index (rays are walked in bin order, results land at the ray's own index)
+    __device__ __forceinline__ bool load(int j, f3& o, f3& d, float& tmin, float& tmax) const {
+        const int i = PERM ? __ldg(&perm[j]) : j;
         o = mk3(ld_stream(&ro[i]));
         d = mk3(ld_stream(&rd[i]));
         tmin = JPBRT_RAY_TMIN;                 // FRay default min_t, geometry.h:395
         tmax = __int_as_float(0x7f800000);     // kInfinity
         return true;
     }
-    __device__ __forceinline__ void store(int i, int slot, float t) const { st_stream(&hit[i], make_float2(t, __int_as_float(slot))); }
+    __device__ __forceinline__ void store(int j, int slot, float t) const {
+        const int i = PERM ? __ldg(&perm[j]) : j;
+        st_stream(&hit[i], make_float2(t, __int_as_float(slot)));
+    }
 };
 
 // MINB = resident blocks per SM the register allocation must allow (5: 48 registers, 6: 40; measured on B200:
 // 6 is 1-3 % faster on all scenes, 8 = 32 registers spills and is 15-25 % slower).
-template <bool COUNT, int MINB>
+template <bool COUNT, int MINB, bool PERM = false>
 __global__ void __launch_bounds__(kBlock, MINB) k_extend(const __grid_constant__ WfParams p, int it) {
     const int n = min(p.counters[CNT_RAYS * p.counter_stride + it], p.queue_capacity);
     int* work = p.counters + CNT_W_EXTEND * p.counter_stride + it;
     const int buf = it & 1;
     unsigned nb = 0, np = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.stats + ST_EXT_RAYS, (unsigned long long)n);
-    ExtendIO io{p.ray_o[buf], p.ray_d[buf], p.hit};
-    traverse_queue<false, COUNT>(p.sc, n, work, io, p.refill_min, p.min_inner, nb, np);
+    ExtendIO<PERM> io{p.ray_o[buf], p.ray_d[buf], p.hit, p.perm};
+    traverse_queue<false, COUNT>(p.sc, n, work, io, p.refill_min, p.min_inner, nb, np, p.stats + ST_STACK_DROPPED);
     if (COUNT) {
         warp_stat_add(p.stats + ST_BOX, nb);
         warp_stat_add(p.stats + ST_PRIM, np);
@@ -229,7 +247,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_connect(const __grid_constant_
     int* work = p.counters + CNT_W_CONNECT * p.counter_stride + it;
     unsigned nb = 0, np = 0, traced = 0;
     ConnectIO io{&p, &traced};
-    traverse_queue<true, COUNT>(p.sc, n, work, io, p.refill_min, p.min_inner, nb, np);
+    traverse_queue<true, COUNT>(p.sc, n, work, io, p.refill_min, p.min_inner, nb, np, p.stats + ST_STACK_DROPPED);
     warp_stat_add(p.stats + ST_SHADOW_RAYS, traced);
     if (COUNT) {
         warp_stat_add(p.stats + ST_SH_BOX, nb);
@@ -254,6 +272,26 @@ __device__ __forceinline__ int bsdf_kind_of(int k) {
     return k == K_LAMBERT ? KIND_LAMBERT : k == K_MICROFACET_CONDUCTOR ? KIND_MF_CONDUCTOR : k == K_MICROFACET_DIELECTRIC ? KIND_MF_DIELECTRIC : KIND_DELTA;
 }
 
+// Reordering key of a ray: Morton code of its origin's cell in a 2^bits-per-axis grid over the scene's bounds, then
+// (optionally) the octant of its direction.  Rays of one bin start in the same region and head the same way: a warp of
+// them walks the same nodes for longer than 32 rays in emission order do.
+__device__ __forceinline__ unsigned spread_bits3(unsigned v) {  // 10 bits -> every third bit
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__device__ __forceinline__ unsigned ray_sort_key(const WfParams& p, const float4& o, const float4& d) {
+    const float hi = (float)((1 << p.sort_cell_bits) - 1);
+    const unsigned cx = (unsigned)fminf(fmaxf((o.x - p.sort_min[0]) * p.sort_scale[0], 0.f), hi);
+    const unsigned cy = (unsigned)fminf(fmaxf((o.y - p.sort_min[1]) * p.sort_scale[1], 0.f), hi);
+    const unsigned cz = (unsigned)fminf(fmaxf((o.z - p.sort_min[2]) * p.sort_scale[2], 0.f), hi);
+    unsigned key = spread_bits3(cx) | (spread_bits3(cy) << 1) | (spread_bits3(cz) << 2);
+    if (p.sort_dir) key = (key << 3) | (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
+    return key;
+}
+
 // Warp-aggregated append of the survivors' records to the next iteration's ray queue.
 // GUARD: the Whitted mode's ray tree can outgrow the pool (a mirror spawns two rays); rays past the end of the
 // queue are dropped and counted (stats.invalid_contributions) -- consumers clamp the queue length to the capacity.
@@ -274,7 +312,21 @@ __device__ __forceinline__ void append_next(const WfParams& p, int* next_count, 
             st_stream(&p.ray_o[nbuf][dst], no);
             st_stream(&p.ray_d[nbuf][dst], nd);
             st_stream(&p.ray_b[nbuf][dst], nbeta);
+            if (!GUARD && p.sort_bins) {  // reordering: count the ray into its bin; the count it found is its rank there
+                const unsigned key = ray_sort_key(p, no, nd);
+                st_stream(&p.sort_kr[dst], make_uint2(key, atomicAdd(p.sort_bins + key, 1u)));
+            }
         }
+    }
+}
+
+// Reordering, second half: after the bins' counters were prefix-summed, ray i belongs at sorted position
+// start[bin] + rank.  k_extend then reads perm[] in order and gathers the rays.
+__global__ void __launch_bounds__(kBlock) k_permute(const __grid_constant__ WfParams p, int it) {
+    const int n = min(p.counters[CNT_RAYS * p.counter_stride + it], p.queue_capacity);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 kr = ld_stream(&p.sort_kr[i]);
+        p.perm[__ldg(p.sort_start + kr.x) + kr.y] = i;
     }
 }
 
@@ -498,6 +550,8 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
                             }
                         } else if (fits) {
                             st_stream(&p.sh_o[si], make_float4(0.f, 0.f, 0.f, -1.f));
+                        } else if (valid) {
+                            atomicAdd(p.stats + ST_NEE_DROPPED, 1ull);  // no shadow slot left: the sample is lost, and counted
                         }
                     }
                 }

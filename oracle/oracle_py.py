@@ -75,6 +75,7 @@ class Oracle:
             g("render_counted").argtypes = [P, I, I, I, F, C.POINTER(C.c_uint64)]
             g("render_counted").restype = C.c_double
             g("philox_block").argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, F]
+            g("philox_raw").argtypes = [C.POINTER(C.c_uint32)] * 3
 
     def _fn(self, name):
         return getattr(self.lib, self.pfx + name)
@@ -115,6 +116,13 @@ class Oracle:
     def philox_block(self, pixel, sample, block, seed):
         o = np.empty(4, np.float32)
         self._fn("philox_block")(pixel, sample, block, seed, _f(o))
+        return o
+
+    def philox_raw(self, ctr4, key2):
+        ctr4 = np.ascontiguousarray(ctr4, np.uint32); key2 = np.ascontiguousarray(key2, np.uint32)
+        o = np.empty(4, np.uint32)
+        u32p = C.POINTER(C.c_uint32)
+        self._fn("philox_raw")(ctr4.ctypes.data_as(u32p), key2.ctypes.data_as(u32p), o.ctypes.data_as(u32p))
         return o
 
 

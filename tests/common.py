@@ -149,3 +149,59 @@ def bsdf_ex_cases(pkg):
         "trans_tr": D(kind=MT, distribution=TR, sample_visible_area=1, color=(.95, .95, .95), alphax=.2, alphay=.2, eta_a=1.0, eta_b=1.5),
         "trans_beckmann_aniso": D(kind=MT, distribution=BK, sample_visible_area=1, color=(.9, .95, .9), alphax=.15, alphay=.3, eta_a=1.0, eta_b=1.33),
     }
+
+
+# Philox4x32-10 known-answer vectors (Random123 kat_vectors: counter[4], key[2] -> output[4])
+PHILOX_KAT = [
+    ((0x00000000, 0x00000000, 0x00000000, 0x00000000), (0x00000000, 0x00000000), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff), (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+]
+
+
+def skewed_scene(pkg, n=1100, ratio=1.03, res=32):
+    """Corner-anchored triangles of geometrically growing size: exact-sweep SAH peels the largest one off at every level,
+    i.e. builds a chain one primitive per level -- deeper than the traversal stack unless the uploader rebuilds it."""
+    cam = pkg.Camera((3.0, 2.0, 40.0), (-0.05, -0.03, -1.0), (0, 1, 0), 60.0, res, res)
+    S, M, L, Pm = pkg.Shape, pkg.Material, pkg.Light, pkg.Primitive
+    z3 = (0.0, 0.0, 0.0)
+    shapes = []
+    for k in range(n):
+        s = float(np.float32(0.5 * ratio ** k))
+        shapes.append(S(pkg.SHAPE_TRIANGLE, 0, ((0, 0, -0.001 * k), (s, 0, -0.001 * k), (0, s, -0.001 * k - 0.5 * s), z3)))
+    mats = [M(pkg.MAT_MATTE, 0, (.7, .6, .5), z3, 0, 0)]
+    lights = [L(pkg.LIGHT_ENVIRONMENT, -1, (.6, .7, .9), z3, z3)]
+    prims = [Pm(k, 0, -1) for k in range(n)]
+    return pkg.HostScene.from_arrays(cam, shapes, mats, lights, prims, max_depth=3, name="skewed")
+
+
+def coincident_scene(pkg, n=100000, res=32):
+    """n triangles with IDENTICAL centroids (concentric, growing): no builder can separate them by position."""
+    cam = pkg.Camera((0.0, 0.0, 30.0), (0, 0, -1.0), (0, 1, 0), 60.0, res, res)
+    S, M, L, Pm = pkg.Shape, pkg.Material, pkg.Light, pkg.Primitive
+    z3 = (0.0, 0.0, 0.0)
+    shapes = []
+    for k in range(n):
+        s = 1.0 + (k % 1000) * 0.004
+        shapes.append(S(pkg.SHAPE_TRIANGLE, 0, ((-s, -s, 0.0), (2 * s, -s, 0.0), (-s, 2 * s, 0.0), z3)))  # centroid (0, 0, 0) for every s
+    mats = [M(pkg.MAT_MATTE, 0, (.7, .6, .5), z3, 0, 0)]
+    lights = [L(pkg.LIGHT_ENVIRONMENT, -1, (.6, .7, .9), z3, z3)]
+    prims = [Pm(k, 0, -1) for k in range(n)]
+    return pkg.HostScene.from_arrays(cam, shapes, mats, lights, prims, max_depth=2, name="coincident")
+
+
+def chain_scene(pkg, n=110, res=16):
+    """Small triangles across the x axis at x = 2^k: with an exact SAH sweep (JPBRT_BVH_SWEEP) every split peels off the
+    farthest one -- a chain of ~n levels.  A ray up the axis enters every box near-child (the rest) first and pushes one
+    far leaf per level."""
+    cam = pkg.Camera((-1.0, 0.0, 0.0), (1.0, 0.0, 0.0), (0, 1, 0), 20.0, res, res)
+    S, M, L, Pm = pkg.Shape, pkg.Material, pkg.Light, pkg.Primitive
+    z3 = (0.0, 0.0, 0.0)
+    shapes = []
+    for k in range(n):
+        x, h = float(2.0 ** k), 0.25 * float(2.0 ** k)
+        shapes.append(S(pkg.SHAPE_TRIANGLE, 0, ((x, -h, -h), (x, h, -h), (x, 0.0, h), z3)))
+    mats = [M(pkg.MAT_MATTE, 0, (.7, .6, .5), z3, 0, 0)]
+    lights = [L(pkg.LIGHT_ENVIRONMENT, -1, (.6, .7, .9), z3, z3)]
+    prims = [Pm(k, 0, -1) for k in range(n)]
+    return pkg.HostScene.from_arrays(cam, shapes, mats, lights, prims, max_depth=2, name="chain")

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 import common
+from test_gpu_parity import check_hits
 from test_host_bvh import check_tree
 
 pytestmark = pytest.mark.gpu
@@ -21,7 +22,7 @@ def build(pkg, name):
 
 
 @pytest.mark.parametrize("name", ["cornell", "bunny", "glossy", "large", "specular"])
-def test_device_built_tree_is_valid_and_gives_the_same_hits(pkg, checker, gpu, name):
+def test_device_built_tree_is_valid_and_gives_the_same_hits(pkg, checker, port, gpu, name):
     sc = build(pkg, name)
     host, dev = pkg.Context(sc, gpu_bvh=False), pkg.Context(sc, gpu_bvh=True)
     assert host.stats()["bvh_builder"] == 0 and dev.stats()["bvh_builder"] == 1
@@ -35,6 +36,12 @@ def test_device_built_tree_is_valid_and_gives_the_same_hits(pkg, checker, gpu, n
     raysB, P, N = common.secondary_rays(ks, raysA, rng)
     raysC = common.bbox_rays(ks.info(), rng, 1 << 15)
     flagged = 0
+    # the device-built tree against the REFERENCE's own hits (not just against the host-built tree): prim id exact except
+    # flagged ties / grazing cases, t / position / normal bit-exact
+    report = []
+    ps = port.scene(sc)
+    for tag, rays in (("A", raysA), ("B", raysB), ("C", raysC)):
+        check_hits(name, sc, "lbvh:" + tag, dev, ks, ps, rays, report)
     for rays in (raysA, raysB, raysC):
         h, d = host.unit_scene_intersect(rays), dev.unit_scene_intersect(rays)
         same = h[0] == d[0]
@@ -44,6 +51,8 @@ def test_device_built_tree_is_valid_and_gives_the_same_hits(pkg, checker, gpu, n
             assert np.array_equal(a[same], b[same])
     tgt = (P + raysB[:, 3:6] * rng.uniform(0.5, 500, (len(P), 1))).astype(np.float32)
     assert (host.unit_scene_occluded(P, tgt) != dev.unit_scene_occluded(P, tgt)).mean() <= 2e-4
+    assert (ks.occluded(P, tgt) != dev.unit_scene_occluded(P, tgt)).mean() <= (2e-2 if name == "large" else 2e-4)
+    print("LBVH vs reference:", report)
     print(name, "LBVH depth", depth, "nodes", len(nodes), "vs SAH nodes", len(host.table("nodes")) // 16, "flagged", flagged,
           "build s: gpu %.4f host %.4f" % (dev.stats()["bvh_build_seconds"], host.stats()["bvh_build_seconds"]))
     host.close(); dev.close()

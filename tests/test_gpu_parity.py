@@ -46,6 +46,16 @@ def test_rng_blocks_bit_exact(pkg, port, gpu):
     assert (g >= 0).all() and (g < 1).all() and abs(g.mean() - 0.5) < 0.01
 
 
+def test_philox_known_answer_vectors(pkg, gpu):
+    """The CUDA generator against the published Philox4x32-10 known-answer vectors (Random123 kat_vectors)."""
+    ctr = np.array([k[0] for k in common.PHILOX_KAT], np.uint32)
+    key = np.array([k[1] for k in common.PHILOX_KAT], np.uint32)
+    want = np.array([k[2] for k in common.PHILOX_KAT], np.uint32)
+    assert np.array_equal(pkg.unit_philox_raw(ctr, key), want)
+    blk = pkg.unit_rng_block([0], [0], [0], 0)[0]
+    assert np.array_equal(blk, (want[0] >> 8).astype(np.float32) / np.float32(1 << 24))
+
+
 @pytest.mark.parametrize("name", ["tri", "tri_flip_big", "rect", "rect_xz_flip", "sphere", "disk"])
 def test_shape_intersect_bit_exact(pkg, checker, gpu, name):
     sh = common.shapes(pkg)[name]

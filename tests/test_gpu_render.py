@@ -287,3 +287,25 @@ def test_pixel_bands_do_not_change_the_film(pkg, gpu):
         assert ctx.stats()["samples"] == n_whole == 200 * 120 * 5
         np.testing.assert_allclose(got, whole, rtol=2e-5, atol=1e-6)
     ctx.close()
+
+
+@pytest.mark.parametrize("name,scale", [("cornell", 1.0), ("bunny", 0.5)])
+def test_ray_reordering_does_not_change_the_film(pkg, gpu, name, scale):
+    """Option "sort_rays": k_extend walks the rays of bounces >= 1 in (origin cell, direction octant) order through a
+    permutation.  Which lane traces a ray must not matter: the same rays, the same hits, the same film."""
+    sc = pkg.HostScene.builtin(name, 160, 120, scale)
+    ctx = pkg.Context(sc)
+    ctx.render_pass(0, 4, seed=11)
+    plain = ctx.read_film(finalize=False)
+    st0 = ctx.stats()
+    for opt in (5, 16 + 5, 16 + 3, 2):
+        ctx.clear_film(); ctx.reset_stats()
+        ctx.set_option("sort_rays", opt)
+        ctx.render_pass(0, 4, seed=11)
+        got = ctx.read_film(finalize=False)
+        st = ctx.stats()
+        for k in ("samples", "extension_rays", "shadow_rays", "shaded_vertices"):
+            assert st[k] == st0[k], (opt, k)
+        assert st["invalid_contributions"] == 0
+        np.testing.assert_allclose(got, plain, rtol=2e-5, atol=1e-6)
+    ctx.close()

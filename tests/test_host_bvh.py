@@ -2,6 +2,8 @@
 import numpy as np
 import pytest
 
+import common
+
 
 def decode(pkg, sc):
     nodes = pkg.debug_flatten(sc, "nodes").reshape(-1, 16)
@@ -159,3 +161,25 @@ def test_reinsertion_lowers_the_cost_and_keeps_the_tree_valid(pkg, monkeypatch):
     monkeypatch.delenv("JPBRT_BVH_REINSERT")
     nd, rd, _, _ = decode(pkg, sc)
     assert np.array_equal(nd.view(np.int32), n2.view(np.int32))  # the default for a scene of this size (bit compare: child refs are ints)
+
+
+def test_tree_deeper_than_the_traversal_stack_is_rebuilt(pkg, monkeypatch):
+    """The kernels' 64-entry node stack would silently lose subtrees of a tree deeper than 62 levels (the host
+    SAH build had no depth check).  The uploader measures the depth of whatever its builder produced and rebuilds with
+    object-median splits when it exceeds the limit; the limit is lowered here to force that path on a skewed scene
+    (nested, corner-anchored triangles of geometrically growing size)."""
+    sc = common.skewed_scene(pkg)
+    nodes, refs, slots, nrm = decode(pkg, sc)
+    natural = check_tree(nodes, refs, slots, nrm, pkg.debug_flatten(sc, "prim_slot"), sc.d.n_primitives)
+    assert 12 < natural + 1 <= 62, natural  # (check_tree counts edges below the root)
+    monkeypatch.setenv("JPBRT_BVH_MAX_DEPTH", "12")
+    nodes, refs, slots, nrm = decode(pkg, sc)
+    rebuilt = check_tree(nodes, refs, slots, nrm, pkg.debug_flatten(sc, "prim_slot"), sc.d.n_primitives)
+    assert rebuilt + 1 <= 12, rebuilt  # 1,100 primitives, leaves of <= 4: ceil(log2(275)) + 1 = 10 levels
+
+
+def test_coincident_centroids_build_a_shallow_valid_tree(pkg):
+    sc = common.coincident_scene(pkg, n=20000)
+    nodes, refs, slots, nrm = decode(pkg, sc)
+    depth = check_tree(nodes, refs, slots, nrm, pkg.debug_flatten(sc, "prim_slot"), sc.d.n_primitives)
+    assert depth <= 20, depth
