@@ -74,7 +74,8 @@ int jpbrt_render_pass(jpbrt_ctx* ctx, int sample_begin, int sample_count, uint64
 /* Replaces FFilmView::AddColor(x, y, Clamp01(L)) (integrator.cc:108, film.h:64-68) and the film
  * readback.  If `finalize` != 0 writes clamp01(sum / spp_total), else the raw sums.  `rgb` is
  * host memory, width*height*3 floats, row 0 = top of the image (the reference's FFilm layout).
- * Synchronises the stream. */
+ * Synchronises the stream.  On a context with a communicator (jpbrt_comm_init) the films of all ranks are first
+ * summed onto rank 0 (one ncclReduce); spp_total is then the total over all ranks, and ranks != 0 may pass rgb = NULL. */
 int jpbrt_read_film(jpbrt_ctx* ctx, float* rgb, int spp_total, int finalize);
 
 /* Zero the device film (FFilm::Clear, film.h:75-82). */
@@ -107,6 +108,35 @@ int    jpbrt_finalize_film_device(jpbrt_ctx* ctx, void* out_device, int spp_tota
 /* Re-upload the flattened scene arrays from the host copy kept in the context (what a per-frame
  * caller pays for a changed scene); returns bytes copied through *bytes. */
 int    jpbrt_reupload_scene(jpbrt_ctx* ctx, size_t* bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU inside the boundary (replaces the thread pool of FIntegrator::Render, integrator.cc:53-74,
+ * parallel.cc, across devices): the scene is replicated, the SAMPLE indices of every pixel are partitioned, and the raw
+ * float32 films are summed onto rank 0 with ONE ncclReduce over NVLink; Clamp01(sum / spp_total) happens after the
+ * reduce, as the reference clamps the mean (integrator.cc:108).  NCCL is bound at run time (dlopen libnccl.so.2: the
+ * instance already loaded in the process, e.g. torch's, else the system's); without it these calls return
+ * JPBRT_ERR_UNSUPPORTED and the single-GPU path is unaffected.
+ *
+ *   one process per GPU : rank 0 calls jpbrt_comm_unique_id and hands the bytes to the other ranks (any transport),
+ *                         every rank calls jpbrt_comm_init on its context, renders its own sample range
+ *                         (jpbrt_sample_partition) with jpbrt_render_pass, then calls jpbrt_read_film: a context with a
+ *                         communicator reduces first; rank 0 receives the image, the other ranks pass rgb = NULL.
+ *   one process, N GPUs : jpbrt_render_multi (ncclCommInitAll + grouped reduce).
+ * ---------------------------------------------------------------------------------------- */
+#define JPBRT_COMM_ID_BYTES 128
+int  jpbrt_comm_unique_id(void* id, size_t bytes);
+int  jpbrt_comm_init(jpbrt_ctx* ctx, const void* id, size_t bytes, int rank, int nranks);
+int  jpbrt_comm_rank(const jpbrt_ctx* ctx);
+int  jpbrt_comm_size(const jpbrt_ctx* ctx);
+/* The reduce alone (stream-ordered, asynchronous): afterwards rank 0's device film holds the sum over all ranks and the
+ * other ranks' films are zero.  jpbrt_read_film calls it if it has not run since the last pass. */
+int  jpbrt_reduce_film(jpbrt_ctx* ctx);
+/* Rank r's share of spp_total sample indices: contiguous, as even as possible. */
+void jpbrt_sample_partition(int spp_total, int rank, int nranks, int* begin, int* count);
+/* FIntegrator::Render with `ngpus` devices (0 .. ngpus-1) of this process for threads: upload to every device, render the
+ * partitions concurrently, reduce, finalize, read back.  reduce_ms_out (optional): device time of the reduce on rank 0. */
+int  jpbrt_render_multi(const jpbrt_scene_desc* desc, int integrator, int spp, uint64_t seed, int ngpus, float* rgb,
+                        double* seconds_out, double* reduce_ms_out);
 
 /* Options (value 0 / 1 unless noted):
  *   "integrator"       jpbrt_integrator
@@ -146,6 +176,10 @@ typedef struct jpbrt_stats {
     uint64_t stack_overflows;  /* far BVH children lost to a full traversal stack (tree deeper than 63 levels of pending subtrees) */
     uint64_t nee_dropped;      /* light samples that found no shadow-ray slot (pool smaller than vertices x lights) */
     uint64_t bvh_depth;        /* levels of the BVH (root = 1); trees deeper than 62 are rebuilt with median splits at upload */
+    double   ms_reduce;        /* with "stage_timing": device time of the NCCL film reduce(s) on this rank */
+    /* with "count_traversal": DISTINCT node / primitive records fetched per warp step (lanes of a warp that sit on the same
+     * node share one fetch) -- what the memory system has to deliver, as opposed to the per-lane test counts above */
+    uint64_t node_fetches, prim_fetches, shadow_node_fetches, shadow_prim_fetches;
 } jpbrt_stats;
 int jpbrt_get_stats(jpbrt_ctx* ctx, jpbrt_stats* out);
 

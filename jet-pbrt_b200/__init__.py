@@ -20,53 +20,8 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libjetpbrt_b200.so"
 
 
-# ---- include/jetpbrt_scene.h --------------------------------------------------------------------
-class Camera(C.Structure):
-    _fields_ = [("pos", C.c_float * 3), ("front", C.c_float * 3), ("up", C.c_float * 3),
-                ("vfov_deg", C.c_float), ("width", C.c_int), ("height", C.c_int)]
-
-
-class Shape(C.Structure):
-    _fields_ = [("type", C.c_int), ("flip_normal", C.c_int), ("p", (C.c_float * 3) * 4)]
-
-
-class Material(C.Structure):
-    _fields_ = [("type", C.c_int), ("remap_roughness", C.c_int), ("a", C.c_float * 3), ("b", C.c_float * 3),
-                ("f0", C.c_float), ("f1", C.c_float)]
-
-
-class BsdfDesc(C.Structure):
-    """jpbrt_bsdf_desc (include/jetpbrt_scene.h): the BSDF classes of the reference that no material builds."""
-    _fields_ = [("kind", C.c_int), ("distribution", C.c_int), ("sample_visible_area", C.c_int), ("fresnel", C.c_int),
-                ("color", C.c_float * 3), ("exponent", C.c_float), ("alphax", C.c_float), ("alphay", C.c_float),
-                ("eta_a", C.c_float), ("eta_b", C.c_float), ("c_eta_i", C.c_float * 3), ("c_eta_t", C.c_float * 3), ("c_k", C.c_float * 3)]
-
-
-BSDF_PHONG, BSDF_MICROFACET_REFLECTION, BSDF_MICROFACET_TRANSMISSION = 0, 1, 2
-DIST_BECKMANN, DIST_TROWBRIDGE_REITZ = 0, 1
-FRESNEL_NOOP, FRESNEL_DIELECTRIC, FRESNEL_CONDUCTOR = 0, 1, 2
-
-
-class Light(C.Structure):
-    _fields_ = [("type", C.c_int), ("shape", C.c_int), ("color", C.c_float * 3), ("pos", C.c_float * 3),
-                ("dir", C.c_float * 3)]
-
-
-class Primitive(C.Structure):
-    _fields_ = [("shape", C.c_int), ("material", C.c_int), ("light", C.c_int)]
-
-
-class SceneDesc(C.Structure):
-    _fields_ = [("camera", Camera), ("max_depth", C.c_int), ("n_shapes", C.c_int), ("n_materials", C.c_int),
-                ("n_lights", C.c_int), ("n_primitives", C.c_int),
-                ("shapes", C.POINTER(Shape)), ("materials", C.POINTER(Material)), ("lights", C.POINTER(Light)),
-                ("primitives", C.POINTER(Primitive)), ("name", C.c_char_p)]
-
-
-SHAPE_TRIANGLE, SHAPE_RECTANGLE, SHAPE_SPHERE, SHAPE_DISK = 0, 1, 2, 3
-UPLOAD_GPU_BVH = 1  # jpbrt_upload_scene_ex flag
-MAT_MATTE, MAT_MIRROR, MAT_GLASS, MAT_PLASTIC, MAT_METAL = 0, 1, 2, 3, 4
-LIGHT_ENVIRONMENT, LIGHT_AREA, LIGHT_POINT, LIGHT_DIRECTION = 0, 1, 2, 3
+from .scene_desc import *  # noqa: F401,F403  (ctypes mirror of include/jetpbrt_scene.h + HostScene)
+from . import scene_desc as _scene_desc
 
 
 class Stats(C.Structure):
@@ -79,7 +34,9 @@ class Stats(C.Structure):
                 ("n_nodes", C.c_uint64), ("n_prim_slots", C.c_uint64), ("scene_bytes", C.c_uint64),
                 ("bvh_build_seconds", C.c_double), ("paths_in_flight", C.c_uint64), ("bvh_builder", C.c_uint64),
                 ("bvh_device_seconds", C.c_double), ("dropped_rays", C.c_uint64), ("stack_overflows", C.c_uint64),
-                ("nee_dropped", C.c_uint64), ("bvh_depth", C.c_uint64)]
+                ("nee_dropped", C.c_uint64), ("bvh_depth", C.c_uint64), ("ms_reduce", C.c_double),
+                ("node_fetches", C.c_uint64), ("prim_fetches", C.c_uint64), ("shadow_node_fetches", C.c_uint64),
+                ("shadow_prim_fetches", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -93,12 +50,9 @@ EXPORTS = [
     "jpbrt_get_stats", "jpbrt_unit_intersect_shape", "jpbrt_unit_scene_intersect", "jpbrt_unit_scene_occluded",
     "jpbrt_unit_bsdf", "jpbrt_unit_bsdf_ex", "jpbrt_unit_light_sample", "jpbrt_unit_emitted", "jpbrt_unit_generate_rays",
     "jpbrt_unit_rng_block", "jpbrt_unit_philox_raw", "jpbrt_scene_info", "jpbrt_scene_builtin", "jpbrt_scene_get_desc",
-    "jpbrt_scene_free", "jpbrt_save_image", "jpbrt_version", "jpbrt_device_count", "jpbrt_debug_flatten", "jpbrt_debug_ctx_table",
+    "jpbrt_comm_unique_id", "jpbrt_comm_init", "jpbrt_comm_rank", "jpbrt_comm_size", "jpbrt_reduce_film", "jpbrt_sample_partition",
+    "jpbrt_render_multi", "jpbrt_scene_free", "jpbrt_save_image", "jpbrt_version", "jpbrt_device_count", "jpbrt_debug_flatten", "jpbrt_debug_ctx_table",
 ]
-
-
-class JpbrtError(RuntimeError):
-    pass
 
 
 def _load():
@@ -142,7 +96,6 @@ def _load():
     lib.jpbrt_unit_generate_rays.argtypes = [P, I, F, F, F]
     lib.jpbrt_unit_rng_block.argtypes = [I, I, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                          C.c_uint64, F]
-    lib.jpbrt_unit_philox_raw.argtypes = [I, I, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.jpbrt_scene_info.argtypes = [P, F]
     lib.jpbrt_scene_builtin.argtypes = [C.c_char_p, I, I, C.c_float]
     lib.jpbrt_scene_builtin.restype = P
@@ -156,10 +109,22 @@ def _load():
     lib.jpbrt_debug_flatten.restype = C.c_longlong
     lib.jpbrt_debug_ctx_table.argtypes = [P, I, P, C.c_longlong]
     lib.jpbrt_debug_ctx_table.restype = C.c_longlong
+    if not hasattr(lib, "jpbrt_render_multi"):  # a round-1 build loaded for an A/B timing (scripts/ab_variants.sh): no round-2 entry points
+        return lib
+    lib.jpbrt_unit_philox_raw.argtypes = [I, I, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.jpbrt_comm_unique_id.argtypes = [P, C.c_size_t]
+    lib.jpbrt_comm_init.argtypes = [P, P, C.c_size_t, I, I]
+    lib.jpbrt_comm_rank.argtypes = [P]
+    lib.jpbrt_comm_size.argtypes = [P]
+    lib.jpbrt_reduce_film.argtypes = [P]
+    lib.jpbrt_sample_partition.argtypes = [I, I, I, IP, IP]
+    lib.jpbrt_sample_partition.restype = None
+    lib.jpbrt_render_multi.argtypes = [C.POINTER(SceneDesc), I, I, C.c_uint64, I, F, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     return lib
 
 
 lib = _load()
+_scene_desc.bind_scene_lib(lib)  # HostScene's built-in scenes come from this library (the same host code as libjetpbrt_host.so)
 
 
 def _f(a):
@@ -181,62 +146,6 @@ def _check(rc, ctx=None):
     if rc != 0:
         msg = lib.jpbrt_last_error(ctx)
         raise JpbrtError(f"jetpbrt_b200 error {rc}: {msg.decode() if msg else '?'}")
-
-
-# ---- scenes --------------------------------------------------------------------------------------
-class HostScene:
-    """A scene description owned by the host library (jetpbrt::Scene) or built in Python."""
-
-    def __init__(self, handle=None, desc=None, keepalive=None):
-        self._handle = handle
-        self._desc = desc
-        self._keepalive = keepalive
-
-    @classmethod
-    def builtin(cls, name: str, width: int, height: int, scale: float = 1.0) -> "HostScene":
-        h = lib.jpbrt_scene_builtin(name.encode(), width, height, scale)
-        if not h:
-            raise JpbrtError(f"unknown built-in scene {name!r}")
-        return cls(handle=h, desc=lib.jpbrt_scene_get_desc(h))
-
-    @classmethod
-    def from_arrays(cls, camera: Camera, shapes, materials, lights, primitives, max_depth=5, name="scene"):
-        """Build a description from Python lists of Shape/Material/Light/Primitive structs."""
-        sa = (Shape * max(1, len(shapes)))(*shapes)
-        ma = (Material * max(1, len(materials)))(*materials)
-        la = (Light * max(1, len(lights)))(*lights)
-        pa = (Primitive * max(1, len(primitives)))(*primitives)
-        nm = name.encode()
-        d = SceneDesc(camera, max_depth, len(shapes), len(materials), len(lights), len(primitives),
-                      C.cast(sa, C.POINTER(Shape)), C.cast(ma, C.POINTER(Material)), C.cast(la, C.POINTER(Light)),
-                      C.cast(pa, C.POINTER(Primitive)), nm)
-        return cls(desc=C.pointer(d), keepalive=(sa, ma, la, pa, nm, d))
-
-    @property
-    def desc(self):
-        return self._desc
-
-    @property
-    def d(self) -> SceneDesc:
-        return self._desc.contents
-
-    def set_max_depth(self, depth: int):
-        self._desc.contents.max_depth = depth
-
-    def set_resolution(self, w: int, h: int):
-        self._desc.contents.camera.width = w
-        self._desc.contents.camera.height = h
-
-    def close(self):
-        if self._handle:
-            lib.jpbrt_scene_free(self._handle)
-            self._handle = None
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
 
 
 # ---- device context --------------------------------------------------------------------------------
@@ -283,6 +192,19 @@ class Context:
         s = Stats()
         _check(lib.jpbrt_get_stats(self._ctx, C.byref(s)), self._ctx)
         return s.as_dict()
+
+    # multi-GPU (one process per GPU): NCCL communicator inside the library
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        buf = C.create_string_buffer(unique_id, COMM_ID_BYTES)
+        _check(lib.jpbrt_comm_init(self._ctx, buf, COMM_ID_BYTES, rank, nranks), self._ctx)
+
+    def reduce_film(self):
+        _check(lib.jpbrt_reduce_film(self._ctx), self._ctx)
+
+    def read_film_root(self, spp_total: int, out_ptr=None, finalize: bool = True):
+        """jpbrt_read_film on a context with a communicator: reduce, then rank 0 finalizes and reads into host memory at
+        `out_ptr` (ranks != 0 pass None)."""
+        _check(lib.jpbrt_read_film(self._ctx, C.cast(out_ptr, C.POINTER(C.c_float)) if out_ptr else None, spp_total, 1 if finalize else 0), self._ctx)
 
     def reupload_scene(self) -> int:
         n = C.c_size_t(0)
@@ -436,6 +358,30 @@ def render(scene: HostScene, spp: int, seed: int = 1234, device: int = 0, integr
     sec = C.c_double(0)
     _check(lib.jpbrt_render_integrator(scene.desc, INTEGRATORS[integrator], spp, seed, device, _f(out), C.byref(sec)))
     return out, sec.value
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0); hand the bytes to the other ranks with any transport."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(lib.jpbrt_comm_unique_id(buf, COMM_ID_BYTES))
+    return buf.raw
+
+
+def sample_partition(spp_total: int, rank: int, nranks: int):
+    b, n = C.c_int(0), C.c_int(0)
+    lib.jpbrt_sample_partition(spp_total, rank, nranks, C.byref(b), C.byref(n))
+    return b.value, n.value
+
+
+def render_multi(scene: HostScene, spp: int, ngpus: int, seed: int = 1234, integrator: str = "path"):
+    """FIntegrator::Render with `ngpus` devices of this process: returns (film, seconds, reduce_ms)."""
+    out = np.empty((scene.d.camera.height, scene.d.camera.width, 3), dtype=np.float32)
+    sec, red = C.c_double(0), C.c_double(0)
+    _check(lib.jpbrt_render_multi(scene.desc, INTEGRATORS[integrator], spp, seed, ngpus, _f(out), C.byref(sec), C.byref(red)))
+    return out, sec.value, red.value
 
 
 def save_image(basename: str, kind: int, film: np.ndarray):

@@ -16,6 +16,7 @@
 
 #include "../../include/jetpbrt_b200.h"
 #include "scene_flatten.h"
+#include "nccl_dl.h"
 #include "bsdf_ex.cuh"
 #include "bvh_build.cuh"
 #include "wavefront.cuh"
@@ -113,9 +114,13 @@ struct jpbrt_ctx {
     unsigned kinds_present = 0;  // bit k set: some material of the scene can build BSDF kind k
     // launch geometry
     int grid_generate = 0, grid_extend = 0, grid_extend_c = 0, grid_extend6 = 0, grid_connect6 = 0, grid_logic = 0, grid_logic_w = 0, grid_debug = 0, grid_shade[4] = {0, 0, 0, 0}, grid_shade_w[4] = {0, 0, 0, 0}, grid_connect = 0, grid_connect_c = 0, grid_finalize = 0;
+    // multi-GPU: this context's rank in an NCCL communicator (jpbrt_comm_init); the film reduce runs on `stream`
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    bool film_reduced = false;  // the film was reduced since the last pass: jpbrt_read_film must not reduce it again
     // host-side accounting
     unsigned long long kernel_launches = 0;
-    double ms_stage[5] = {0, 0, 0, 0, 0};
+    double ms_stage[6] = {0, 0, 0, 0, 0, 0};  // generate, extend, shade, connect, finalize, reduce
     std::vector<StageEvent> pending_events;
     std::vector<cudaEvent_t> free_events;
     std::vector<void*> pinned;  // host scene arrays registered with cudaHostRegister
@@ -338,6 +343,93 @@ WfParams make_params(jpbrt_ctx* c) {
 
 }  // namespace
 
+// Second half of an upload: the context's HostScene is flattened; allocate, copy and size everything on `device`.
+// On failure the context is destroyed.
+static int finish_upload(jpbrt_ctx* c, int device) {
+    int rc = select_device(nullptr, device);
+    if (rc != 0) { delete c; return rc; }
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    auto fail = [&](int code) { jpbrt_destroy(c); return code; };
+    if (!c->stream && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError())));
+    HostScene& hs = c->hs;
+    cudaError_t e = cudaSuccess;
+    if ((e = c->nodes.Alloc(hs.nodes.size())) != cudaSuccess || (e = c->slots.Alloc(hs.slots.size())) != cudaSuccess ||
+        (e = c->slot_nrm.Alloc(hs.slot_nrm.size())) != cudaSuccess || (e = c->slot_ml.Alloc(hs.slot_ml.size())) != cudaSuccess ||
+        (e = c->materials.Alloc(hs.materials.size())) != cudaSuccess || (e = c->lights.Alloc(hs.lights.size())) != cudaSuccess ||
+        (e = c->inf_lights.Alloc(hs.inf_lights.size())) != cudaSuccess || (e = c->prim_slot.Alloc(hs.prim_slot.size())) != cudaSuccess ||
+        (e = c->slot_frame.Alloc(hs.slot_frame.size())) != cudaSuccess || (e = c->nee_lights.Alloc(hs.nee_lights.size())) != cudaSuccess ||
+        (e = c->pixel_order.Alloc(hs.pixel_order.size())) != cudaSuccess ||
+        (e = c->film.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess ||
+        (e = c->film_final.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess || (e = c->dstats.Alloc(ST_COUNT)) != cudaSuccess ||
+        (e = c->pass_args.Alloc(1)) != cudaSuccess)
+        return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)));
+    pin_vector(c, hs.nodes); pin_vector(c, hs.slots); pin_vector(c, hs.slot_nrm); pin_vector(c, hs.slot_ml);
+    pin_vector(c, hs.materials); pin_vector(c, hs.lights); pin_vector(c, hs.inf_lights); pin_vector(c, hs.prim_slot);
+    pin_vector(c, hs.slot_frame); pin_vector(c, hs.nee_lights);
+    rc = upload_arrays(c, nullptr);
+    if (rc == 0 && c->pixel_order.Upload(hs.pixel_order.data(), hs.pixel_order.size(), c->stream) != cudaSuccess)
+        rc = set_error(c, JPBRT_ERR_CUDA, "pixel order upload failed");
+    if (rc != 0) { g_last_error = c->error; return fail(rc); }
+    DevScene& d = c->dsc;
+    d.pixel_order = c->pixel_order.ptr;
+    d.nodes = c->nodes.ptr; d.slots = c->slots.ptr; d.slot_nrm = c->slot_nrm.ptr; d.slot_ml = c->slot_ml.ptr;
+    d.materials = c->materials.ptr; d.lights = c->lights.ptr; d.inf_lights = c->inf_lights.ptr; d.prim_slot = c->prim_slot.ptr;
+    d.slot_frame = c->slot_frame.ptr; d.nee_lights = c->nee_lights.ptr;
+    d.n_nee_lights = (int)hs.nee_lights.size();
+    d.n_nodes = (int)(hs.nodes.size() / kNodeStride);
+    d.n_slots = (int)hs.slot_nrm.size();
+    d.n_materials = (int)(hs.materials.size() / kMaterialStride);
+    d.n_lights = (int)(hs.lights.size() / kLightStride);
+    d.n_inf_lights = (int)hs.inf_lights.size();
+    d.n_prims = hs.n_prims;
+    d.max_depth = hs.max_depth;
+    d.width = hs.width;
+    d.height = hs.height;
+    d.world_radius = hs.world_radius;
+    d.cam = hs.cam;
+    for (const Int2& ml : hs.slot_ml) {  // BSDF kinds that materials bound to primitives can build
+        if (ml.x < 0) continue;
+        int type;
+        memcpy(&type, &hs.materials[(size_t)ml.x * kMaterialStride].w, 4);
+        c->kinds_present |= type == JPBRT_MAT_MATTE ? 1u : type == JPBRT_MAT_METAL ? 2u : type == JPBRT_MAT_PLASTIC ? (1u | 4u) : 8u;
+        if (type == JPBRT_MAT_MIRROR) c->has_mirror = true;
+    }
+    // iterations: bounces 0..max_depth, plus slack for null-material pass-through vertices
+    c->n_iters = hs.max_depth + 1 + (hs.has_null_material ? 16 : 0);
+    c->counter_stride = c->n_iters + 2;
+    if ((e = c->counters.Alloc((size_t)CNT_KINDS * c->counter_stride)) != cudaSuccess)
+        return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)));
+    c->grid_generate = occupancy_grid(c, k_generate);
+    c->grid_extend = occupancy_grid(c, k_extend<false, 5>);
+    c->grid_extend6 = occupancy_grid(c, k_extend<false, 6>);
+    c->grid_extend_c = occupancy_grid(c, k_extend<true, 5>);
+    c->grid_logic = occupancy_grid(c, k_logic<false>);
+    c->grid_logic_w = occupancy_grid(c, k_logic<true>);
+    c->grid_debug = occupancy_grid(c, k_debug);
+    c->grid_shade[0] = occupancy_grid(c, k_shade<0>);
+    c->grid_shade[1] = occupancy_grid(c, k_shade<1>);
+    c->grid_shade[2] = occupancy_grid(c, k_shade<2>);
+    c->grid_shade[3] = occupancy_grid(c, k_shade<3>);
+    c->grid_shade_w[0] = occupancy_grid(c, k_shade<0, true>);
+    c->grid_shade_w[1] = occupancy_grid(c, k_shade<1, true>);
+    c->grid_shade_w[2] = occupancy_grid(c, k_shade<2, true>);
+    c->grid_shade_w[3] = occupancy_grid(c, k_shade<3, true>);
+    c->grid_connect = occupancy_grid(c, k_connect<false, 5>);
+    c->grid_connect6 = occupancy_grid(c, k_connect<false, 6>);
+    c->grid_connect_c = occupancy_grid(c, k_connect<true, 5>);
+    c->grid_finalize = occupancy_grid(c, k_finalize);
+    rc = jpbrt_clear_film(c);
+    if (rc == 0) rc = jpbrt_reset_stats(c);
+    if (rc != 0) { g_last_error = c->error; return fail(rc); }
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess)
+        return fail(set_error(nullptr, JPBRT_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e)));
+    return 0;
+}
+
+
 extern "C" {
 
 int jpbrt_device_count(void) {
@@ -419,84 +511,8 @@ int jpbrt_upload_scene_ex(const jpbrt_scene_desc* desc, int device, unsigned fla
         rc = select_device(nullptr, device);
         if (rc != 0) { delete c; return rc; }
     }
-    c->device = device;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
-    auto fail = [&](int code) { jpbrt_destroy(c); return code; };
-    if (!c->stream && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
-        return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError())));
-    HostScene& hs = c->hs;
-    cudaError_t e = cudaSuccess;
-    if ((e = c->nodes.Alloc(hs.nodes.size())) != cudaSuccess || (e = c->slots.Alloc(hs.slots.size())) != cudaSuccess ||
-        (e = c->slot_nrm.Alloc(hs.slot_nrm.size())) != cudaSuccess || (e = c->slot_ml.Alloc(hs.slot_ml.size())) != cudaSuccess ||
-        (e = c->materials.Alloc(hs.materials.size())) != cudaSuccess || (e = c->lights.Alloc(hs.lights.size())) != cudaSuccess ||
-        (e = c->inf_lights.Alloc(hs.inf_lights.size())) != cudaSuccess || (e = c->prim_slot.Alloc(hs.prim_slot.size())) != cudaSuccess ||
-        (e = c->slot_frame.Alloc(hs.slot_frame.size())) != cudaSuccess || (e = c->nee_lights.Alloc(hs.nee_lights.size())) != cudaSuccess ||
-        (e = c->pixel_order.Alloc(hs.pixel_order.size())) != cudaSuccess ||
-        (e = c->film.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess ||
-        (e = c->film_final.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess || (e = c->dstats.Alloc(ST_COUNT)) != cudaSuccess ||
-        (e = c->pass_args.Alloc(1)) != cudaSuccess)
-        return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)));
-    pin_vector(c, hs.nodes); pin_vector(c, hs.slots); pin_vector(c, hs.slot_nrm); pin_vector(c, hs.slot_ml);
-    pin_vector(c, hs.materials); pin_vector(c, hs.lights); pin_vector(c, hs.inf_lights); pin_vector(c, hs.prim_slot);
-    pin_vector(c, hs.slot_frame); pin_vector(c, hs.nee_lights);
-    rc = upload_arrays(c, nullptr);
-    if (rc == 0 && c->pixel_order.Upload(hs.pixel_order.data(), hs.pixel_order.size(), c->stream) != cudaSuccess)
-        rc = set_error(c, JPBRT_ERR_CUDA, "pixel order upload failed");
-    if (rc != 0) { g_last_error = c->error; return fail(rc); }
-    DevScene& d = c->dsc;
-    d.pixel_order = c->pixel_order.ptr;
-    d.nodes = c->nodes.ptr; d.slots = c->slots.ptr; d.slot_nrm = c->slot_nrm.ptr; d.slot_ml = c->slot_ml.ptr;
-    d.materials = c->materials.ptr; d.lights = c->lights.ptr; d.inf_lights = c->inf_lights.ptr; d.prim_slot = c->prim_slot.ptr;
-    d.slot_frame = c->slot_frame.ptr; d.nee_lights = c->nee_lights.ptr;
-    d.n_nee_lights = (int)hs.nee_lights.size();
-    d.n_nodes = (int)(hs.nodes.size() / kNodeStride);
-    d.n_slots = (int)hs.slot_nrm.size();
-    d.n_materials = (int)(hs.materials.size() / kMaterialStride);
-    d.n_lights = (int)(hs.lights.size() / kLightStride);
-    d.n_inf_lights = (int)hs.inf_lights.size();
-    d.n_prims = hs.n_prims;
-    d.max_depth = hs.max_depth;
-    d.width = hs.width;
-    d.height = hs.height;
-    d.world_radius = hs.world_radius;
-    d.cam = hs.cam;
-    for (const Int2& ml : hs.slot_ml) {  // BSDF kinds that materials bound to primitives can build
-        if (ml.x < 0) continue;
-        int type;
-        memcpy(&type, &hs.materials[(size_t)ml.x * kMaterialStride].w, 4);
-        c->kinds_present |= type == JPBRT_MAT_MATTE ? 1u : type == JPBRT_MAT_METAL ? 2u : type == JPBRT_MAT_PLASTIC ? (1u | 4u) : 8u;
-        if (type == JPBRT_MAT_MIRROR) c->has_mirror = true;
-    }
-    // iterations: bounces 0..max_depth, plus slack for null-material pass-through vertices
-    c->n_iters = hs.max_depth + 1 + (hs.has_null_material ? 16 : 0);
-    c->counter_stride = c->n_iters + 2;
-    if ((e = c->counters.Alloc((size_t)CNT_KINDS * c->counter_stride)) != cudaSuccess)
-        return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)));
-    c->grid_generate = occupancy_grid(c, k_generate);
-    c->grid_extend = occupancy_grid(c, k_extend<false, 5>);
-    c->grid_extend6 = occupancy_grid(c, k_extend<false, 6>);
-    c->grid_extend_c = occupancy_grid(c, k_extend<true, 5>);
-    c->grid_logic = occupancy_grid(c, k_logic<false>);
-    c->grid_logic_w = occupancy_grid(c, k_logic<true>);
-    c->grid_debug = occupancy_grid(c, k_debug);
-    c->grid_shade[0] = occupancy_grid(c, k_shade<0>);
-    c->grid_shade[1] = occupancy_grid(c, k_shade<1>);
-    c->grid_shade[2] = occupancy_grid(c, k_shade<2>);
-    c->grid_shade[3] = occupancy_grid(c, k_shade<3>);
-    c->grid_shade_w[0] = occupancy_grid(c, k_shade<0, true>);
-    c->grid_shade_w[1] = occupancy_grid(c, k_shade<1, true>);
-    c->grid_shade_w[2] = occupancy_grid(c, k_shade<2, true>);
-    c->grid_shade_w[3] = occupancy_grid(c, k_shade<3, true>);
-    c->grid_connect = occupancy_grid(c, k_connect<false, 5>);
-    c->grid_connect6 = occupancy_grid(c, k_connect<false, 6>);
-    c->grid_connect_c = occupancy_grid(c, k_connect<true, 5>);
-    c->grid_finalize = occupancy_grid(c, k_finalize);
-    rc = jpbrt_clear_film(c);
-    if (rc == 0) rc = jpbrt_reset_stats(c);
-    if (rc != 0) { g_last_error = c->error; return fail(rc); }
-    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess)
-        return fail(set_error(nullptr, JPBRT_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e)));
+    rc = finish_upload(c, device);
+    if (rc != 0) return rc;
     *out_ctx = c;
     return 0;
 }
@@ -638,6 +654,7 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
     CU_CHECK(c, cudaSetDevice(c->device));
     // Whitted traces a mirror vertex twice (bsdf.h:282): leave room for the ray tree, x2 per mirror bounce, at most x8
     const int tree_growth = (c->opt_integrator == JPBRT_INTEGRATOR_WHITTED && c->has_mirror) ? 1 << std::min(3, std::max(0, c->hs.max_depth - 1)) : 1;
+    c->film_reduced = false;
     int rc = ensure_pool(c, (long long)c->hs.width * c->hs.height * std::max(1, sample_count) * tree_growth);
     if (rc == 0) rc = ensure_sort_buffers(c);
     if (rc != 0) return rc;
@@ -713,9 +730,36 @@ int jpbrt_finalize_film_device(jpbrt_ctx* c, void* out_device, int spp_total) {
     return 0;
 }
 
+// The ONE collective of the path: the raw float32 film sums of all ranks are added onto rank 0 with a single
+// ncclReduce over NVLink, queued on the context's stream right behind the rank's last wavefront.  The other ranks'
+// films are cleared afterwards, so that "sum over ranks = total" keeps holding if more passes follow.
+static int reduce_film(jpbrt_ctx* c, bool grouped = false) {
+    if (c->comm_size <= 1 || c->film_reduced) return 0;
+    NcclApi& n = nccl();
+    {
+        StageTimer t(c, 5);
+        ncclResult_t r = n.Reduce(c->film.ptr, c->film.ptr, c->film.count, ncclFloat32, ncclSum, 0, c->comm, c->stream);
+        if (r != ncclSuccess) return set_error(c, JPBRT_ERR_CUDA, "ncclReduce failed: %s", n.GetErrorString(r));
+    }
+    // (inside an ncclGroup the reduce is only queued at ncclGroupEnd: a memset issued here would overtake it)
+    if (c->comm_rank != 0 && !grouped) CU_CHECK(c, cudaMemsetAsync(c->film.ptr, 0, c->film.count * sizeof(float), c->stream));
+    c->film_reduced = true;
+    return 0;
+}
+
 int jpbrt_read_film(jpbrt_ctx* c, float* rgb, int spp_total, int finalize) {
-    if (!c || !rgb) return set_error(c, JPBRT_ERR_INVALID, "null argument");
+    if (!c) return set_error(c, JPBRT_ERR_INVALID, "null argument");
     CU_CHECK(c, cudaSetDevice(c->device));
+    if (c->comm_size > 1) {  // multi-GPU: the film is complete only on rank 0, after the reduce
+        int rc = reduce_film(c);
+        if (rc != 0) return rc;
+        if (c->comm_rank != 0) {
+            CU_CHECK(c, cudaStreamSynchronize(c->stream));
+            drain_events(c);
+            return 0;
+        }
+    }
+    if (!rgb) return set_error(c, JPBRT_ERR_INVALID, "rgb is null");
     const size_t n = c->film.count;
     if (finalize) {
         if (spp_total <= 0) return set_error(c, JPBRT_ERR_INVALID, "spp_total must be positive");
@@ -759,6 +803,10 @@ int jpbrt_get_stats(jpbrt_ctx* c, jpbrt_stats* out) {
     out->prim_tests = h[ST_PRIM];
     out->shadow_box_tests = h[ST_SH_BOX];
     out->shadow_prim_tests = h[ST_SH_PRIM];
+    out->node_fetches = h[ST_NODE_FETCH];
+    out->prim_fetches = h[ST_PRIM_FETCH];
+    out->shadow_node_fetches = h[ST_SH_NODE_FETCH];
+    out->shadow_prim_fetches = h[ST_SH_PRIM_FETCH];
     out->invalid_contributions = h[ST_INVALID] + h[ST_DROPPED] + h[ST_STACK_DROPPED] + h[ST_NEE_DROPPED];
     out->dropped_rays = h[ST_DROPPED];
     out->stack_overflows = h[ST_STACK_DROPPED];
@@ -770,6 +818,7 @@ int jpbrt_get_stats(jpbrt_ctx* c, jpbrt_stats* out) {
     out->ms_shade = c->ms_stage[2];
     out->ms_connect = c->ms_stage[3];
     out->ms_finalize = c->ms_stage[4];
+    out->ms_reduce = c->ms_stage[5];
     out->n_nodes = c->dsc.n_nodes;
     out->n_prim_slots = c->dsc.n_slots;
     out->scene_bytes = c->hs.Bytes();
@@ -787,6 +836,7 @@ void jpbrt_destroy(jpbrt_ctx* c) {
     for (auto& ev : c->pending_events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto& ev : c->free_events) cudaEventDestroy(ev);
     if (c->wave_graph) cudaGraphExecDestroy(c->wave_graph);
+    if (c->comm) nccl().CommDestroy(c->comm);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (void* p : c->pinned) cudaHostUnregister(p);
     delete c;
@@ -811,6 +861,125 @@ int jpbrt_render_integrator(const jpbrt_scene_desc* desc, int integrator, int sp
     if (rc != 0) g_last_error = c->error;
     if (seconds_out) *seconds_out = std::chrono::duration<double>(t1 - t0).count();
     jpbrt_destroy(c);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Multi-GPU: scene replicated, samples partitioned, one NCCL reduce of the film.
+// ------------------------------------------------------------------------------------------------------------------
+int jpbrt_comm_unique_id(void* id, size_t bytes) {
+    if (!id || bytes < sizeof(ncclUniqueId)) return set_error(nullptr, JPBRT_ERR_INVALID, "id buffer must hold JPBRT_COMM_ID_BYTES bytes");
+    NcclApi& n = nccl();
+    if (!n.Load()) return set_error(nullptr, JPBRT_ERR_UNSUPPORTED, "%s", n.error.c_str());
+    ncclUniqueId uid;
+    ncclResult_t r = n.GetUniqueId(&uid);
+    if (r != ncclSuccess) return set_error(nullptr, JPBRT_ERR_CUDA, "ncclGetUniqueId failed: %s", n.GetErrorString(r));
+    memset(id, 0, bytes);
+    memcpy(id, &uid, sizeof(uid));
+    return 0;
+}
+
+int jpbrt_comm_init(jpbrt_ctx* c, const void* id, size_t bytes, int rank, int nranks) {
+    if (!c || !id || bytes < sizeof(ncclUniqueId)) return set_error(c, JPBRT_ERR_INVALID, "null argument / short id");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return set_error(c, JPBRT_ERR_INVALID, "rank %d outside [0, %d)", rank, nranks);
+    if (c->comm) return set_error(c, JPBRT_ERR_INVALID, "the context already has a communicator");
+    NcclApi& n = nccl();
+    if (!n.Load()) return set_error(c, JPBRT_ERR_UNSUPPORTED, "%s", n.error.c_str());
+    CU_CHECK(c, cudaSetDevice(c->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    ncclResult_t r = n.CommInitRank(&c->comm, nranks, uid, rank);
+    if (r != ncclSuccess) { c->comm = nullptr; return set_error(c, JPBRT_ERR_CUDA, "ncclCommInitRank failed: %s", n.GetErrorString(r)); }
+    c->comm_rank = rank;
+    c->comm_size = nranks;
+    return 0;
+}
+
+int jpbrt_comm_rank(const jpbrt_ctx* c) { return c ? c->comm_rank : 0; }
+int jpbrt_comm_size(const jpbrt_ctx* c) { return c ? c->comm_size : 1; }
+
+int jpbrt_reduce_film(jpbrt_ctx* c) {
+    if (!c) return set_error(nullptr, JPBRT_ERR_INVALID, "ctx is null");
+    CU_CHECK(c, cudaSetDevice(c->device));
+    return reduce_film(c);
+}
+
+void jpbrt_sample_partition(int spp_total, int rank, int nranks, int* begin, int* count) {
+    // as even as possible, contiguous: rank r renders [begin, begin + count) of every pixel
+    const int base = nranks > 0 ? spp_total / nranks : spp_total, rem = nranks > 0 ? spp_total % nranks : 0;
+    if (begin) *begin = rank * base + std::min(rank, rem);
+    if (count) *count = base + (rank < rem ? 1 : 0);
+}
+
+// One process, `ngpus` devices: FIntegrator::Render(scene, sampler, film, numthreads) with GPUs for threads.
+int jpbrt_render_multi(const jpbrt_scene_desc* desc, int integrator, int spp, uint64_t seed, int ngpus, float* rgb, double* seconds_out,
+                       double* reduce_ms_out) {
+    if (spp <= 0 || !rgb || ngpus < 1) return set_error(nullptr, JPBRT_ERR_INVALID, "spp and ngpus must be positive and rgb non-null");
+    if (ngpus == 1) {
+        if (reduce_ms_out) *reduce_ms_out = 0;
+        return jpbrt_render_integrator(desc, integrator, spp, seed, 0, rgb, seconds_out);
+    }
+    if (ngpus > jpbrt_device_count()) return set_error(nullptr, JPBRT_ERR_INVALID, "%d GPUs requested, %d visible", ngpus, jpbrt_device_count());
+    NcclApi& n = nccl();
+    if (!n.Load()) return set_error(nullptr, JPBRT_ERR_UNSUPPORTED, "%s", n.error.c_str());
+    // flatten (and build the BVH) once; every device gets a copy
+    HostScene hs;
+    std::string err;
+    int rc = FlattenScene(desc, &hs, &err);
+    if (rc != 0) return set_error(nullptr, rc, "%s", err.c_str());
+    std::vector<jpbrt_ctx*> ctx(ngpus, nullptr);
+    auto cleanup = [&]() { for (jpbrt_ctx* c : ctx) jpbrt_destroy(c); };
+    for (int d = 0; d < ngpus; ++d) {
+        jpbrt_ctx* c = new jpbrt_ctx();
+        c->hs = hs;
+        rc = finish_upload(c, d);
+        if (rc != 0) { cleanup(); return rc; }
+        ctx[d] = c;
+        if ((rc = jpbrt_set_option(c, "integrator", integrator)) != 0) { g_last_error = c->error; cleanup(); return rc; }
+    }
+    std::vector<int> devs(ngpus);
+    std::vector<ncclComm_t> comms(ngpus);
+    for (int d = 0; d < ngpus; ++d) devs[d] = d;
+    ncclResult_t r = n.CommInitAll(comms.data(), ngpus, devs.data());
+    if (r != ncclSuccess) { cleanup(); return set_error(nullptr, JPBRT_ERR_CUDA, "ncclCommInitAll failed: %s", n.GetErrorString(r)); }
+    for (int d = 0; d < ngpus; ++d) { ctx[d]->comm = comms[d]; ctx[d]->comm_rank = d; ctx[d]->comm_size = ngpus; }
+    auto t0 = std::chrono::steady_clock::now();
+    for (int d = 0; d < ngpus && rc == 0; ++d) {  // asynchronous: every device works on its own stream
+        int begin, count;
+        jpbrt_sample_partition(spp, d, ngpus, &begin, &count);
+        if (count > 0) rc = jpbrt_render_pass(ctx[d], begin, count, seed);
+        if (rc != 0) g_last_error = ctx[d]->error;
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (rc == 0) {
+        cudaSetDevice(0);
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, ctx[0]->stream);
+        n.GroupStart();  // one thread drives several communicators: the calls must be grouped
+        for (int d = 0; d < ngpus && rc == 0; ++d) {
+            cudaSetDevice(d);
+            rc = reduce_film(ctx[d], true);
+            if (rc != 0) g_last_error = ctx[d]->error;
+        }
+        n.GroupEnd();
+        cudaSetDevice(0);
+        cudaEventRecord(e1, ctx[0]->stream);
+    }
+    if (rc == 0) {
+        for (int d = 1; d < ngpus; ++d) jpbrt_synchronize(ctx[d]);
+        rc = jpbrt_read_film(ctx[0], rgb, spp, 1);
+        if (rc != 0) g_last_error = ctx[0]->error;
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds_out) *seconds_out = std::chrono::duration<double>(t1 - t0).count();
+    if (reduce_ms_out) {
+        float ms = 0;
+        if (rc == 0 && e0 && e1) { cudaSetDevice(0); cudaEventElapsedTime(&ms, e0, e1); }
+        *reduce_ms_out = ms;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cleanup();
     return rc;
 }
 
@@ -880,9 +1049,9 @@ struct UnitRayIO {
 };
 
 __global__ void __launch_bounds__(kBlock) k_unit_scene_intersect(DevScene sc, int n, int* work, const float* rays8, int* prim, float* t, float* pos3, float* nrm3) {
-    unsigned a = 0, b = 0;
+    TravCounts cnt;
     UnitRayIO io{rays8, prim, t, pos3, nrm3, &sc};
-    traverse_queue<false, false>(sc, n, work, io, 8, 8, a, b);
+    traverse_queue<false, false>(sc, n, work, io, 8, 8, cnt);
 }
 
 struct UnitOccIO {
@@ -903,9 +1072,9 @@ struct UnitOccIO {
 };
 
 __global__ void __launch_bounds__(kBlock) k_unit_scene_occluded(DevScene sc, int n, int* work, const float* pos3, const float* target3, int* occ) {
-    unsigned a = 0, b = 0;
+    TravCounts cnt;
     UnitOccIO io{pos3, target3, occ};
-    traverse_queue<true, false>(sc, n, work, io, 8, 8, a, b);
+    traverse_queue<true, false>(sc, n, work, io, 8, 8, cnt);
 }
 
 __global__ void k_unit_bsdf(const Float4* mat, int n, const float* nrm3, const float* wo3, const float* wi3, const float* u2,

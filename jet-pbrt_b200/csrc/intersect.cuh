@@ -141,14 +141,17 @@ constexpr int kTraversalStack = 64;     // deepest node stack a ray can use (ent
 constexpr int kTravDone = 0x7fffffff;  // `cur` value of a lane whose stack is empty (or that found an any-hit)
 constexpr int kTravBlock = 256;        // threads per block of every kernel that traverses (wavefront.cuh: kBlock)
 
-// The first JPB_SMEM_STACK entries of every lane's node stack live in SHARED memory, laid out [entry][thread]: lane l of a
-// warp always hits bank l whatever its stack depth, so a push or pop is ONE conflict-free wavefront even when the 32 lanes
-// sit at 32 different depths (the local-memory stack of round 1 cost one L1 wavefront per distinct depth, was a quarter of
-// the kernel's load/store instructions and ran its push / pop branches at 5.5 / 1.9 of 32 lanes: profiles/
-// r01_lane_profile_bunny_v8.txt).  Deeper entries spill to a local array, which only trees deeper than the shared part
-// ever touch.  0 = the whole stack in local memory (A/B builds).
+// Where the node stack lives.  Round 1's ncu profile showed the local-memory stack as a quarter of the traversal kernels'
+// load/store instructions, with its push / pop branches running at 5.5 / 1.9 of 32 lanes, so round 2 built the obvious
+// alternative: the first JPB_SMEM_STACK entries of every lane's stack in SHARED memory, laid out [entry][thread] (lane l
+// always hits bank l: one conflict-free wavefront per push or pop whatever the 32 depths are), deeper entries spilling to
+// the local array.  Measured on B200 (profiles/ab/r02_ab_stack.log, 48 spp): shared depth 8 / 12 / 16 is 4-5 % SLOWER than
+// the all-local stack on every scene (bunny k_extend 13.09 vs 12.52 ms, k_connect 12.25 vs 11.84; Cornell 11.16 vs 10.49):
+// the local stack's lines live in L1 anyway (interleaved per lane, so a converged push is one wavefront too), while the
+// shared variant pays two extra address instructions per access and takes 48-96 KB per SM away from L1.  Default: 0 = the
+// whole stack in local memory; the shared variant stays buildable for A/B runs (-DJPB_SMEM_STACK=8).
 #ifndef JPB_SMEM_STACK
-#define JPB_SMEM_STACK 8
+#define JPB_SMEM_STACK 0
 #endif
 constexpr int kSmemStack = JPB_SMEM_STACK;
 static_assert(kSmemStack >= 0 && kSmemStack < kTraversalStack, "JPB_SMEM_STACK out of range");
@@ -210,14 +213,26 @@ __device__ __forceinline__ bool trav_done(const Trav& t) { return t.cur == kTrav
 
 // One inner node: fetch 64 bytes, test both child boxes, descend into the nearer hit child.  Written without
 // divergent branches: the push (both children hit) and the pop (none hit) are short predicated sequences.
+// Counters of the COUNT kernel variants (bench.py's roofline): per-lane tests as SURVEY.md 8(d) accounts them, and
+// DISTINCT records per warp step -- lanes of a warp that sit on the same node (or primitive) share one fetch, so the
+// distinct counts are what the memory system actually has to deliver.
+struct TravCounts {
+    unsigned box = 0, prim = 0;            // box tests (2 per node step) and primitive tests, per lane
+    unsigned node_fetch = 0, prim_fetch = 0;  // distinct nodes / primitive records fetched per warp step (counted on one lane)
+};
+
 template <bool COUNT>
-__device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, const TravStack& stk, unsigned& n_box) {
+__device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, const TravStack& stk, TravCounts& cnt, unsigned step_mask) {
     const float widen = 1.0000004f;  // 1 + 2*gamma(3): pbrt's conservative slab bound
     const Float4* np = sc.nodes + (size_t)t.cur * kNodeStride;
     float4 n0, n1, n2, n3;
     ldg8<kWideNodeLoads>(np, n0, n1);
     ldg8<kWideNodeLoads>(np + 2, n2, n3);
-    if (COUNT) n_box += 2;
+    if (COUNT) {
+        cnt.box += 2;
+        const unsigned same = __match_any_sync(step_mask, t.cur);  // the lanes of this step that sit on the same node
+        if ((threadIdx.x & 31) == __ffs(same) - 1) cnt.node_fetch += 1;
+    }
     // left box: min = (n0.x n0.y n0.z), max = (n0.w n1.x n1.y)
     float a0 = __fmaf_rn(n0.x, t.inv.x, t.oi.x), a1 = __fmaf_rn(n0.w, t.inv.x, t.oi.x);
     float b0 = __fmaf_rn(n0.y, t.inv.y, t.oi.y), b1 = __fmaf_rn(n1.x, t.inv.y, t.oi.y);
@@ -243,13 +258,30 @@ __device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, cons
 
 // One leaf: test its (<= 4) primitives, then pop.
 template <bool ANY_HIT, bool COUNT>
-__device__ __forceinline__ void trav_leaf_step(const DevScene& sc, Trav& t, const TravStack& stk, unsigned& n_prim) {
+__device__ __forceinline__ void trav_leaf_step(const DevScene& sc, Trav& t, const TravStack& stk, TravCounts& cnt, unsigned leaf_mask) {
     const int bits = ~t.cur;
     const int first = bits >> kLeafCountBits;
-    const int cnt = bits & ((1 << kLeafCountBits) - 1);
-    for (int k = 0; k < cnt; ++k) {
+    const int n = bits & ((1 << kLeafCountBits) - 1);
+    if (COUNT) {
+        // the counting variant keeps the lanes of the phase together (no early return) so that it can count, per
+        // primitive round, how many DISTINCT records the warp fetches
+        bool found = false;
+        for (int k = 0; k < kMaxLeafPrims; ++k) {
+            const bool active = k < n && !(ANY_HIT && found);
+            const unsigned m = __ballot_sync(leaf_mask, active);
+            if (active) {
+                const int s = first + k;
+                cnt.prim += 1;
+                const unsigned same = __match_any_sync(m, s);
+                if ((threadIdx.x & 31) == __ffs(same) - 1) cnt.prim_fetch += 1;
+                if (intersect_slot(sc.slots + (size_t)s * kSlotStride, sc.slot_nrm + s, t.o, t.d, t.tmin, t.tmax)) { t.hit = s; found = true; }
+            }
+        }
+        t.cur = (ANY_HIT && found) ? kTravDone : stk.pop(t.sp);
+        return;
+    }
+    for (int k = 0; k < n; ++k) {
         const int s = first + k;
-        if (COUNT) n_prim += 1;
         if (intersect_slot(sc.slots + (size_t)s * kSlotStride, sc.slot_nrm + s, t.o, t.d, t.tmin, t.tmax)) {
             t.hit = s;
             if (ANY_HIT) { t.cur = kTravDone; return; }
@@ -273,7 +305,7 @@ __device__ __forceinline__ void trav_leaf_step(const DevScene& sc, Trav& t, cons
 #endif
 template <bool ANY_HIT, bool COUNT, typename IO>
 __device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* work, const IO& io, int refill_min, int min_inner,
-                                               unsigned& n_box, unsigned& n_prim, unsigned long long* dropped = nullptr) {
+                                               TravCounts& cnt, unsigned long long* dropped = nullptr) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     __shared__ int s_stack[(kSmemStack > 0 ? kSmemStack : 1) * kTravBlock];
@@ -318,10 +350,13 @@ __device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* w
             if (m_inner == 0) break;
             if (__popc(m_inner) < min_inner && __any_sync(full, trav_at_leaf(t))) break;
 #pragma unroll
-            for (int u = 0; u < JPB_NODE_UNROLL; ++u)
-                if (trav_at_inner(t)) trav_node_step<COUNT>(sc, t, stk, n_box);
+            for (int u = 0; u < JPB_NODE_UNROLL; ++u) {
+                const unsigned step_mask = COUNT ? (u == 0 ? m_inner : __ballot_sync(full, trav_at_inner(t))) : 0u;
+                if (trav_at_inner(t)) trav_node_step<COUNT>(sc, t, stk, cnt, step_mask);
+            }
         }
-        if (trav_at_leaf(t)) trav_leaf_step<ANY_HIT, COUNT>(sc, t, stk, n_prim);
+        const unsigned leaf_mask = COUNT ? __ballot_sync(full, trav_at_leaf(t)) : 0u;
+        if (trav_at_leaf(t)) trav_leaf_step<ANY_HIT, COUNT>(sc, t, stk, cnt, leaf_mask);
         if (idx >= 0 && trav_done(t)) {
             io.store(idx, t.hit, t.tmax);
             idx = -1;

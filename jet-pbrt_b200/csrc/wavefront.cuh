@@ -45,6 +45,7 @@ enum {
     ST_SAMPLES = 0, ST_EXT_RAYS, ST_SHADOW_RAYS, ST_VERTICES, ST_BOX, ST_PRIM, ST_SH_BOX, ST_SH_PRIM, ST_INVALID, ST_DROPPED,
     ST_STACK_DROPPED,  // far children lost to a full traversal stack (intersect.cuh: kTraversalStack)
     ST_NEE_DROPPED,    // light samples that found no shadow slot (pool smaller than vertices x lights)
+    ST_NODE_FETCH, ST_PRIM_FETCH, ST_SH_NODE_FETCH, ST_SH_PRIM_FETCH,  // COUNT variants: distinct records per warp step
     ST_COUNT
 };
 
@@ -200,13 +201,15 @@ __global__ void __launch_bounds__(kBlock, MINB) k_extend(const __grid_constant__
     const int n = min(p.counters[CNT_RAYS * p.counter_stride + it], p.queue_capacity);
     int* work = p.counters + CNT_W_EXTEND * p.counter_stride + it;
     const int buf = it & 1;
-    unsigned nb = 0, np = 0;
+    TravCounts cnt;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.stats + ST_EXT_RAYS, (unsigned long long)n);
     ExtendIO<PERM> io{p.ray_o[buf], p.ray_d[buf], p.hit, p.perm};
-    traverse_queue<false, COUNT>(p.sc, n, work, io, p.refill_min, p.min_inner, nb, np, p.stats + ST_STACK_DROPPED);
+    traverse_queue<false, COUNT>(p.sc, n, work, io, p.refill_min, p.min_inner, cnt, p.stats + ST_STACK_DROPPED);
     if (COUNT) {
-        warp_stat_add(p.stats + ST_BOX, nb);
-        warp_stat_add(p.stats + ST_PRIM, np);
+        warp_stat_add(p.stats + ST_BOX, cnt.box);
+        warp_stat_add(p.stats + ST_PRIM, cnt.prim);
+        warp_stat_add(p.stats + ST_NODE_FETCH, cnt.node_fetch);
+        warp_stat_add(p.stats + ST_PRIM_FETCH, cnt.prim_fetch);
     }
 }
 
@@ -245,13 +248,16 @@ __global__ void __launch_bounds__(kBlock, MINB) k_connect(const __grid_constant_
     const long long slots = (long long)nee_vertex_count(p, it) * p.sc.n_nee_lights;
     const int n = (int)(slots < p.shadow_capacity ? slots : p.shadow_capacity);
     int* work = p.counters + CNT_W_CONNECT * p.counter_stride + it;
-    unsigned nb = 0, np = 0, traced = 0;
+    TravCounts cnt;
+    unsigned traced = 0;
     ConnectIO io{&p, &traced};
-    traverse_queue<true, COUNT>(p.sc, n, work, io, p.refill_min, p.min_inner, nb, np, p.stats + ST_STACK_DROPPED);
+    traverse_queue<true, COUNT>(p.sc, n, work, io, p.refill_min, p.min_inner, cnt, p.stats + ST_STACK_DROPPED);
     warp_stat_add(p.stats + ST_SHADOW_RAYS, traced);
     if (COUNT) {
-        warp_stat_add(p.stats + ST_SH_BOX, nb);
-        warp_stat_add(p.stats + ST_SH_PRIM, np);
+        warp_stat_add(p.stats + ST_SH_BOX, cnt.box);
+        warp_stat_add(p.stats + ST_SH_PRIM, cnt.prim);
+        warp_stat_add(p.stats + ST_SH_NODE_FETCH, cnt.node_fetch);
+        warp_stat_add(p.stats + ST_SH_PRIM_FETCH, cnt.prim_fetch);
     }
 }
 

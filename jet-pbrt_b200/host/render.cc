@@ -47,4 +47,28 @@ bool Integrator::Render(Scene* scene, int spp, Film* film, int device, uint64_t 
     return true;
 }
 
+bool Integrator::RenderMultiGpu(Scene* scene, int spp, Film* film, int ngpus, uint64_t seed) const {
+    if (ngpus <= 1) return Render(scene, spp, film, 0, seed);
+    if (maxDepth_ >= 0) scene->SetMaxDepth(maxDepth_);
+    const jpbrt_scene_desc* desc = scene->Desc();
+    if (desc->camera.width != film->Width() || desc->camera.height != film->Height()) {
+        fprintf(stdout, "film resolution does not match the camera's\n");
+        return false;
+    }
+    fprintf(stdout, "start rendering ...\n");  // integrator.cc:44
+    std::vector<float> tmp((size_t)film->Width() * film->Height() * 3);
+    double sec = 0, reduce_ms = 0;
+    int rc = jpbrt_render_multi(desc, kind_, spp, seed, ngpus, tmp.data(), &sec, &reduce_ms);
+    if (rc != 0) {
+        fprintf(stdout, "render failed: %s\n", jpbrt_last_error(nullptr));
+        return false;
+    }
+    float* dst = film->Data();
+    for (size_t i = 0; i < tmp.size(); ++i) dst[i] += tmp[i];  // FFilm::AddColor, film.h:64-68
+    fprintf(stdout, "finish rendering ...\n");                                   // integrator.cc:78
+    fprintf(stdout, "FIntegrator::Render used %f seconds.\n", (float)sec);        // integrator.cc:79
+    fprintf(stdout, "  (%d GPUs, samples partitioned, NCCL film reduce %.3f ms)\n", ngpus, reduce_ms);
+    return true;
+}
+
 }  // namespace jetpbrt

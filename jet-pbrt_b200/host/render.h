@@ -6,6 +6,7 @@
 //   FPathIntegratorIteration integrator(5)                             jetpbrt::PathIntegratorIteration integrator(5)
 //   FDebugIntegrator / FWhittedIntegrator(5) / FPathIntegratorRecursive(5)   jetpbrt::DebugIntegrator / WhittedIntegrator(5) / ...
 //   integrator.Render(scene, sampler, &film, 16)                       integrator.Render(scene, spp, &film, device)
+//     (numthreads = 16 host threads, integrator.cc:53-74)                integrator.Render(scene, spp, &film, ngpus): GPUs for threads
 //   film.SaveAsImage(name, EImageType::BMP)                            film.SaveAsImage(name, EImageType::BMP)
 #pragma once
 
@@ -42,6 +43,10 @@ public:
     // Clamp01(mean radiance) onto the film (film.h:64-68).  Returns false and prints the C-ABI
     // error on failure (the reference's Render returns void and cannot fail).
     bool Render(Scene* scene, int spp, Film* film, int device = 0, uint64_t seed = 1234) const;
+    // The same with `ngpus` devices (0 .. ngpus-1) of this process where the reference has `numthreads` host threads
+    // (integrator.h:32): the samples of every pixel are partitioned across the devices, the partial films are summed
+    // with one NCCL reduce (jpbrt_render_multi).
+    bool RenderMultiGpu(Scene* scene, int spp, Film* film, int ngpus, uint64_t seed = 1234) const;
 
 protected:
     Integrator(int kind, int maxDepth) : kind_(kind), maxDepth_(maxDepth) {}
