@@ -1,24 +1,31 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200 wavefront path tracer (BASELINE.json metric).
+"""bench.py -- headline benchmark of the B200 wavefront path tracer (BASELINE.json metric: Msamples/s and Mrays/s at
+1/2/4/8 B200 vs the host-CPU reference; image RMSE vs CPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config bunny|cornell|glossy|large|cornell4k]
-    python bench.py --impl reference ...        # the reference's own CPU renderer, same metric/config
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config bunny|cornell|glossy|large|cornell4k] [--quick]
+    python bench.py --impl reference ...        # the reference's own CPU renderer, same metric / config
 
-One "step" = one complete render of the workload: every pixel x spp samples through the hot path
-(generate, extend, shade, connect, accumulate) + the film finalize; with N > 1 every rank renders its
-own `spp` sample indices of every pixel (weak scaling, scene replicated) and the raw float32 films are
-summed with ONE NCCL reduce onto rank 0 inside the step.
+One "step" = one complete render of the workload: every pixel x spp samples through the hot path (generate, extend,
+shade, connect, accumulate) + the film finalize.  With N > 1 (one process per GPU, torchrun) the scene is replicated,
+the SAMPLE indices are partitioned, and the raw float32 films are summed onto rank 0 by ONE ncclReduce issued inside
+the library (jpbrt_comm_init / jpbrt_read_film) -- torch.distributed only carries the rendezvous and the barriers.
 
-  value : whole-job Msamples/s over the K timed steps, scene already resident in HBM, CUDA-event time,
-          max over ranks.
-  e2e   : the same metric through the C-ABI calls a caller of FIntegrator::Render would make, with HOST
-          buffers: every step re-uploads the flattened scene from pinned host memory, renders, reduces,
-          finalizes and reads the film back to pinned host memory (wall clock with device sync).
-  roofline : the closest-hit traversal kernel (k_extend): algorithmic bytes (32 B per box test + 48 B per
-          primitive test + 48 B ray/hit record) over its CUDA-event time, against the
-          measured HBM copy bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline : the UNMODIFIED reference (oracle/_ref, else the pinned restatement) timed on this host's
-          cores on a bounded sample of the same workload.
+The ONE JSON line rank 0 prints:
+  value / ms_per_step : headline config (BASELINE configs[1], the bunny scene, 1024^2 x 50 spp PER GPU: weak scaling),
+          scene resident in HBM, CUDA events on the library's stream, max over ranks.
+  e2e   : the same through the calls a caller of FIntegrator::Render makes, with HOST buffers: every step re-uploads the
+          flattened scene from pinned host memory, renders, reduces, finalizes, reads the film back (wall clock).
+  strong: STRONG scaling -- the headline scene at 50 spp TOTAL and the 3840x2160 Cornell box at 4096 spp TOTAL
+          (BASELINE configs[4]) split over the N ranks, with the film reduce timed on its own.
+  configs (N = 1): every other BASELINE config (cornell, large at 64 spp, glossy at 64 spp) with value / e2e / roofline /
+          cpu_baseline / image error, measured by the same code.
+  roofline : the closest-hit traversal kernel (k_extend) against ceilings MEASURED in this run on this GPU by
+          jet-pbrt_b200/build/peaks_l2 (scripts/peaks_l2.cu): bytes of the DISTINCT node / primitive records each warp step
+          fetches (+ ray in, hit out) per second, over the gather bandwidth of 64-byte records at the scene's working-set
+          size.  The per-lane SURVEY 8(d) figure, the HBM stream peak (MEASURED_PEAKS.json), the DRAM traffic and the
+          issue-slot utilisation from this build's ncu capture (profiles/r02_ncu_constants.json) are quoted beside it.
+  cpu_baseline : the UNMODIFIED reference (oracle/_ref) on this host's cores, on a bounded sample of the same workload.
+  reduce_check (N > 1): the NCCL-reduced film against all N x spp samples rendered by rank 0 alone.
 """
 from __future__ import annotations
 
@@ -36,23 +43,24 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 CONFIGS = {
-    # name: (scene, scale, width, height, spp per GPU, BASELINE.json config it is)
+    # name: (scene, scale, width, height, spp, BASELINE.json config it is)
     "bunny": ("bunny", 1.0, 1024, 1024, 50, "configs[1] bunny scene: 4 x 5,040-triangle mesh stand-in, matte/plastic/metal/glass, depth 5"),
     "cornell": ("cornell", 1.0, 1024, 1024, 50, "configs[0] Cornell box as in main.cc, depth 5"),
-    "large": ("large", 1.0, 1024, 1024, 16, "configs[2] synthetic 5M-triangle scene, depth 8"),
-    "glossy": ("glossy", 1.0, 1024, 1024, 16, "configs[3] glossy room, 16 area lights, depth 16"),
-    "cornell4k": ("cornell", 1.0, 3840, 2160, 64, "configs[4] Cornell box 3840x2160 (spp reduced per step; throughput is spp-independent)"),
+    "large": ("large", 1.0, 1024, 1024, 64, "configs[2] synthetic 5M-triangle scene, depth 8"),
+    "glossy": ("glossy", 1.0, 1024, 1024, 64, "configs[3] glossy room, 16 area lights, depth 16"),
+    "cornell4k": ("cornell", 1.0, 3840, 2160, 4096, "configs[4] Cornell box 3840x2160, 4096 spp"),
 }
+SEED = 1234
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of k_extend per ray, from the committed `ncu --set full` captures
-# (profiles/r01_ncu_bunny_v7.md launch #0: 273.08 + 42.40 MB for 8,388,608 rays; profiles/r01_ncu_cornell_v2.md
-# launch #0: 268.52 + 52.58 MB for 8,388,608 rays; profiles/r01_ncu_large_v7.md launch #0: 760 + 44.5 MB for 4,194,304
-# rays).  Where the scene is cache-resident DRAM only sees the 32-byte ray read and the 8-byte hit write.
-NCU_EXTEND_DRAM_BYTES_PER_RAY = {"bunny": 37.61, "cornell": 38.28, "large": 191.8}
+def workload_config(name, cfg, scene_d):
+    """The workload, described identically by both arms (the driver compares the two `config` objects)."""
+    scene_name, scale, w, h, spp, desc = cfg
+    return {"workload": f"{name}: {desc}", "width": w, "height": h, "spp": spp, "max_depth": scene_d.max_depth,
+            "n_primitives": scene_d.n_primitives, "n_lights": scene_d.n_lights, "seed": SEED}
 
 
-def peaks():
+def measured_hbm_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         try:
@@ -60,6 +68,32 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_peaks(device):
+    """The gather / L2 / issue ceilings of THIS GPU (scripts/peaks_l2.cu), measured before the benchmark's own work."""
+    exe = ROOT / "jet-pbrt_b200" / "build" / "peaks_l2"
+    if not exe.exists():
+        return None
+    try:
+        r = subprocess.run([str(exe), str(device)], capture_output=True, text=True, timeout=120)
+        return json.loads(r.stdout) if r.returncode == 0 else None
+    except Exception:
+        return None
+
+
+def gather_peak_at(peaks, working_set_bytes):
+    """Divergent 64-byte-record gather bandwidth at a working-set size: log-interpolated between the measured sizes."""
+    import math
+
+    pts = [(g["working_set_bytes"], g["divergent_gbs"]) for g in peaks["gather64"]]
+    if working_set_bytes <= pts[0][0]:
+        return pts[0][1]
+    for (a, fa), (b, fb) in zip(pts, pts[1:]):
+        if working_set_bytes <= b:
+            t = (math.log(working_set_bytes) - math.log(a)) / (math.log(b) - math.log(a))
+            return fa + t * (fb - fa)
+    return pts[-1][1]
 
 
 class ClockSampler:
@@ -107,44 +141,439 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def run_reference(args, cfg, emit):
-    """--impl reference: the reference's own CPU implementation of the path (parallel.cc thread pool)."""
+# =====================================================================================================================
+# reference arm: the reference's own CPU implementation of the path (FIntegrator::Render + parallel.cc thread pool)
+# =====================================================================================================================
+def load_scene_module():
+    """jet-pbrt_b200/scene_desc.py + libjetpbrt_host.so: the scene DESCRIPTION only -- no CUDA library in this process."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("jpbrt_scene_desc", ROOT / "jet-pbrt_b200" / "scene_desc.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["jpbrt_scene_desc"] = mod
+    spec.loader.exec_module(mod)
+    mod.load_host_lib()
+    return mod
+
+
+def run_reference(args, name, cfg, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import __graft_entry__ as ge
 
-    pkg, orc = ge.load_package(), ge.load_oracle()
+    sd = load_scene_module()
+    orc = ge.load_oracle()
     scene_name, scale, w, h, spp, desc = cfg
     kind = "reference" if orc.have("ref") else "port"
     o = orc.Oracle("ref" if kind == "reference" else "port")
     threads = os.cpu_count() or 1
-    sc = pkg.HostScene.builtin(scene_name, w, h, scale)
+    sc = sd.HostScene.builtin(scene_name, w, h, scale)
     t0 = time.perf_counter()
     s = o.scene(sc)
     build_s = time.perf_counter() - t0
-    # bounded sample: 1 spp probe, then an spp that keeps one step near 6 s
+    # bounded sample: the step renders as many of the workload's spp as keep the whole K + W run near 3 minutes
     _, probe = s.render(1, threads)
-    step_spp = max(1, min(spp, int(6.0 / max(probe, 1e-3))))
-    for _ in range(max(0, min(args.warmup, 1))):
+    n_runs = args.steps + min(args.warmup, 1)
+    step_spp = max(1, min(spp, int(min(180.0, 30.0 * n_runs) / n_runs / max(probe, 1e-3))))
+    for _ in range(min(args.warmup, 1)):
         s.render(step_spp, threads)
     times = []
     for _ in range(args.steps):
         _, sec = s.render(step_spp, threads)
         times.append(sec)
     total = sum(times)
-    samples = w * h * step_spp * args.steps
-    value = samples / total / 1e6
+    value = w * h * step_spp * args.steps / total / 1e6
     line = {"impl": "reference", "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config}: {desc}", "width": w, "height": h, "spp_per_step": step_spp, "max_depth": sc.d.max_depth,
-                       "n_primitives": sc.d.n_primitives, "n_lights": sc.d.n_lights},
+            "config": workload_config(name, cfg, sc.d),
+            "sample_spp_per_step": step_spp,
             "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": kind,
-                             "sample": f"{w}x{h} x {step_spp} spp per step, FIntegrator::Render with numthreads={threads}; scene build {build_s:.2f}s excluded"},
+                             "sample": f"{w}x{h} x {step_spp} of the workload's {spp} spp per step (the metric is per sample), unmodified FIntegrator::Render with "
+                                       f"numthreads={threads}; scene build {build_s:.2f}s excluded; no CUDA library loaded in this process"},
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+    return 0
+
+
+# =====================================================================================================================
+# B200 arm
+# =====================================================================================================================
+class Bench:
+    def __init__(self, args):
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        import __graft_entry__ as ge
+
+        self.np, self.torch, self.dist, self.ge = np, torch, dist, ge
+        self.args = args
+        self.pkg = ge.load_package()
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available() or self.pkg.device_count() <= self.local:
+            raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device(f"cuda:{self.local}")
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.peaks = None
+
+    # ---- plumbing -------------------------------------------------------------------------------------------------
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def open(self, name, cfg_override=None):
+        """Scene + context (+ the library's own NCCL communicator when N > 1)."""
+        scene_name, scale, w, h, spp, desc = cfg_override or CONFIGS[name]
+        sc = self.pkg.HostScene.builtin(scene_name, w, h, scale)
+        t0 = time.perf_counter()
+        ctx = self.pkg.Context(sc, device=self.local)
+        upload_s = time.perf_counter() - t0
+        if self.args.paths_in_flight:
+            ctx.set_option("paths_in_flight", self.args.paths_in_flight)
+        if self.world > 1:
+            buf = self.torch.zeros(self.pkg.COMM_ID_BYTES, dtype=self.torch.uint8, device=self.dev)
+            if self.rank == 0:
+                uid = self.pkg.comm_unique_id()
+                buf.copy_(self.torch.frombuffer(bytearray(uid), dtype=self.torch.uint8))
+            self.dist.broadcast(buf, 0)
+            ctx.comm_init(bytes(buf.cpu().numpy().tobytes()), self.rank, self.world)
+        return sc, ctx, upload_s
+
+    # ---- one configuration --------------------------------------------------------------------------------------------
+    def measure(self, name, mode, steps, warmup, spp_override=0, full=True, sample_clocks=False, image_error=True, cpu=True, spp_warm=0):
+        """mode "weak": every rank renders the config's spp (total = N x spp); "strong": the config's spp split over the ranks."""
+        torch, np, pkg = self.torch, self.np, self.pkg
+        cfg = list(CONFIGS[name])
+        if spp_override:
+            cfg[4] = spp_override
+        scene_name, scale, w, h, spp, desc = cfg
+        sc, ctx, upload_s = self.open(name, cfg)
+        world, rank = self.world, self.rank
+        if mode == "weak":
+            begin, count, spp_total = rank * spp, spp, spp * world
+        else:
+            begin, count = pkg.sample_partition(spp, rank, world)
+            spp_total = spp
+        stream = torch.cuda.ExternalStream(ctx.stream(), device=self.local)
+        nfloats = ctx.film_num_floats()
+        host_film = torch.empty(nfloats, dtype=torch.float32, pin_memory=True) if rank == 0 else None
+        host_ptr = host_film.data_ptr() if rank == 0 else None
+        out = {}
+
+        def step_resident(n=count, b=begin):
+            ctx.clear_film()
+            if n > 0:
+                ctx.render_pass(b, n, SEED)
+            ctx.reduce_film()                      # ncclReduce onto rank 0 on the library's stream (no-op at N = 1)
+            if rank == 0:
+                ctx.finalize_film_device(ctx.film_device_ptr(), spp_total)
+
+        with torch.cuda.stream(stream):
+            # ---- counting pass (outside every timed region): tests and DISTINCT fetches per ray on OUR BVH ----
+            ctx.set_option("count_traversal", 1)
+            ctx.clear_film()
+            ctx.render_pass(begin, max(1, min(count, 4)), SEED)
+            ctx.synchronize()
+            cst = ctx.stats()
+            ctx.set_option("count_traversal", 0)
+            ctx.reset_stats()
+            for _ in range(warmup):
+                step_resident(spp_warm or count)
+            self.barrier()
+
+            # ---- e2e: host buffers in, host film out, every step (wall clock around the C-ABI calls) ----
+            e2e = None
+            if full:
+                def step_e2e():
+                    nbytes = ctx.reupload_scene()
+                    ctx.clear_film()
+                    if count > 0:
+                        ctx.render_pass(begin, count, SEED)
+                    ctx.read_film_root(spp_total, host_ptr)   # (reduce +) finalize + HBM -> pinned host, synchronises
+                    return nbytes
+
+                for _ in range(max(3, warmup)):
+                    h2d = step_e2e()
+                self.barrier()
+                import gc
+                gc.collect()
+                gc.disable()
+                t0 = time.perf_counter()
+                each = []
+                for _ in range(steps):
+                    ts = time.perf_counter()
+                    step_e2e()
+                    each.append(1e3 * (time.perf_counter() - ts))
+                self.barrier()
+                e2e_s = self.max_over_ranks(time.perf_counter() - t0)
+                gc.enable()
+                e2e = {"value": w * h * spp_total * steps / e2e_s / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(nfloats * 4), "ms_per_step": 1e3 * e2e_s / steps, "ms_each_step": [round(x, 2) for x in each],
+                       "what": "jpbrt_reupload_scene (pinned host -> HBM) + jpbrt_render_pass + jpbrt_read_film (ncclReduce at N > 1, finalize, HBM -> pinned host)"}
+                out["film_mean"] = float(host_film.mean()) if rank == 0 else 0.0
+
+            # ---- value: scene resident, CUDA events on the library's stream, per-stage events inside ----
+            ctx.set_option("stage_timing", 1)  # per-launch CUDA events => the eager launch path (the graph path is what e2e ran)
+            step_resident(spp_warm or count)
+            self.barrier()
+            clocks = ClockSampler(self.local)
+            if sample_clocks and rank == 0 and not self.args.no_clocks:
+                clocks.start()
+                clocks.wait_first_sample(5.0)  # nvidia-smi's start-up stays OUT of the timed region
+            self.barrier()
+            step_resident(spp_warm or count)
+            self.barrier()
+            ctx.clear_film()
+            ctx.reset_stats()
+            clocks.rows.clear()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            # hold the stream ~100 ms (untimed, before ev0) while the host queues the first steps: a stalled driver call
+            # (seen on these boxes while nvidia-smi polls) cannot leave the GPU idle inside the timed region
+            torch.cuda._sleep(int(0.1 * 1.9e9))
+            ev0.record(stream)
+            for _ in range(steps):
+                step_resident()
+            ev1.record(stream)
+            self.barrier()
+            ms_total = self.max_over_ranks(ev0.elapsed_time(ev1))
+            clock_info = clocks.stop() if (sample_clocks and rank == 0 and not self.args.no_clocks) else None
+            st = ctx.stats()
+            ctx.set_option("stage_timing", 0)
+
+            # ---- the film reduce on its own: every rank idle, then the collective alone (device time on rank 0) ----
+            reduce_alone_ms = None
+            if world > 1:
+                times = []
+                for _ in range(5):
+                    ctx.clear_film()
+                    ctx.render_pass(begin, 1, SEED)   # marks the film "not reduced"; its time is outside the events
+                    self.barrier()
+                    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    r0.record(stream)
+                    ctx.reduce_film()
+                    r1.record(stream)
+                    self.barrier()
+                    times.append(r0.elapsed_time(r1))
+                reduce_alone_ms = self.max_over_ranks(min(times[1:]))
+
+        ms_per_step = ms_total / steps
+        ext_rays, sh_rays = st["extension_rays"], st["shadow_rays"]
+        out.update({
+            "value": w * h * spp_total / (ms_per_step * 1e-3) / 1e6, "unit": "Msamples/s", "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
+            "mode": mode, "spp_total": spp_total, "spp_this_rank": count,
+            "mrays_per_s": (ext_rays + sh_rays) / steps * world / (ms_per_step * 1e-3) / 1e6,
+            "rays_per_sample": (ext_rays + sh_rays) / steps / max(1, w * h * count),
+            "stages_ms_per_step": {k[3:]: st[k] / steps for k in ("ms_generate", "ms_extend", "ms_shade", "ms_connect", "ms_finalize", "ms_reduce")},
+            "reduce_alone_ms": reduce_alone_ms,
+            "gpu_launches": int(st["kernel_launches"]), "paths_in_flight": int(st["paths_in_flight"]),
+            "dropped": {k: int(st[k]) for k in ("invalid_contributions", "dropped_rays", "stack_overflows", "nee_dropped")},
+            "upload_s": upload_s, "bvh_build_s": st["bvh_build_seconds"], "bvh_depth": int(st["bvh_depth"]), "scene_bytes": int(st["scene_bytes"]),
+        })
+        if e2e:
+            out["e2e"] = e2e
+        if clock_info:
+            out["clocks"] = clock_info
+        if rank == 0:
+            out["roofline"] = self.roofline(name, st, cst, steps)
+            out["config"] = workload_config(name, cfg, sc.d)
+            if cpu and world == 1 and not self.args.no_cpu_baseline:
+                out["cpu_baseline"] = self.cpu_baseline(cfg, sc)
+                if image_error:
+                    out["image_error_vs_cpu"] = self.image_error(cfg)
+        ctx.close()
+        return out
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------------------------------
+    def roofline(self, name, st, cst, steps):
+        rays = max(cst["extension_rays"], 1)
+        box, prim = cst["box_tests"] / rays, cst["prim_tests"] / rays
+        nodef, primf = cst["node_fetches"] / rays, cst["prim_fetches"] / rays
+        lane_bytes = 32.0 * box + 48.0 * prim + 48.0          # SURVEY 8(d): every lane's tests as if each were a fetch
+        warp_bytes = 64.0 * nodef + 48.0 * primf + 48.0       # distinct records per warp step + ray in (32+8... 48 B) per ray
+        ext_ms = st["ms_extend"]
+        n_rays = st["extension_rays"]
+        achieved = n_rays * warp_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+        lane_gbs = n_rays * lane_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+        hbm, hbm_src = measured_hbm_peak()
+        r = {"kernel": "k_extend (closest-hit BVH traversal)", "unit": "GB/s", "achieved": achieved,
+             "kernel_ms_per_step": ext_ms / steps, "rays_per_step": int(n_rays / steps),
+             "what": "bytes of the DISTINCT 64-byte node / 48-byte primitive records each warp step fetches + 48 B ray/hit per ray, per second of k_extend",
+             "distinct_bytes_per_ray": warp_bytes, "node_fetches_per_ray": nodef, "prim_fetches_per_ray": primf,
+             "per_lane_survey8d": {"bytes_per_ray": lane_bytes, "box_tests_per_ray": box, "prim_tests_per_ray": prim, "gbs": lane_gbs,
+                                   "note": "32 B per box test + 48 B per primitive test + 48 B per ray, every lane counted (lanes on the same node share a fetch)"},
+             "hbm_stream_peak": hbm, "hbm_peak_source": hbm_src}
+        ws = int(st["scene_bytes"])
+        if self.peaks:
+            peak = gather_peak_at(self.peaks, ws)
+            level = "L1" if ws <= (128 << 10) else "L2" if ws <= (96 << 20) else "L2+HBM" if ws <= (512 << 20) else "HBM"
+            r.update({"bound": f"{level} gather of 64-byte records (scene working set {ws / 1e6:.1f} MB)", "peak": peak, "frac": achieved / peak if peak else None,
+                      "peak_source": "measured in this run by jet-pbrt_b200/build/peaks_l2 (scripts/peaks_l2.cu): divergent 64-byte gather at the scene's working-set size",
+                      "uniform_gather_peak": max(g["uniform_gbs"] for g in self.peaks["gather64"]),
+                      "frac_of_hbm_stream": achieved / hbm})
+        else:
+            r.update({"bound": "hbm", "peak": hbm, "frac": achieved / hbm, "peak_source": hbm_src + " (peaks_l2 micro-benchmark unavailable)"})
+        consts = ROOT / "profiles" / "r02_ncu_constants.json"
+        if consts.exists():
+            try:
+                c = json.loads(consts.read_text()).get(name)
+                if c:
+                    ke = c["k_extend"]
+                    r["traffic"] = ke["dram_bytes_per_ray"] * n_rays / steps / max(1, c.get("extend_launches_per_step", 1))
+                    r["traffic_unit"] = "bytes per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum per ray of this build x rays per launch"
+                    r["ncu"] = {"source": c.get("source"), "dram_bytes_per_ray": ke["dram_bytes_per_ray"],
+                                "dram_frac_of_hbm_peak": ke.get("dram_frac"), "l2_bytes_per_ray": ke.get("l2_bytes_per_ray"),
+                                "ipc": ke.get("ipc"), "lanes_per_inst": ke.get("lanes_per_inst"),
+                                "issue_x_lane_efficiency": ke.get("issue_lane_eff"), "k_connect": c.get("k_connect")}
+            except Exception:
+                pass
+        r.setdefault("traffic", None)
+        return r
+
+    # ---- CPU reference on this host ---------------------------------------------------------------------------------------
+    def cpu_baseline(self, cfg, sc):
+        orc = self.ge.load_oracle()
+        scene_name, scale, w, h, spp, desc = cfg
+        kind = "reference" if orc.have("ref") else "port"
+        o = orc.Oracle("ref" if kind == "reference" else "port")
+        threads = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        s = o.scene(sc)
+        build = time.perf_counter() - t0
+        _, probe = s.render(1, threads)
+        n = max(1, min(spp, int(self.args.cpu_seconds / max(probe, 1e-3))))
+        sec = probe
+        if n > 1:
+            _, sec = s.render(n, threads)
+        return {"value": w * h * n / sec / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind,
+                "sample": f"{w}x{h} x {n} spp of the same scene, FIntegrator::Render numthreads={threads}, {sec:.1f}s (BVH build {build:.2f}s excluded)"}
+
+    def image_error(self, cfg):
+        """BASELINE.json metric, second half: image RMSE of the GPU render against the reference CPU render at EQUAL spp, next to
+        the CPU-vs-CPU figure for two independent seeds (the Monte Carlo noise floor).  Outside every timed region, at a reduced
+        resolution so that the CPU side costs about a second; the full-size comparisons are in tests/test_gpu_full_size.py."""
+        np, pkg = self.np, self.pkg
+        orc = self.ge.load_oracle()
+        scene_name, scale, w, h, spp, desc = cfg
+        res, n = 256, 64
+        sc = pkg.HostScene.builtin(scene_name, res, max(1, res * h // w), scale if scene_name != "large" else 0.3)
+        o = orc.Oracle("ref" if orc.have("ref") else "port").scene(sc)
+        threads = os.cpu_count() or 1
+        cpu_a, _ = o.render(n, threads, seed=1234)
+        cpu_b, _ = o.render(n, threads, seed=4321)
+        gpu, _ = pkg.render(sc, n, seed=5, device=self.local)
+        rmse = lambda a, b: float(np.sqrt(np.mean((a - b) ** 2)))  # noqa: E731
+        relmse = lambda a, b: float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))  # noqa: E731
+        return {"what": f"{res}x{sc.d.camera.height} x {n} spp, clamped linear film values",
+                "rmse_gpu_vs_cpu": rmse(gpu, cpu_a), "rmse_cpu_vs_cpu": rmse(cpu_b, cpu_a),
+                "relmse_gpu_vs_cpu": relmse(gpu, cpu_a), "relmse_cpu_vs_cpu": relmse(cpu_b, cpu_a),
+                "mean_gpu": float(gpu.mean()), "mean_cpu": float(cpu_a.mean())}
+
+    # ---- N > 1: the reduced film against one GPU rendering everything -------------------------------------------------------
+    def reduce_check(self, name, spp):
+        """SURVEY 8(e) validation ON THE B200s: ranks render their partitions, the library reduces; then rank 0 alone renders
+        all N x spp sample indices.  The two raw films must agree to float summation order."""
+        torch, np, pkg = self.torch, self.np, self.pkg
+        sc, ctx, _ = self.open(name)
+        world, rank = self.world, self.rank
+        ctx.clear_film()
+        ctx.render_pass(rank * spp, spp, SEED)
+        ctx.reduce_film()
+        ctx.synchronize()
+        self.barrier()
+        res = None
+        if rank == 0:
+            reduced = ctx.film_tensor().clone()
+            ctx.clear_film()
+            ctx.render_pass(0, spp * world, SEED)
+            ctx.synchronize()
+            alone = ctx.film_tensor()
+            diff = (reduced - alone).abs()
+            rel = diff / alone.abs().clamp_min(1e-3)
+            res = {"what": f"{name} 1024^2: ncclReduce of {world} x {spp} spp partitions vs rank 0 rendering all {world * spp} spp alone, raw float32 sums",
+                   "max_rel_err": float(rel.max()), "mean_rel_err": float(rel.mean()), "pixels_beyond_1e-5": int((rel > 1e-5).sum()),
+                   "sum_reduced": float(reduced.double().sum()), "sum_alone": float(alone.double().sum()),
+                   "ok": bool(rel.max() <= 1e-4 and abs(float(reduced.double().sum()) / float(alone.double().sum()) - 1) <= 1e-6)}
+        self.barrier()
+        ctx.close()
+        return res
+
+
+def run_b200(args, emit):
+    args.warmup = max(args.warmup, 3)
+    b = Bench(args)
+    rank, world = b.rank, b.world
+    if rank == 0:
+        b.peaks = run_peaks(b.local)
+    b.barrier()
+    name = args.config
+    head = b.measure(name, "weak", args.steps, args.warmup, spp_override=args.spp, full=True, sample_clocks=True)
+    # ---- strong scaling: fixed total work split over the ranks ----
+    strong = {}
+    if not args.quick:
+        s = b.measure(name, "strong", max(3, min(args.steps, 10)), 3, spp_override=args.spp, full=True, cpu=False)
+        strong[name] = {k: s.get(k) for k in ("value", "unit", "ms_per_step", "spp_total", "spp_this_rank", "mrays_per_s", "stages_ms_per_step",
+                                              "reduce_alone_ms", "e2e", "steps")}
+        # BASELINE configs[4]: 3840 x 2160, 4096 spp in total, ONE timed render (18 s on one B200), warmed up with 3 short passes
+        c5 = b.measure("cornell4k", "strong", 1, 3, spp_override=args.c5_spp, full=False, cpu=(world == 1), image_error=False, spp_warm=8)
+        strong["cornell4k"] = {k: c5.get(k) for k in ("value", "unit", "ms_per_step", "spp_total", "spp_this_rank", "mrays_per_s", "rays_per_sample",
+                                                      "stages_ms_per_step", "reduce_alone_ms", "roofline", "cpu_baseline", "config", "steps", "dropped")}
+    # ---- the other BASELINE configs, one GPU ----
+    configs = {}
+    if world == 1 and not args.quick:
+        for other in ("cornell", "large", "glossy"):
+            if other == name:
+                continue
+            c = b.measure(other, "weak", 3, 3, full=True, image_error=(other != "large"))  # (a CPU image of the 5 M-triangle scene costs minutes)
+            configs[other] = {k: c.get(k) for k in ("value", "unit", "ms_per_step", "e2e", "mrays_per_s", "rays_per_sample", "stages_ms_per_step", "roofline",
+                                                    "cpu_baseline", "image_error_vs_cpu", "config", "upload_s", "bvh_build_s", "bvh_depth", "dropped", "steps")}
+    check = b.reduce_check(name, 8) if world > 1 else None
+    if rank == 0:
+        cfg = CONFIGS[name]
+        line = {
+            "metric": "Msamples/s", "value": head["value"], "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": head["config"],
+            "run": {"spp_per_gpu_per_step": head["spp_this_rank"], "spp_total": head["spp_total"],
+                    "parallelism": f"sample-partition x{world}, scene replicated, ONE ncclReduce of the f32 film per step inside the library (jpbrt_comm_init / jpbrt_read_film)",
+                    "paths_in_flight": head["paths_in_flight"],
+                    "l2": f"no explicit flush: each step streams {cfg[2] * cfg[3] * head['spp_this_rank'] * 104 / 1e6:.0f} MB of wavefront state (> 126 MB L2); "
+                          "the scene arrays are legitimately cache-resident across the step"},
+            "mrays_per_s": head["mrays_per_s"], "rays_per_sample": head["rays_per_sample"],
+            "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
+            "stages_ms_per_step": head["stages_ms_per_step"], "reduce_alone_ms": head["reduce_alone_ms"],
+            "clocks": head.get("clocks"), "dropped": head["dropped"],
+            "upload_s": head["upload_s"], "bvh_build_s": head["bvh_build_s"], "film_mean": head.get("film_mean"),
+            "peaks_measured": b.peaks,
+        }
+        for k in ("cpu_baseline", "image_error_vs_cpu"):
+            if k in head:
+                line[k] = head[k]
+        if strong:
+            line["strong"] = strong
+        if configs:
+            line["configs"] = configs
+        if check:
+            line["reduce_check"] = check
+    if world > 1:
+        b.dist.barrier()
+        b.dist.destroy_process_group()
+    if rank == 0:
+        emit(line)
     return 0
 
 
@@ -155,12 +584,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="bunny", choices=sorted(CONFIGS))
-    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per GPU per step")
+    ap.add_argument("--spp", type=int, default=0, help="override the config's samples per pixel")
+    ap.add_argument("--c5-spp", type=int, default=0, help="override the 4096 spp of the 3840x2160 strong-scaling render")
+    ap.add_argument("--quick", action="store_true", help="headline config only: no strong-scaling block, no other configs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU time budget of each cpu_baseline sample")
     ap.add_argument("--paths-in-flight", type=int, default=0)
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks during the timed region")
     args = ap.parse_args()
-    cfg = CONFIGS[args.config]
     # stdout carries exactly ONE JSON line: everything else (NCCL banners, library chatter) goes to stderr
     real_stdout = os.dup(1)
     os.dup2(2, 1)
@@ -171,255 +602,8 @@ def main():
         print(json.dumps(line), flush=True)
 
     if args.impl == "reference":
-        return run_reference(args, cfg, emit)
-    args.warmup = max(args.warmup, 3)
-
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    import __graft_entry__ as ge
-
-    pkg = ge.load_package()
-    sys.path.insert(0, str(ROOT / "jet-pbrt_b200"))
-    import multi_gpu
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available() or pkg.device_count() <= local:
-        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    ddist = dist if world > 1 else None
-
-    scene_name, scale, w, h, spp, desc = cfg
-    if args.spp > 0:
-        spp = args.spp
-    sc = pkg.HostScene.builtin(scene_name, w, h, scale)
-    t0 = time.perf_counter()
-    ctx = pkg.Context(sc, device=local)
-    upload_s = time.perf_counter() - t0
-    if args.paths_in_flight:
-        ctx.set_option("paths_in_flight", args.paths_in_flight)
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=local)
-    film = ctx.film_tensor()
-    nfloats = film.numel()
-    host_film = torch.empty(nfloats, dtype=torch.float32, pin_memory=True)
-    begin, count = multi_gpu.sample_range(spp, rank)
-    spp_total = spp * world
-    seed = 1234
-
-    def step_resident():
-        ctx.clear_film()
-        ctx.render_pass(begin, count, seed)
-        multi_gpu.reduce_film(film, ddist, 0)
-        if rank == 0:
-            ctx.finalize_film_device(film.data_ptr(), spp_total)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    with torch.cuda.stream(stream):
-        # ---- counting pass (outside the timed region): box / primitive tests per ray on OUR BVH ----
-        ctx.set_option("count_traversal", 1)
-        ctx.clear_film()
-        ctx.render_pass(begin, min(count, 4), seed)
-        ctx.synchronize()
-        cst = ctx.stats()
-        ctx.set_option("count_traversal", 0)
-        box_per_ray = cst["box_tests"] / max(cst["extension_rays"], 1)
-        prim_per_ray = cst["prim_tests"] / max(cst["extension_rays"], 1)
-        bytes_per_ray = 32.0 * box_per_ray + 48.0 * prim_per_ray + 48.0
-
-        for _ in range(args.warmup):
-            step_resident()
-        barrier()
-        # ---- e2e: host buffers in, host film out, every step.  Measured BEFORE the nvidia-smi clock sampler of the
-        # `value` loop is started: on these boxes host driver calls stall for 30-80 ms for a while after (and
-        # during) nvidia-smi polling, which an asynchronous launch loop hides but a per-step round trip does not. ----
-        queue_ms = []
-
-        def step_e2e():
-            tq = time.perf_counter()
-            nbytes = ctx.reupload_scene()
-            ctx.clear_film()
-            ctx.render_pass(begin, count, seed)
-            queue_ms.append(1e3 * (time.perf_counter() - tq))  # host time to queue the step's copies and launches
-            multi_gpu.reduce_film(film, ddist, 0)
-            if rank == 0:
-                pkg._check(pkg.lib.jpbrt_read_film(ctx._ctx, pkg.C.cast(host_film.data_ptr(), pkg.C.POINTER(pkg.C.c_float)), spp_total, 1), ctx._ctx)
-            else:
-                ctx.synchronize()
-            return nbytes
-
-        for _ in range(max(3, args.warmup)):  # the same W >= 3 untimed steps as the `value` loop, on this path
-            h2d = step_e2e()
-        barrier()
-        import gc
-        gc.collect()
-        gc.disable()  # no collector pauses inside the timed region
-        queue_ms.clear()
-        t0 = time.perf_counter()
-        e2e_steps_ms = []
-        for _ in range(args.steps):
-            ts = time.perf_counter()
-            step_e2e()  # ends with a device->host copy + stream synchronize on rank 0
-            e2e_steps_ms.append(1e3 * (time.perf_counter() - ts))
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        gc.enable()
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-        e2e_value = w * h * spp_total * args.steps / e2e_s / 1e6
-        ctx.set_option("stage_timing", 1)  # per-launch CUDA events => the eager launch path, not the graph
-        step_resident()                    # one more untimed step on exactly that path (creates its event pool)
-        barrier()
-        ctx.clear_film()
-        ctx.reset_stats()
-        clocks = ClockSampler(local)
-        if rank == 0 and not args.no_clocks:
-            clocks.start()
-            clocks.wait_first_sample(5.0)  # nvidia-smi's start-up (NVML init, driver locks) stays OUT of the timed region
-        barrier()
-        step_resident()                    # one more untimed step (every rank: it holds the reduce) with the sampler polling
-        barrier()
-        ctx.clear_film()
-        ctx.reset_stats()
-        clocks.rows.clear()                # only samples taken during the timed region count
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # Hold the stream for ~100 ms (untimed: before ev0) while the host queues the first steps' launches, so that a
-        # stalled host driver call (seen on these boxes while nvidia-smi polls) cannot leave the GPU idle inside the
-        # timed region: from then on the host stays several steps ahead of the device.
-        torch.cuda._sleep(int(0.1 * 1.9e9))
-        ev0.record(stream)
-        for _ in range(args.steps):
-            step_resident()
-        ev1.record(stream)
-        barrier()
-        ms_total = ev0.elapsed_time(ev1)
-        clock_info = clocks.stop() if rank == 0 else None
-        st = ctx.stats()  # totals over the K timed steps (reset_stats() was called just before them)
-        ctx.set_option("stage_timing", 0)
-        t = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-        ms_per_step = ms_total / args.steps
-        samples_per_step = w * h * spp_total
-        value = samples_per_step / (ms_per_step * 1e-3) / 1e6
-        rays_per_step_rank = (st["extension_rays"] + st["shadow_rays"]) / args.steps
-
-        final_mean = float(host_film.mean()) if rank == 0 else 0.0
-
-    line = None
-    if rank == 0:
-        peak, peak_src = peaks()
-        ext_ms = st["ms_extend"]  # CUDA-event time of all k_extend launches of the K timed steps
-        ext_bytes = st["extension_rays"] * bytes_per_ray
-        achieved = ext_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
-        # wavefronts per render_pass: bands of <= 2^20 pixels x as many samples as the pool holds (csrc/c_api.cu)
-        n_bands = max(1, -(-(w * h) // (1 << 20)))
-        band_pixels = -(-(w * h) // n_bands)
-        n_waves = n_bands * max(1, -(-spp // max(1, int(st["paths_in_flight"]) // band_pixels)))
-        n_ext_launches = (sc.d.max_depth + 1) * n_waves
-        line = {
-            "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": f"{args.config}: {desc}", "width": w, "height": h, "spp_per_gpu_per_step": spp, "spp_total": spp_total,
-                       "max_depth": sc.d.max_depth, "n_primitives": sc.d.n_primitives, "n_lights": sc.d.n_lights,
-                       "parallelism": f"sample-partition x{world}, scene replicated, one NCCL reduce of the f32 film per step",
-                       "paths_in_flight": int(st["paths_in_flight"]),
-                       "l2": f"no explicit flush: each step streams {st_bytes(ctx, sc, spp, w, h) / 1e6:.0f} MB of wavefront state (> 126 MB L2); "
-                             "the scene arrays are legitimately cache-resident across the step",
-                       "seed": seed},
-            "mrays_per_s": rays_per_step_rank * world / (ms_per_step * 1e-3) / 1e6,
-            "rays_per_sample": rays_per_step_rank / (w * h * spp),
-            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(nfloats * 4),
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "ms_each_step": [round(x, 2) for x in e2e_steps_ms],
-                    "host_queue_ms_each_step": [round(x, 2) for x in queue_ms],
-                    "what": "jpbrt_reupload_scene (pinned host -> HBM) + jpbrt_render_pass + reduce + jpbrt_read_film (finalize, HBM -> pinned host)"},
-            "gpu_launches": int(st["kernel_launches"]),
-            "roofline": {"bound": "hbm", "kernel": "k_extend (closest-hit BVH traversal)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         "traffic": (NCU_EXTEND_DRAM_BYTES_PER_RAY[args.config] * st["extension_rays"] / args.steps / n_ext_launches
-                                     if args.config in NCU_EXTEND_DRAM_BYTES_PER_RAY else None),
-                         "traffic_unit": "bytes per launch (ncu dram bytes per ray x rays per launch)",
-                         "algorithmic_bytes_per_launch": ext_bytes / args.steps / n_ext_launches,
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_ray": bytes_per_ray, "box_tests_per_ray": box_per_ray, "prim_tests_per_ray": prim_per_ray,
-                         "rays_per_step": int(st["extension_rays"] / args.steps), "kernel_ms_per_step": ext_ms / args.steps,
-                         "launches_per_step": n_ext_launches,
-                         "note": ("scene is %.1f MB: L1/L2-resident, so the HBM fraction is an upper-bound yardstick, not a DRAM measurement"
-                                  if st["scene_bytes"] < 100e6 else
-                                  "scene is %.1f MB (> 126 MB L2): nodes and primitives are fetched through L1/L2 (hit rates ~60 %% each, ncu) and the "
-                                  "kernel is latency/issue-bound with DRAM at ~11 %% of peak; the algorithmic fraction counts every node visit as a fetch")
-                                 % (st["scene_bytes"] / 1e6)},
-            "stages_ms_per_step": {k[3:]: st[k] / args.steps for k in ("ms_generate", "ms_extend", "ms_shade", "ms_connect", "ms_finalize")},
-            "clocks": clock_info,
-            "upload_s": upload_s, "bvh_build_s": st["bvh_build_seconds"], "film_mean": final_mean,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(pkg, ge, cfg, sc)
-            line["image_error_vs_cpu"] = image_error(pkg, ge, cfg, local)
-    ctx.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    if line is not None:
-        emit(line)
-    return 0
-
-
-def st_bytes(ctx, sc, spp, w, h):
-    # path records (2 x 48 B ping-pong + 8 B hit) for every path of the step, shadow records on top
-    return w * h * spp * (48 * 2 + 8)
-
-
-def cpu_baseline(pkg, ge, cfg, sc):
-    """The reference's CPU renderer on this host, on a bounded sample of the same workload."""
-    orc = ge.load_oracle()
-    scene_name, scale, w, h, spp, desc = cfg
-    kind = "reference" if orc.have("ref") else "port"
-    o = orc.Oracle("ref" if kind == "reference" else "port")
-    threads = os.cpu_count() or 1
-    t0 = time.perf_counter()
-    s = o.scene(sc)
-    build = time.perf_counter() - t0
-    _, probe = s.render(1, threads)
-    n = max(1, min(spp, int(12.0 / max(probe, 1e-3))))
-    _, sec = s.render(n, threads)
-    return {"value": w * h * n / sec / 1e6, "unit": "Msamples/s", "cores": threads, "kind": kind,
-            "sample": f"{w}x{h} x {n} spp of the same scene, FIntegrator::Render numthreads={threads}, {sec:.1f}s (BVH build {build:.2f}s excluded)"}
-
-
-def image_error(pkg, ge, cfg, device):
-    """BASELINE.json metric, second half: image RMSE of the GPU render against the reference CPU render at EQUAL
-    spp, next to the CPU-vs-CPU figure for two independent seeds (the Monte Carlo noise floor).  Outside every
-    timed region, at 256 x 256 x 64 spp so that the CPU side costs about a second."""
-    import numpy as np
-
-    orc = ge.load_oracle()
-    scene_name, scale, w, h, spp, desc = cfg
-    res, n = 256, 64
-    sc = pkg.HostScene.builtin(scene_name, res, res * h // w if h != w else res, scale)
-    o = orc.Oracle("ref" if orc.have("ref") else "port").scene(sc)
-    threads = os.cpu_count() or 1
-    cpu_a, _ = o.render(n, threads, seed=1234)
-    cpu_b, _ = o.render(n, threads, seed=4321)
-    gpu, _ = pkg.render(sc, n, seed=5, device=device)
-    rmse = lambda a, b: float(np.sqrt(np.mean((a - b) ** 2)))  # noqa: E731
-    relmse = lambda a, b: float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))  # noqa: E731
-    return {"what": f"{res}x{sc.d.camera.height} x {n} spp, clamped linear film values",
-            "rmse_gpu_vs_cpu": rmse(gpu, cpu_a), "rmse_cpu_vs_cpu": rmse(cpu_b, cpu_a),
-            "relmse_gpu_vs_cpu": relmse(gpu, cpu_a), "relmse_cpu_vs_cpu": relmse(cpu_b, cpu_a),
-            "mean_gpu": float(gpu.mean()), "mean_cpu": float(cpu_a.mean())}
+        return run_reference(args, args.config, CONFIGS[args.config], emit)
+    return run_b200(args, emit)
 
 
 if __name__ == "__main__":
