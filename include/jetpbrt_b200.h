@@ -231,8 +231,21 @@ jpbrt_scene*            jpbrt_scene_builtin(const char* name, int width, int hei
 const jpbrt_scene_desc* jpbrt_scene_get_desc(jpbrt_scene* s);
 void                    jpbrt_scene_free(jpbrt_scene* s);
 
-/* FFilm::SaveAsImage (film.cc:13-43): kind 0 = PPM, 1 = BMP, 2 = HDR; `basename` without extension. */
+/* FFilm::SaveAsImage (film.cc:11-188): kind 0 = PPM, 1 = BMP, 2 = HDR (EImageType, film.h:15-20); `basename` without
+ * extension.  Byte-identical to the reference's files wherever those are well defined: HDR for every pixel whose largest
+ * channel is >= 1e-32 (below that the reference writes an uninitialised rgbe[4], film.cc:159-181; here: zeros), BMP whenever a row of
+ * width*3 bytes needs no padding (width % 4 == 0 -- all BASELINE resolutions), PPM always -- including the reference's
+ * quirk of streaming every channel as one raw byte under a "P3" header (film.cc:53-55).  Kind 3 writes the well-formed
+ * text P3 instead.  For widths whose rows need padding the reference's BMP writer reads its padded buffer with the
+ * unpadded stride (film.cc:139-141: a skewed, short file); this writer emits the valid padded BMP. */
 int jpbrt_save_image(const char* basename, int kind, int width, int height, const float* rgb);
+
+/* Wavefront OBJ -> triangles as LoadTriangleMesh delivers them (shape.cc:23-68, scene.cc:49-64): positions only, 9 floats
+ * per triangle, transformed in the reference's order (z negated if flip_handedness, then * scale, then + offset3; offset3
+ * may be NULL).  Backslashes in `filename` are accepted (the reference spells "scene\\bunny\\bunny.obj", main.cc:94).
+ * Copies up to `capacity` triangles into tris9 (may be NULL) and returns the triangle count, or a negative status. */
+long long jpbrt_load_obj_triangles(const char* filename, int flip_handedness, const float* offset3, float scale, float* tris9,
+                                   long long capacity);
 
 /* Number of CUDA devices visible (0 if none / no driver): lets callers skip instead of fail. */
 int jpbrt_device_count(void);

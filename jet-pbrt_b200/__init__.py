@@ -51,7 +51,7 @@ EXPORTS = [
     "jpbrt_unit_bsdf", "jpbrt_unit_bsdf_ex", "jpbrt_unit_light_sample", "jpbrt_unit_emitted", "jpbrt_unit_generate_rays",
     "jpbrt_unit_rng_block", "jpbrt_unit_philox_raw", "jpbrt_scene_info", "jpbrt_scene_builtin", "jpbrt_scene_get_desc",
     "jpbrt_comm_unique_id", "jpbrt_comm_init", "jpbrt_comm_rank", "jpbrt_comm_size", "jpbrt_reduce_film", "jpbrt_sample_partition",
-    "jpbrt_render_multi", "jpbrt_scene_free", "jpbrt_save_image", "jpbrt_version", "jpbrt_device_count", "jpbrt_debug_flatten", "jpbrt_debug_ctx_table",
+    "jpbrt_render_multi", "jpbrt_load_obj_triangles", "jpbrt_scene_free", "jpbrt_save_image", "jpbrt_version", "jpbrt_device_count", "jpbrt_debug_flatten", "jpbrt_debug_ctx_table",
 ]
 
 
@@ -120,6 +120,8 @@ def _load():
     lib.jpbrt_sample_partition.argtypes = [I, I, I, IP, IP]
     lib.jpbrt_sample_partition.restype = None
     lib.jpbrt_render_multi.argtypes = [C.POINTER(SceneDesc), I, I, C.c_uint64, I, F, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.jpbrt_load_obj_triangles.argtypes = [C.c_char_p, I, F, C.c_float, F, C.c_longlong]
+    lib.jpbrt_load_obj_triangles.restype = C.c_longlong
     return lib
 
 
@@ -388,6 +390,17 @@ def save_image(basename: str, kind: int, film: np.ndarray):
     film = _f32(film)
     h, w = film.shape[0], film.shape[1]
     _check(lib.jpbrt_save_image(basename.encode(), kind, w, h, _f(film)))
+
+
+def load_obj_triangles(filename: str, flip_handedness=False, offset=(0, 0, 0), scale=1.0):
+    """jpbrt_load_obj_triangles: tris[n, 3, 3] as the reference's LoadTriangleMesh delivers them, or None on failure."""
+    off = np.asarray(offset, np.float32)
+    n = lib.jpbrt_load_obj_triangles(filename.encode(), int(flip_handedness), _f(off), scale, None, 0)
+    if n < 0:
+        return None
+    out = np.empty((n, 3, 3), np.float32)
+    lib.jpbrt_load_obj_triangles(filename.encode(), int(flip_handedness), _f(off), scale, _f(out), n)
+    return out
 
 
 def device_count() -> int:

@@ -22,14 +22,19 @@ inline float Clamp01(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
 // gamma_encoding, film.h:24
 inline uint8_t GammaEncode(float x) { return (uint8_t)(std::pow(Clamp01(x), (float)(1 / 2.2)) * 255.0); }
 
-// FFilm::SaveAsPPM, film.cc:45-60 (the reference streams uint8_t with operator<<, i.e. as characters; the
-// numbers are written as text here so the "P3" header is honoured -- DESIGN.md "Deviations").
-bool SavePPM(const std::string& fn, int w, int h, const float* rgb) {
+// FFilm::SaveAsPPM, film.cc:45-60.  The reference streams gamma_encoding()'s uint8_t with operator<<, which writes each
+// value as ONE RAW BYTE (a char), under a "P3" (text) header.  `text` = false reproduces those bytes exactly (the drop-in
+// behaviour, byte-identical to the reference's file); `text` = true writes the numbers as decimal text, i.e. the
+// well-formed P3 file the header promises (image kind 3).
+bool SavePPM(const std::string& fn, int w, int h, const float* rgb, bool text) {
     std::ofstream f(fn, std::ios::binary);
     if (!f) return false;
     f << "P3\n" << w << " " << h << "\n255\n";
-    for (int i = 0; i < w * h; ++i)
-        f << (int)GammaEncode(rgb[3 * i]) << "  " << (int)GammaEncode(rgb[3 * i + 1]) << "  " << (int)GammaEncode(rgb[3 * i + 2]) << "\n";
+    for (int i = 0; i < w * h; ++i) {
+        const uint8_t r = GammaEncode(rgb[3 * i]), g = GammaEncode(rgb[3 * i + 1]), b = GammaEncode(rgb[3 * i + 2]);
+        if (text) f << (int)r << "  " << (int)g << "  " << (int)b << "\n";
+        else f << (char)r << "  " << (char)g << "  " << (char)b << "\n";
+    }
     return (bool)f;
 }
 
@@ -103,12 +108,32 @@ const jpbrt_scene_desc* jpbrt_scene_get_desc(jpbrt_scene* s) { return s ? s->sce
 
 void jpbrt_scene_free(jpbrt_scene* s) { delete s; }
 
+long long jpbrt_load_obj_triangles(const char* filename, int flip_handedness, const float* offset3, float scale, float* tris9,
+                                   long long capacity) {
+    if (!filename) return JPBRT_ERR_INVALID;
+    std::vector<float> tris;
+    std::string err;
+    if (!jetpbrt::LoadObjTriangles(filename, &tris, &err)) return JPBRT_ERR_IO;
+    const long long n = (long long)(tris.size() / 9);
+    const float off[3] = {offset3 ? offset3[0] : 0.f, offset3 ? offset3[1] : 0.f, offset3 ? offset3[2] : 0.f};
+    for (long long i = 0; i < n && i < capacity && tris9; ++i)
+        for (int v = 0; v < 3; ++v) {
+            float p[3] = {tris[9 * i + 3 * v], tris[9 * i + 3 * v + 1], tris[9 * i + 3 * v + 2]};
+            if (flip_handedness) p[2] = -p[2];                    // LoadTriangleMesh's order, shape.cc:48-62:
+            for (int c = 0; c < 3; ++c) p[c] = p[c] * scale;     //   negate z, then scale,
+            for (int c = 0; c < 3; ++c) p[c] = p[c] + off[c];    //   then offset
+            for (int c = 0; c < 3; ++c) tris9[9 * i + 3 * v + c] = p[c];
+        }
+    return n;
+}
+
 int jpbrt_save_image(const char* basename, int kind, int width, int height, const float* rgb) {
     if (!basename || !rgb || width <= 0 || height <= 0) return JPBRT_ERR_INVALID;
     std::string base(basename);
     bool ok = false;
     switch (kind) {  // EImageType, film.h:15-20
-    case 0: ok = SavePPM(base + ".ppm", width, height, rgb); break;
+    case 0: ok = SavePPM(base + ".ppm", width, height, rgb, false); break;
+    case 3: ok = SavePPM(base + ".ppm", width, height, rgb, true); break;
     case 1: ok = SaveBMP(base + ".bmp", width, height, rgb); break;
     case 2: ok = SaveHDR(base + ".hdr", width, height, rgb); break;
     default: return JPBRT_ERR_INVALID;

@@ -66,6 +66,9 @@ class Oracle:
         g("render_mode").argtypes = [P, I, I, I, I, F]
         g("render_mode").restype = C.c_double
         g("scene_info").argtypes = [P, F]
+        if kind == "ref":
+            g("save_image").argtypes = [C.c_char_p, I, I, I, F]
+            g("load_obj").argtypes = [C.c_char_p, I, I, F, C.c_float, F, F, I]
         if kind == "port":
             g("scene_intersect_brute").argtypes = [P, I, F, IP, F, F, F]
             g("render_counter").argtypes = [P, I, I, C.c_uint64, I, F, C.POINTER(C.c_uint64)]
@@ -117,6 +120,19 @@ class Oracle:
         o = np.empty(4, np.float32)
         self._fn("philox_block")(pixel, sample, block, seed, _f(o))
         return o
+
+    def save_image(self, basename: str, kind: int, film):
+        """(ref only) FFilm::AddColor + FFilm::SaveAsImage of the unmodified reference."""
+        film = _f32(film)
+        h, w = film.shape[0], film.shape[1]
+        return self._fn("save_image")(basename.encode(), kind, w, h, _f(film))
+
+    def load_obj(self, filename: str, flip_normal=False, flip_handedness=False, offset=(0, 0, 0), scale=1.0, capacity=1 << 20):
+        """(ref only) LoadTriangleMesh through the vendored obj_loader.h: (tris[n,3,3], normals[n,3]) or None on failure."""
+        tris = np.zeros((capacity, 3, 3), np.float32); nrm = np.zeros((capacity, 3), np.float32)
+        off = np.asarray(offset, np.float32)
+        n = self._fn("load_obj")(filename.encode(), int(flip_normal), int(flip_handedness), _f(off), scale, _f(tris), _f(nrm), capacity)
+        return None if n < 0 else (tris[:n].copy(), nrm[:n].copy())
 
     def philox_raw(self, ctr4, key2):
         ctr4 = np.ascontiguousarray(ctr4, np.uint32); key2 = np.ascontiguousarray(key2, np.uint32)

@@ -346,4 +346,31 @@ int jref_scene_info(jref_scene* s, float* out7) {
     return 0;
 }
 
+// ---- the callers and data formats either side of the path, for pinning the product's writers ----
+
+// FFilm::AddColor + FFilm::SaveAsImage (film.h:64-68, film.cc:11-188): kind 0 PPM, 1 BMP, 2 HDR; basename without extension.
+int jref_save_image(const char* basename, int kind, int width, int height, const float* rgb) {
+    FFilm film(width, height);
+    for (int y = 0; y < height; ++y)
+        for (int x = 0; x < width; ++x) {
+            const float* p = rgb + 3 * ((size_t)y * width + x);
+            film.AddColor(x, y, FColor(p[0], p[1], p[2]));
+        }
+    const EImageType t = kind == 0 ? EImageType::PPM : kind == 1 ? EImageType::BMP : EImageType::HDR;
+    return film.SaveAsImage(basename, t) ? 0 : -1;
+}
+
+// LoadTriangleMesh (shape.cc:23-68, through external/obj_loader.h): 9 floats per triangle (p0, p1, p2) + its stored normal.
+// Returns the triangle count (also when it exceeds `capacity`), or -1 when the load fails.
+int jref_load_obj(const char* filename, int flip_normal, int flip_handedness, const float* offset3, float scale,
+                  float* tris9, float* normals3, int capacity) {
+    std::vector<std::shared_ptr<FTriangle>> mesh;
+    if (!LoadTriangleMesh(filename, mesh, flip_normal != 0, flip_handedness != 0, V3(offset3), scale)) return -1;
+    for (int i = 0; i < (int)mesh.size() && i < capacity; ++i) {
+        put3(tris9 + 9 * i, mesh[i]->p0); put3(tris9 + 9 * i + 3, mesh[i]->p1); put3(tris9 + 9 * i + 6, mesh[i]->p2);
+        if (normals3) put3(normals3 + 3 * i, mesh[i]->normal);
+    }
+    return (int)mesh.size();
+}
+
 }  // extern "C"

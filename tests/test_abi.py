@@ -97,7 +97,7 @@ def test_save_image_formats(pkg, tmp_path):
     h, w = 6, 8  # w*3 is a multiple of 4: identical bytes to the reference's writer (film.cc:62-144)
     film = np.linspace(0, 1.2, h * w * 3, dtype=np.float32).reshape(h, w, 3)
     base = str(tmp_path / "img")
-    for kind in (0, 1, 2):
+    for kind in (3, 1, 2):  # 3 = the well-formed text P3 (kind 0 reproduces the reference's raw-byte PPM: test_reference_io_pin.py)
         pkg.save_image(base, kind, film)
     bmp = (tmp_path / "img.bmp").read_bytes()
     assert bmp[:2] == b"BM" and len(bmp) == 54 + w * 3 * h
