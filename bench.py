@@ -389,7 +389,7 @@ class Bench:
         if clock_info:
             out["clocks"] = clock_info
         if rank == 0:
-            out["roofline"] = self.roofline(name, st, cst, steps)
+            out["roofline"] = self.roofline(name, st, cst, steps, sc.d.max_depth)
             out["config"] = workload_config(name, cfg, sc.d)
             if cpu and world == 1 and not self.args.no_cpu_baseline:
                 out["cpu_baseline"] = self.cpu_baseline(cfg, sc)
@@ -399,7 +399,7 @@ class Bench:
         return out
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------------------------------
-    def roofline(self, name, st, cst, steps):
+    def roofline(self, name, st, cst, steps, cst_depth=5):
         rays = max(cst["extension_rays"], 1)
         box, prim = cst["box_tests"] / rays, cst["prim_tests"] / rays
         nodef, primf = cst["node_fetches"] / rays, cst["prim_fetches"] / rays
@@ -418,29 +418,53 @@ class Bench:
                                    "note": "32 B per box test + 48 B per primitive test + 48 B per ray, every lane counted (lanes on the same node share a fetch)"},
              "hbm_stream_peak": hbm, "hbm_peak_source": hbm_src}
         ws = int(st["scene_bytes"])
+        cfgt = CONFIGS[name]
+        n_bands = max(1, -(-(cfgt[2] * cfgt[3]) // (1 << 20)))
+        band_pixels = -(-(cfgt[2] * cfgt[3]) // n_bands)
+        spp_rank = max(1, int(st["samples"] / steps / (cfgt[2] * cfgt[3])))
+        n_waves = n_bands * max(1, -(-spp_rank // max(1, int(st["paths_in_flight"]) // band_pixels)))
+        launches = (int(cst_depth) + 1) * n_waves
+        r["launches_per_step"] = launches
         if self.peaks:
-            peak = gather_peak_at(self.peaks, ws)
-            level = "L1" if ws <= (128 << 10) else "L2" if ws <= (96 << 20) else "L2+HBM" if ws <= (512 << 20) else "HBM"
-            r.update({"bound": f"{level} gather of 64-byte records (scene working set {ws / 1e6:.1f} MB)", "peak": peak, "frac": achieved / peak if peak else None,
-                      "peak_source": "measured in this run by jet-pbrt_b200/build/peaks_l2 (scripts/peaks_l2.cu): divergent 64-byte gather at the scene's working-set size",
-                      "uniform_gather_peak": max(g["uniform_gbs"] for g in self.peaks["gather64"]),
+            g = {x["working_set_bytes"]: x["divergent_gbs"] for x in self.peaks["gather64"]}
+            l1_peak, l2_peak, dram_peak = g[min(g)], gather_peak_at(self.peaks, 32 << 20), g[max(g)]
+            if ws <= (128 << 10):
+                level, peak = "L1", l1_peak
+            elif ws <= (96 << 20):
+                level, peak = "L2", gather_peak_at(self.peaks, ws)
+            else:  # the scene exceeds L2: no gather can beat the L2-resident rate; how much of it comes from DRAM is ncu's to say
+                level, peak = "L2 (upper bound: the scene exceeds the 126 MB L2; a uniformly random gather over it reaches only %.0f GB/s)" % gather_peak_at(self.peaks, ws), l2_peak
+            r.update({"bound": f"issue + {level} gather of 64-byte records (scene working set {ws / 1e6:.1f} MB); ncu: IPC ~2.9 of 4 at ~16-24 of 32 lanes, L1/TEX ~75 % busy, DRAM < 10 %",
+                      "peak": peak, "frac": achieved / peak if peak else None,
+                      "peak_source": "measured in this run by jet-pbrt_b200/build/peaks_l2 (scripts/peaks_l2.cu): divergent gather of 64-byte records (one per lane, two 256-bit loads) "
+                                     "at the scene's working-set size",
+                      "gather_peaks_gbs": {"l1_resident": l1_peak, "l2_resident": l2_peak, "dram_random": dram_peak,
+                                           "uniform_all_lanes_same_record": max(x["uniform_gbs"] for x in self.peaks["gather64"])},
+                      "issue_peak_warp_ginst_s": self.peaks.get("ffma_warp_ginst_s"),
                       "frac_of_hbm_stream": achieved / hbm})
         else:
             r.update({"bound": "hbm", "peak": hbm, "frac": achieved / hbm, "peak_source": hbm_src + " (peaks_l2 micro-benchmark unavailable)"})
         consts = ROOT / "profiles" / "r02_ncu_constants.json"
         if consts.exists():
             try:
-                c = json.loads(consts.read_text()).get(name)
+                c = json.loads(consts.read_text()).get("cornell" if name == "cornell4k" else name)
                 if c:
                     ke = c["k_extend"]
-                    r["traffic"] = ke["dram_bytes_per_ray"] * n_rays / steps / max(1, c.get("extend_launches_per_step", 1))
-                    r["traffic_unit"] = "bytes per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum per ray of this build x rays per launch"
-                    r["ncu"] = {"source": c.get("source"), "dram_bytes_per_ray": ke["dram_bytes_per_ray"],
-                                "dram_frac_of_hbm_peak": ke.get("dram_frac"), "l2_bytes_per_ray": ke.get("l2_bytes_per_ray"),
-                                "ipc": ke.get("ipc"), "lanes_per_inst": ke.get("lanes_per_inst"),
-                                "issue_x_lane_efficiency": ke.get("issue_lane_eff"), "k_connect": c.get("k_connect")}
-            except Exception:
-                pass
+                    r["traffic"] = ke["dram_bytes_per_ray"] * n_rays / steps / launches
+                    r["traffic_unit"] = "bytes per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum per ray of THIS build x rays per launch"
+                    r["algorithmic_bytes_per_launch"] = n_rays * warp_bytes / steps / launches
+                    issue = None
+                    if self.peaks and ke.get("thread_inst_per_ray") and ext_ms > 0:
+                        tps = ke["thread_inst_per_ray"] * n_rays / (ext_ms * 1e-3) / 1e9
+                        issue = {"achieved_thread_ginst_s": tps, "peak_thread_ginst_s": 32.0 * self.peaks["ffma_warp_ginst_s"],
+                                 "frac": tps / (32.0 * self.peaks["ffma_warp_ginst_s"]),
+                                 "what": "thread instructions per ray (ncu, this build) x rays / k_extend time, over 32 lanes x the measured warp-instruction issue rate"}
+                    r["ncu"] = {"source": c.get("source"), "k_extend": {k: ke.get(k) for k in ("dram_bytes_per_ray", "dram_frac", "l2_bytes_per_ray", "l2_gbs", "ipc", "lanes_per_inst",
+                                                                                                "issue_lane_eff", "thread_inst_per_ray", "warp_inst_per_ray")},
+                                "k_connect": {k: c.get("k_connect", {}).get(k) for k in ("dram_frac", "l2_gbs", "ipc", "lanes_per_inst", "issue_lane_eff")},
+                                "issue": issue}
+            except Exception as e:  # noqa: BLE001
+                r["ncu_error"] = repr(e)
         r.setdefault("traffic", None)
         return r
 

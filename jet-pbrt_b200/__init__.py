@@ -51,7 +51,7 @@ EXPORTS = [
     "jpbrt_unit_bsdf", "jpbrt_unit_bsdf_ex", "jpbrt_unit_light_sample", "jpbrt_unit_emitted", "jpbrt_unit_generate_rays",
     "jpbrt_unit_rng_block", "jpbrt_unit_philox_raw", "jpbrt_scene_info", "jpbrt_scene_builtin", "jpbrt_scene_get_desc",
     "jpbrt_comm_unique_id", "jpbrt_comm_init", "jpbrt_comm_rank", "jpbrt_comm_size", "jpbrt_reduce_film", "jpbrt_sample_partition",
-    "jpbrt_render_multi", "jpbrt_load_obj_triangles", "jpbrt_scene_free", "jpbrt_save_image", "jpbrt_version", "jpbrt_device_count", "jpbrt_debug_flatten", "jpbrt_debug_ctx_table",
+    "jpbrt_render_multi", "jpbrt_set_default_option", "jpbrt_load_obj_triangles", "jpbrt_scene_free", "jpbrt_save_image", "jpbrt_version", "jpbrt_device_count", "jpbrt_debug_flatten", "jpbrt_debug_ctx_table",
 ]
 
 
@@ -120,6 +120,7 @@ def _load():
     lib.jpbrt_sample_partition.argtypes = [I, I, I, IP, IP]
     lib.jpbrt_sample_partition.restype = None
     lib.jpbrt_render_multi.argtypes = [C.POINTER(SceneDesc), I, I, C.c_uint64, I, F, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.jpbrt_set_default_option.argtypes = [C.c_char_p, C.c_longlong]
     lib.jpbrt_load_obj_triangles.argtypes = [C.c_char_p, I, F, C.c_float, F, C.c_longlong]
     lib.jpbrt_load_obj_triangles.restype = C.c_longlong
     return lib
@@ -197,6 +198,7 @@ class Context:
 
     # multi-GPU (one process per GPU): NCCL communicator inside the library
     def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        _load_torch_nccl_first()
         buf = C.create_string_buffer(unique_id, COMM_ID_BYTES)
         _check(lib.jpbrt_comm_init(self._ctx, buf, COMM_ID_BYTES, rank, nranks), self._ctx)
 
@@ -365,8 +367,19 @@ def render(scene: HostScene, spp: int, seed: int = 1234, device: int = 0, integr
 COMM_ID_BYTES = 128
 
 
+def _load_torch_nccl_first():
+    """The library binds NCCL at run time (dlopen libnccl.so.2) and a process gets ONE libnccl.so.2: the first loaded.
+    torch ships a newer NCCL than the system's and fails to import against the older one, so when torch is installed it
+    must load (its) NCCL before the library's first communicator call does."""
+    try:
+        import torch  # noqa: F401
+    except ImportError:
+        pass
+
+
 def comm_unique_id() -> bytes:
     """ncclGetUniqueId through the library (rank 0); hand the bytes to the other ranks with any transport."""
+    _load_torch_nccl_first()
     buf = C.create_string_buffer(COMM_ID_BYTES)
     _check(lib.jpbrt_comm_unique_id(buf, COMM_ID_BYTES))
     return buf.raw
@@ -380,6 +393,7 @@ def sample_partition(spp_total: int, rank: int, nranks: int):
 
 def render_multi(scene: HostScene, spp: int, ngpus: int, seed: int = 1234, integrator: str = "path"):
     """FIntegrator::Render with `ngpus` devices of this process: returns (film, seconds, reduce_ms)."""
+    _load_torch_nccl_first()
     out = np.empty((scene.d.camera.height, scene.d.camera.width, 3), dtype=np.float32)
     sec, red = C.c_double(0), C.c_double(0)
     _check(lib.jpbrt_render_multi(scene.desc, INTEGRATORS[integrator], spp, seed, ngpus, _f(out), C.byref(sec), C.byref(red)))
@@ -401,6 +415,10 @@ def load_obj_triangles(filename: str, flip_handedness=False, offset=(0, 0, 0), s
     out = np.empty((n, 3, 3), np.float32)
     lib.jpbrt_load_obj_triangles(filename.encode(), int(flip_handedness), _f(off), scale, _f(out), n)
     return out
+
+
+def set_default_option(name: str, value: int):
+    _check(lib.jpbrt_set_default_option(name.encode(), value))
 
 
 def device_count() -> int:

@@ -300,8 +300,12 @@ __device__ __forceinline__ void trav_leaf_step(const DevScene& sc, Trav& t, cons
 //   leaves : lanes at a leaf test its primitives and pop; finished lanes store their result.
 // Invariant: a lane without a ray (idx < 0) has t.cur == kTravDone, so "at an inner node" / "at a leaf" need no idx test.
 // Must be called by every thread of a kTravBlock-thread block (static shared memory).
+// Node steps per warp vote of the node phase.  The votes that decide whether the phase goes on (any lane at an inner node?
+// fewer than min_inner? any lane at a leaf?) are ~15 of the ~85 instructions of a step; taking two steps per vote -- a lane
+// that reaches a leaf on the first sits out the second -- measured +1.5-2 % on all scenes (bunny 1,543 -> 1,568 Msamples/s at
+// 48 spp, Cornell 1,076 -> 1,090, glossy 186 -> 190), three steps per vote gives the gain back (profiles/ab/r02_ab_unroll.log).
 #ifndef JPB_NODE_UNROLL
-#define JPB_NODE_UNROLL 1  // node steps per warp vote of the node phase (A/B builds)
+#define JPB_NODE_UNROLL 2
 #endif
 template <bool ANY_HIT, bool COUNT, typename IO>
 __device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* work, const IO& io, int refill_min, int min_inner,

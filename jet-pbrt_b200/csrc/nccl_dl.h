@@ -9,6 +9,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
+
 #include <string>
 
 namespace jpbrt {
@@ -30,7 +32,13 @@ struct NcclApi {
     bool Load() {
         if (handle) return true;
         const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        // JPBRT_NCCL_LIB=<path>: load exactly this NCCL.  (Whichever libnccl.so.2 is loaded FIRST is the one the whole
+        // process gets: a program that also uses another NCCL client -- torch.distributed brings its own, newer copy --
+        // must let that client load first, or point this at the same file.  The Python glue imports torch before the
+        // first communicator call for that reason.)
+        if (const char* forced = getenv("JPBRT_NCCL_LIB")) handle = dlopen(forced, RTLD_NOW | RTLD_GLOBAL);
         for (const char* n : names) {
+            if (handle) break;
             handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD);  // already in the process (e.g. torch's)?
             if (handle) break;
         }
