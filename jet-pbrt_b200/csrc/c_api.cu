@@ -681,6 +681,10 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
     if (sample_begin < 0 || sample_count < 0 || (long long)sample_begin + sample_count > 0xffffff)
         return set_error(c, JPBRT_ERR_INVALID, "sample range [%d, %d) outside [0, 2^24)", sample_begin, sample_begin + sample_count);
     CU_CHECK(c, cudaSetDevice(c->device));
+    // Whitted numbers the vertices of its ray tree in 32 bits (children 3n+1 / 3n+3 key the sampler): past depth 20 the ids wrap
+    // and sampler streams would correlate.  Refuse instead of rendering a subtly wrong image.
+    if (c->opt_integrator == JPBRT_INTEGRATOR_WHITTED && c->has_mirror && c->hs.max_depth > 20)
+        return set_error(c, JPBRT_ERR_UNSUPPORTED, "Whitted integrator with mirrors supports max_depth <= 20 (scene has %d)", c->hs.max_depth);
     // Whitted traces a mirror vertex twice (bsdf.h:282): leave room for the ray tree, x2 per mirror bounce, at most x8
     const int tree_growth = (c->opt_integrator == JPBRT_INTEGRATOR_WHITTED && c->has_mirror) ? 1 << std::min(3, std::max(0, c->hs.max_depth - 1)) : 1;
     c->film_reduced = false;
@@ -887,6 +891,13 @@ int jpbrt_render_integrator(const jpbrt_scene_desc* desc, int integrator, int sp
     rc = jpbrt_render_pass(c, 0, spp, seed);
     if (rc == 0) rc = jpbrt_read_film(c, rgb, spp, 1);
     auto t1 = std::chrono::steady_clock::now();
+    if (rc == 0) {  // the image is in rgb; but a one-shot caller never looks at the stats, so lost rays must not pass silently
+        jpbrt_stats st;
+        if (jpbrt_get_stats(c, &st) == 0 && (st.dropped_rays || st.stack_overflows || st.nee_dropped))
+            rc = set_error(c, JPBRT_ERR_UNSUPPORTED, "render completed but lost work: %llu rays dropped (ray tree outgrew the path pool), %llu traversal-stack "
+                           "overflows, %llu light samples without a shadow slot -- the image is too dark; use passes of fewer samples or a larger paths_in_flight",
+                           (unsigned long long)st.dropped_rays, (unsigned long long)st.stack_overflows, (unsigned long long)st.nee_dropped);
+    }
     if (rc != 0) g_last_error = c->error;
     if (seconds_out) *seconds_out = std::chrono::duration<double>(t1 - t0).count();
     jpbrt_destroy(c);

@@ -123,3 +123,18 @@ def test_whitted_tree_overflow_is_counted_not_fatal(pkg, gpu):
     else:
         assert (small <= full + 1e-4 * np.maximum(full, 1)).all()  # only non-negative contributions can be missing
     ctx.close()
+
+
+def test_whitted_refuses_depths_whose_ray_tree_ids_would_wrap(pkg, gpu):
+    """The Whitted mode numbers ray-tree vertices in 32 bits (3n+1 / 3n+3); beyond depth 20 the ids wrap and sampler streams
+    would correlate.  The pass is refused with a message instead of rendering a subtly wrong image; the path
+    integrator, which has no ray tree, takes the same scene at the same depth."""
+    sc = common.specular_scene(pkg, 32, max_depth=24)
+    ctx = pkg.Context(sc)
+    ctx.set_option("integrator", pkg.INTEGRATORS["whitted"])
+    with pytest.raises(pkg.JpbrtError, match="max_depth <= 20"):
+        ctx.render_pass(0, 1, seed=1)
+    ctx.set_option("integrator", pkg.INTEGRATORS["path"])
+    ctx.render_pass(0, 1, seed=1)
+    assert np.isfinite(ctx.read_film(finalize=False)).all() and ctx.stats()["invalid_contributions"] == 0
+    ctx.close()
