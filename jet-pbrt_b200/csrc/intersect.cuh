@@ -221,7 +221,10 @@ struct TravCounts {
     unsigned node_fetch = 0, prim_fetch = 0;  // distinct nodes / primitive records fetched per warp step (counted on one lane)
 };
 
-template <bool COUNT>
+#ifndef JPB_ANYHIT_UNORDERED
+#define JPB_ANYHIT_UNORDERED 0  // A/B: shadow rays descend left-first instead of near-first (any hit answers the query)
+#endif
+template <bool COUNT, bool ANY_HIT = false>
 __device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, const TravStack& stk, TravCounts& cnt, unsigned step_mask) {
     const float widen = 1.0000004f;  // 1 + 2*gamma(3): pbrt's conservative slab bound
     const Float4* np = sc.nodes + (size_t)t.cur * kNodeStride;
@@ -249,7 +252,8 @@ __device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, cons
     const bool hr = rtn <= rtf * widen;
     const int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
     const bool both = hl && hr;
-    const bool right_first = both ? !(ltn <= rtn) : hr;  // the nearer child first; left on ties (the reference's order, bvh.h:99-100)
+    const bool right_first = (JPB_ANYHIT_UNORDERED && ANY_HIT) ? !hl  // occlusion only: any order finds the same boolean
+                                                               : (both ? !(ltn <= rtn) : hr);  // the nearer child first; left on ties (the reference's order, bvh.h:99-100)
     const int near = right_first ? cr : cl;
     const int far = right_first ? cl : cr;
     if (both) stk.push(t.sp, far);  // (prefetching the far child measured 3-6 % slower)
@@ -356,7 +360,7 @@ __device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* w
 #pragma unroll
             for (int u = 0; u < JPB_NODE_UNROLL; ++u) {
                 const unsigned step_mask = COUNT ? (u == 0 ? m_inner : __ballot_sync(full, trav_at_inner(t))) : 0u;
-                if (trav_at_inner(t)) trav_node_step<COUNT>(sc, t, stk, cnt, step_mask);
+                if (trav_at_inner(t)) trav_node_step<COUNT, ANY_HIT>(sc, t, stk, cnt, step_mask);
             }
         }
         const unsigned leaf_mask = COUNT ? __ballot_sync(full, trav_at_leaf(t)) : 0u;
