@@ -397,6 +397,7 @@ static int finish_upload(jpbrt_ctx* c, int device) {
     d.n_inf_lights = (int)hs.inf_lights.size();
     d.n_prims = hs.n_prims;
     d.max_depth = hs.max_depth;
+    d.max_leaf_prims = hs.max_leaf_prims;
     d.width = hs.width;
     d.height = hs.height;
     d.world_radius = hs.world_radius;

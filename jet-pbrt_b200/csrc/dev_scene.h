@@ -72,6 +72,7 @@ struct DevScene {
     const int*    pixel_order;  // path i of a wavefront renders pixel pixel_order[i % npix]: 8x4 tiles in Morton order
     int n_nodes, n_slots, n_materials, n_lights, n_inf_lights, n_prims, n_nee_lights;
     int max_depth;
+    int max_leaf_prims;  // most primitives any leaf holds (<= kMaxLeafPrims unless JPBRT_BVH_LEAF asked for more)
     int width, height;
     float world_radius;  // FEnvironmentLight::worldRadius (light.cc:26-33)
     DevCamera cam;

@@ -294,6 +294,63 @@ __device__ __forceinline__ void trav_leaf_step(const DevScene& sc, Trav& t, cons
     t.cur = stk.pop(t.sp);
 }
 
+// The leaf phase with the primitive tests SPREAD OVER THE WARP (JPB_LEAF_SHARE, round 2).  In the per-lane form above a lane
+// tests its own leaf's 1-4 primitives one after the other: ncu shows ~11 lanes in the first test and ~8 in the later ones,
+// ~2.1 rounds per phase.  Here every (ray, primitive) pair of the phase is an ITEM; the items are laid out in a per-warp
+// shared-memory list (offsets from three ballots: a leaf holds <= 4 primitives) and lane j takes item j -- fetching the
+// owner's ray by shuffle -- so that ~24 items run as ONE round on ~24 lanes.  Every pair is tested with the reference's
+// arithmetic against the owner's tmax at the start of the phase, the results go back through the same list, and the
+// owner folds them in primitive order with the reference's strict `t < tmax`: exactly what the sequential loop accepts
+// (a later primitive wins only if it is strictly closer), hence the same hit record, ties included.
+// Called by ALL lanes of the warp, converged.  items: this warp's 32 * kMaxLeafPrims words of shared memory.
+#ifndef JPB_LEAF_SHARE
+#define JPB_LEAF_SHARE 0
+#endif
+template <bool ANY_HIT>
+__device__ __forceinline__ void trav_leaf_phase_shared(const DevScene& sc, Trav& t, const TravStack& stk, unsigned* items) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool at_leaf = trav_at_leaf(t);
+    int first = 0, n = 0;
+    if (at_leaf) {
+        const int bits = ~t.cur;
+        first = bits >> kLeafCountBits;
+        n = bits & ((1 << kLeafCountBits) - 1);
+    }
+    // exclusive prefix sum of n over the lanes, n in 0..4, from the ballots of its three bits
+    const unsigned b0 = __ballot_sync(full, n & 1), b1 = __ballot_sync(full, n & 2), b2 = __ballot_sync(full, n & 4);
+    const unsigned below = (1u << lane) - 1;
+    const int off = __popc(b0 & below) + 2 * __popc(b1 & below) + 4 * __popc(b2 & below);
+    const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+    for (int k = 0; k < n; ++k) items[off + k] = ((unsigned)lane << 27) | (unsigned)(first + k);
+    __syncwarp();
+    for (int base = 0; base < total; base += 32) {
+        const int j = base + lane;
+        const bool mine = j < total;
+        const unsigned item = mine ? items[j] : ((unsigned)lane << 27);
+        const int owner = (int)(item >> 27), slot = (int)(item & 0x7ffffffu);
+        f3 o, d;
+        o.x = __shfl_sync(full, t.o.x, owner); o.y = __shfl_sync(full, t.o.y, owner); o.z = __shfl_sync(full, t.o.z, owner);
+        d.x = __shfl_sync(full, t.d.x, owner); d.y = __shfl_sync(full, t.d.y, owner); d.z = __shfl_sync(full, t.d.z, owner);
+        const float tmin = __shfl_sync(full, t.tmin, owner);
+        float tmax = __shfl_sync(full, t.tmax, owner);
+        if (mine) {
+            const bool hit = intersect_slot(sc.slots + (size_t)slot * kSlotStride, sc.slot_nrm + slot, o, d, tmin, tmax);
+            items[j] = hit ? __float_as_uint(tmax) : 0x7f800000u;  // the accepted t, or +inf
+        }
+    }
+    __syncwarp();
+    if (at_leaf) {
+        bool found = false;
+        for (int k = 0; k < n; ++k) {  // in primitive order, strict <: the sequential loop's acceptance (shape.h:318)
+            const float r = __uint_as_float(items[off + k]);
+            if (r < t.tmax) { t.tmax = r; t.hit = first + k; found = true; }
+        }
+        t.cur = (ANY_HIT && found) ? kTravDone : stk.pop(t.sp);
+    }
+    __syncwarp();  // the list is rewritten by the next phase
+}
+
 // Warp-cooperative traversal of a whole ray queue.
 //   io.load(i, o, d, tmin, tmax)    fetch ray i (false: slot i holds no ray)   io.store(i, slot, t)   deliver its result
 // Every lane owns one ray at a time.  Each trip round the outer loop has three converged phases:
@@ -317,6 +374,8 @@ __device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* w
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     __shared__ int s_stack[(kSmemStack > 0 ? kSmemStack : 1) * kTravBlock];
+    __shared__ unsigned s_items[JPB_LEAF_SHARE ? kTravBlock * kMaxLeafPrims : 1];  // per warp: 32 * kMaxLeafPrims leaf-phase items
+    const bool share_leaves = JPB_LEAF_SHARE && !COUNT && sc.n_slots < (1 << 27) && sc.max_leaf_prims <= kMaxLeafPrims;
     int l_stack[kTraversalStack - kSmemStack];
     const TravStack stk{s_stack + threadIdx.x, l_stack, dropped};
     stk.init();
@@ -364,7 +423,11 @@ __device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* w
             }
         }
         const unsigned leaf_mask = COUNT ? __ballot_sync(full, trav_at_leaf(t)) : 0u;
-        if (trav_at_leaf(t)) trav_leaf_step<ANY_HIT, COUNT>(sc, t, stk, cnt, leaf_mask);
+        if (share_leaves) {
+            if (__any_sync(full, trav_at_leaf(t))) trav_leaf_phase_shared<ANY_HIT>(sc, t, stk, s_items + (threadIdx.x >> 5) * (32 * kMaxLeafPrims));
+        } else if (trav_at_leaf(t)) {
+            trav_leaf_step<ANY_HIT, COUNT>(sc, t, stk, cnt, leaf_mask);
+        }
         if (idx >= 0 && trav_done(t)) {
             io.store(idx, t.hit, t.tmax);
             idx = -1;

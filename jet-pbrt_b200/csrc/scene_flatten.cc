@@ -769,6 +769,7 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, Bv
         fn[f * kNodeStride + 1] = Float4{mx[1], mx[2], inf, inf};
         fn[f * kNodeStride + 2] = Float4{inf, -inf, -inf, -inf};
         fn[f * kNodeStride + 3] = Float4{IntAsFloat(LeafRef(bld.nodes[root].first, bld.nodes[root].count)), IntAsFloat(LeafRef(0, 0)), 0, 0};
+        hs.max_leaf_prims = bld.nodes[root].count;
     } else {
         stack.push_back(Item{root, emit_inner()});
         while (!stack.empty()) {
@@ -782,7 +783,7 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, Bv
             for (int k = 0; k < 2; ++k) {
                 const TmpNode& K = bld.nodes[kids[k]];
                 box_of(kids[k], mn[k], mx[k]);
-                if (K.count > 0) refs[k] = LeafRef(K.first, K.count);
+                if (K.count > 0) { refs[k] = LeafRef(K.first, K.count); hs.max_leaf_prims = std::max(hs.max_leaf_prims, K.count); }
                 else { child_flat[k] = emit_inner(); refs[k] = child_flat[k]; }
             }
             fn[it.flat * kNodeStride + 0] = Float4{mn[0][0], mn[0][1], mn[0][2], mx[0][0]};

@@ -29,6 +29,7 @@ struct HostScene {
     bool has_null_material = false;
     double bvh_build_seconds = 0;
     int bvh_builder = 0;  // 0 host binned SAH, 1 GPU LBVH, 2 host object-median rebuild (the SAH/LBVH tree was too deep)
+    int max_leaf_prims = 0;  // most primitives any leaf holds
     int bvh_depth = 0;    // levels of the tree (root = 1); at most kMaxBvhDepth
     double bvh_device_seconds = 0;  // GPU builder only: upload of the boxes + kernels + download of the tree
     size_t Bytes() const {
