@@ -145,11 +145,12 @@ int  jpbrt_render_multi(const jpbrt_scene_desc* desc, int integrator, int spp, u
  *   "stage_timing"     per-stage CUDA events (jpbrt_stats.ms_*); disables CUDA-graph replay
  *   "count_traversal"  node / primitive test counters (jpbrt_stats.box_tests ...); uses the counting kernel variants
  *   "use_graph"        replay a wavefront as one CUDA graph (default 1)
- *   "shade_math"       arithmetic of the shade stage (k_logic, k_shade): 0 = the reference's float expressions operation for
- *                      operation (no FMA contraction, IEEE division: BSDF values bit-comparable with the CPU code);
- *                      1 = FMA contraction + reciprocal-multiply division / sqrt (csrc/shade_fast.cu): f, pdf and directions
- *                      within north_star's 1e-5, ~25 % fewer instructions.  Which primitive a ray hits never depends on it:
- *                      generate / extend / connect are exact in both modes.  Default: 0, or JPBRT_SHADE_MATH=fast
+ *   "shade_math"       0 = the whole shade stage evaluates the reference's float expressions operation for operation (no FMA
+ *                      contraction, IEEE division); 1 = k_logic and the LAMBERT shade kernel come from a second build with FMA
+ *                      contraction + reciprocal-multiply division / sqrt (csrc/shade_fast.cu): measured within 3e-6 of the
+ *                      reference's f / pdf / directions (north_star's bar: 1e-5), -12 % of Cornell's shade stage.  Microfacet and
+ *                      delta vertices are shaded by the exact build in both modes (relaxed, their cancellation-prone expressions
+ *                      do not keep 1e-5), and so is every intersection.  Default: 0, or JPBRT_SHADE_MATH=fast
  *   "sort_rays"        reorder the rays of bounces >= 1 by (origin cell, direction octant) before they are traced:
  *                      0 off, else cell bits per axis 1..6, +16 to include the octant
  *   traversal tunables "trav_blocks" (5 or 6 resident blocks per SM; other values are clamped), "refill_min" (idle lanes

@@ -118,8 +118,8 @@ struct jpbrt_ctx {
     long long opt_band_pixels = 0;  // pixels per band of a wavefront (0 = default 2^20); >= the frame: no banding
     int opt_integrator = JPBRT_INTEGRATOR_PATH;  // jpbrt_integrator: which FIntegrator::Li the passes evaluate
     bool has_mirror = false;                     // Whitted traces a mirror vertex twice: the ray tree can grow
-    int opt_shade_math = g_default_shade_math;  // 0: the reference's float expressions bit for bit; 1: FMA + reciprocal division (shade_fast.cu)
-    int grid_logic_fast = 0, grid_shade_fast[4] = {0, 0, 0, 0};
+    int opt_shade_math = g_default_shade_math;  // 0: the reference's float expressions bit for bit; 1: k_logic + the Lambert kernel relaxed (shade_fast.cu)
+    int grid_logic_fast = 0, grid_shade_lambert_fast = 0;
     int opt_sort_rays = 0;    // 0 off; else cell bits per axis (1..6) + 16 x (direction octant in the key)
     int opt_trav_blocks = 6;  // resident blocks per SM the traversal kernels are compiled for: 6 (40 registers, default) or 5 (48)
     unsigned kinds_present = 0;  // bit k set: some material of the scene can build BSDF kind k
@@ -430,7 +430,7 @@ static int finish_upload(jpbrt_ctx* c, int device) {
     c->grid_shade_w[2] = occupancy_grid(c, k_shade<2, true>);
     c->grid_shade_w[3] = occupancy_grid(c, k_shade<3, true>);
     c->grid_logic_fast = c->sm_count * jpbrt_shade_fast::occupancy_logic();
-    for (int k = 0; k < 4; ++k) c->grid_shade_fast[k] = c->sm_count * jpbrt_shade_fast::occupancy_shade(k);
+    c->grid_shade_lambert_fast = c->sm_count * jpbrt_shade_fast::occupancy_shade_lambert();
     c->grid_connect = occupancy_grid(c, k_connect<false, 5>);
     c->grid_connect6 = occupancy_grid(c, k_connect<false, 6>);
     c->grid_connect_c = occupancy_grid(c, k_connect<true, 5>);
@@ -641,20 +641,16 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
             c->kernel_launches++;
             continue;
         }
-        if (c->opt_shade_math) {  // the same stage from the relaxed-arithmetic build (csrc/shade_fast.cu)
+        {
+            // option "shade_math" = 1: k_logic and the Lambert kernel come from the relaxed-arithmetic build (csrc/shade_fast.cu);
+            // the microfacet and delta kernels are the exact ones in both modes (their expressions do not keep 1e-5 when relaxed)
+            const bool relaxed = c->opt_shade_math != 0;
             StageTimer t(c, 2);
-            jpbrt_shade_fast::launch_logic(&p, it, c->grid_logic_fast, c->stream);
-            if (it < c->n_iters - 1 || c->hs.has_null_material) {
-                for (int k = 0; k < 4; ++k)
-                    if (c->kinds_present & (1u << k)) jpbrt_shade_fast::launch_shade(k, &p, it, c->grid_shade_fast[k], c->stream);
-                c->kernel_launches += __builtin_popcount(c->kinds_present);
-            }
-            c->kernel_launches++;
-        } else {
-            StageTimer t(c, 2);
-            k_logic<false><<<c->grid_logic, kBlock, 0, c->stream>>>(p, it);
+            if (relaxed) jpbrt_shade_fast::launch_logic(&p, it, c->grid_logic_fast, c->stream);
+            else k_logic<false><<<c->grid_logic, kBlock, 0, c->stream>>>(p, it);
             if (it < c->n_iters - 1 || c->hs.has_null_material) {  // at bounce == maxDepth nothing is left to shade
-                if (c->kinds_present & 1) k_shade<0><<<c->grid_shade[0], kBlock, 0, c->stream>>>(p, it);
+                if ((c->kinds_present & 1) && relaxed) jpbrt_shade_fast::launch_shade_lambert(&p, it, c->grid_shade_lambert_fast, c->stream);
+                else if (c->kinds_present & 1) k_shade<0><<<c->grid_shade[0], kBlock, 0, c->stream>>>(p, it);
                 if (c->kinds_present & 2) k_shade<1><<<c->grid_shade[1], kBlock, 0, c->stream>>>(p, it);
                 if (c->kinds_present & 4) k_shade<2><<<c->grid_shade[2], kBlock, 0, c->stream>>>(p, it);
                 if (c->kinds_present & 8) k_shade<3><<<c->grid_shade[3], kBlock, 0, c->stream>>>(p, it);
@@ -1284,7 +1280,8 @@ int jpbrt_unit_bsdf(const jpbrt_material* mat, int device, int n, const float* n
     float *d_sf = a.Out<float>((size_t)n * 3), *d_sp = a.Out<float>(n);
     int *d_fl = a.Out<int>(n), *d_dl = a.Out<int>(n);
     if (a.err == cudaSuccess && n > 0) {
-        if (g_default_shade_math) jpbrt_shade_fast::launch_unit_bsdf(unit_grid(n), d_m, n, d_n, d_wo, d_wi, d_u, d_ul, d_fe, d_pe, d_swi, d_sf, d_sp, d_fl, d_dl);
+        // the relaxed build only ever shades Lambert vertices: its unit kernel answers for matte materials, the exact one for the rest
+        if (g_default_shade_math && mat->type == JPBRT_MAT_MATTE) jpbrt_shade_fast::launch_unit_bsdf(unit_grid(n), d_m, n, d_n, d_wo, d_wi, d_u, d_ul, d_fe, d_pe, d_swi, d_sf, d_sp, d_fl, d_dl);
         else k_unit_bsdf<<<unit_grid(n), kBlock>>>(d_m, n, d_n, d_wo, d_wi, d_u, d_ul, d_fe, d_pe, d_swi, d_sf, d_sp, d_fl, d_dl);
     }
     rc = finish_unit(nullptr, a);

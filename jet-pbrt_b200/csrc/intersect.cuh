@@ -221,8 +221,11 @@ struct TravCounts {
     unsigned node_fetch = 0, prim_fetch = 0;  // distinct nodes / primitive records fetched per warp step (counted on one lane)
 };
 
+// Occlusion queries (k_connect) descend LEFT-first instead of near-first: FScene::Occluded only asks whether anything is hit
+// (scene.h:36-47), so any order gives the same boolean, and skipping the distance compare + child ordering measured
+// k_connect -5.8 % on the bunny scene, -5.6 % on 5 M triangles, -1.7 % Cornell, -1.1 % glossy (profiles/ab/r02_ab_anyhit.log).
 #ifndef JPB_ANYHIT_UNORDERED
-#define JPB_ANYHIT_UNORDERED 0  // A/B: shadow rays descend left-first instead of near-first (any hit answers the query)
+#define JPB_ANYHIT_UNORDERED 1
 #endif
 template <bool COUNT, bool ANY_HIT = false>
 __device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, const TravStack& stk, TravCounts& cnt, unsigned step_mask) {
@@ -303,6 +306,9 @@ __device__ __forceinline__ void trav_leaf_step(const DevScene& sc, Trav& t, cons
 // owner folds them in primitive order with the reference's strict `t < tmax`: exactly what the sequential loop accepts
 // (a later primitive wins only if it is strictly closer), hence the same hit record, ties included.
 // Called by ALL lanes of the warp, converged.  items: this warp's 32 * kMaxLeafPrims words of shared memory.
+// MEASURED AND REJECTED (profiles/ab/r02_ab_leafshare.log): bit-identical films, but k_extend +17 % (bunny) / +32 % (Cornell),
+// k_connect +21 % / +40 %: eight shuffles, two __syncwarp and the list traffic per phase cost more than the ~1.1 primitive
+// rounds they save -- the sequential per-lane loop stays.  Kept buildable (-DJPB_LEAF_SHARE=1) as the record of the experiment.
 #ifndef JPB_LEAF_SHARE
 #define JPB_LEAF_SHARE 0
 #endif

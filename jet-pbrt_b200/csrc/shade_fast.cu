@@ -1,6 +1,6 @@
-// shade_fast.cu -- the shade stage (k_logic, k_shade<KIND>) built a second time with relaxed arithmetic:
-// FMA contraction on, division and square root by reciprocal approximation (nvcc -fmad=true -prec-div=false
-// -prec-sqrt=false, set for THIS file by the Makefile).  See shade_fast.h.
+// shade_fast.cu -- k_logic and the LAMBERT shade kernel built a second time with relaxed arithmetic: FMA contraction on,
+// division and square root by reciprocal approximation (nvcc -fmad=true -prec-div=false -prec-sqrt=false, set for THIS
+// file by the Makefile).  See shade_fast.h for why only these two.
 //
 // The shared headers put everything in `namespace jpbrt`; this translation unit renames that namespace so that its
 // kernels and device functions are distinct symbols from the exact build's in csrc/c_api.cu.
@@ -25,27 +25,14 @@ static int blocks_per_sm(K kernel) {
 
 int occupancy_logic() { return blocks_per_sm(k_logic<false>); }
 
-int occupancy_shade(int kind) {
-    switch (kind) {
-    case 0: return blocks_per_sm(k_shade<0>);
-    case 1: return blocks_per_sm(k_shade<1>);
-    case 2: return blocks_per_sm(k_shade<2>);
-    default: return blocks_per_sm(k_shade<3>);
-    }
-}
+int occupancy_shade_lambert() { return blocks_per_sm(k_shade<KIND_LAMBERT>); }
 
 void launch_logic(const void* wf_params, int it, int grid, cudaStream_t stream) {
     k_logic<false><<<grid, kBlock, 0, stream>>>(*static_cast<const WfParams*>(wf_params), it);
 }
 
-void launch_shade(int kind, const void* wf_params, int it, int grid, cudaStream_t stream) {
-    const WfParams& p = *static_cast<const WfParams*>(wf_params);
-    switch (kind) {
-    case 0: k_shade<0><<<grid, kBlock, 0, stream>>>(p, it); break;
-    case 1: k_shade<1><<<grid, kBlock, 0, stream>>>(p, it); break;
-    case 2: k_shade<2><<<grid, kBlock, 0, stream>>>(p, it); break;
-    default: k_shade<3><<<grid, kBlock, 0, stream>>>(p, it); break;
-    }
+void launch_shade_lambert(const void* wf_params, int it, int grid, cudaStream_t stream) {
+    k_shade<KIND_LAMBERT><<<grid, kBlock, 0, stream>>>(*static_cast<const WfParams*>(wf_params), it);
 }
 
 void launch_unit_bsdf(int grid, const void* mat, int n, const float* nrm3, const float* wo3, const float* wi3, const float* u2, const float* ulobe,
