@@ -490,25 +490,30 @@ class Bench:
                 "sample": f"{w}x{h} x {n} spp of the same scene, FIntegrator::Render numthreads={threads}, {sec:.1f}s (BVH build {build:.2f}s excluded)"}
 
     def image_error(self, cfg):
-        """BASELINE.json metric, second half: image RMSE of the GPU render against the reference CPU render at EQUAL spp, next to
-        the CPU-vs-CPU figure for two independent seeds (the Monte Carlo noise floor).  Outside every timed region, at a reduced
-        resolution so that the CPU side costs about a second; the full-size comparisons are in tests/test_gpu_full_size.py."""
+        """BASELINE.json metric, second half: image error of the GPU render against the reference CPU render at EQUAL spp, next to
+        the CPU-vs-CPU figure between independently seeded reference renders (the Monte Carlo noise floor) -- K = 4 seeds on each
+        side, all pairs, because a single pair scatters by several per cent.  Outside every timed region, at a reduced resolution so
+        that the CPU side costs a few seconds; the comparisons at the configs' own size (1024^2 x 50 spp, K = 8) are in
+        tests/test_gpu_full_size.py."""
         np, pkg = self.np, self.pkg
         orc = self.ge.load_oracle()
         scene_name, scale, w, h, spp, desc = cfg
-        res, n = 256, 64
+        res, n, K = 256, 64, 4
         sc = pkg.HostScene.builtin(scene_name, res, max(1, res * h // w), scale if scene_name != "large" else 0.3)
         o = orc.Oracle("ref" if orc.have("ref") else "port").scene(sc)
         threads = os.cpu_count() or 1
-        cpu_a, _ = o.render(n, threads, seed=1234)
-        cpu_b, _ = o.render(n, threads, seed=4321)
-        gpu, _ = pkg.render(sc, n, seed=5, device=self.local)
+        cpu = [o.render(n, threads, seed=1234 + 97 * k)[0] for k in range(K)]
+        gpu = [pkg.render(sc, n, seed=5 + k, device=self.local)[0] for k in range(K)]
         rmse = lambda a, b: float(np.sqrt(np.mean((a - b) ** 2)))  # noqa: E731
         relmse = lambda a, b: float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))  # noqa: E731
-        return {"what": f"{res}x{sc.d.camera.height} x {n} spp, clamped linear film values",
-                "rmse_gpu_vs_cpu": rmse(gpu, cpu_a), "rmse_cpu_vs_cpu": rmse(cpu_b, cpu_a),
-                "relmse_gpu_vs_cpu": relmse(gpu, cpu_a), "relmse_cpu_vs_cpu": relmse(cpu_b, cpu_a),
-                "mean_gpu": float(gpu.mean()), "mean_cpu": float(cpu_a.mean())}
+        gc = [(g, c) for g in gpu for c in cpu]
+        cc = [(cpu[i], cpu[j]) for i in range(K) for j in range(K) if i != j]
+        out = {"what": f"{res}x{sc.d.camera.height} x {n} spp, clamped linear film values, K = {K} seeds per side, mean over all pairs",
+               "rmse_gpu_vs_cpu": float(np.mean([rmse(a, b) for a, b in gc])), "rmse_cpu_vs_cpu": float(np.mean([rmse(a, b) for a, b in cc])),
+               "relmse_gpu_vs_cpu": float(np.mean([relmse(a, b) for a, b in gc])), "relmse_cpu_vs_cpu": float(np.mean([relmse(a, b) for a, b in cc])),
+               "mean_gpu": float(np.mean([g.mean() for g in gpu])), "mean_cpu": float(np.mean([c.mean() for c in cpu]))}
+        out["relmse_ratio"] = out["relmse_gpu_vs_cpu"] / out["relmse_cpu_vs_cpu"]
+        return out
 
     # ---- N > 1: the reduced film against one GPU rendering everything -------------------------------------------------------
     def reduce_check(self, name, spp):

@@ -146,6 +146,13 @@ __device__ __forceinline__ float tr_G(float ax, float ay, const f3& wo, const f3
 __device__ __forceinline__ float tr_pdf(float ax, float ay, const f3& wo, const f3& wh) {  // sampleVisibleArea = true
     return tr_D(ax, ay, wh) * tr_G1(ax, ay, wo) * absdot(wo, wh) / fabsf(wo.z);
 }
+// The same with Lambda(wo) supplied by the caller: at a shading vertex wo is fixed while the lights (and the sampled
+// direction) vary, and Lambda(wo) -- two divisions and four square roots of exact arithmetic -- is the same number every
+// time.  The expressions and their order are unchanged, so the values are bit-identical to the forms above.
+__device__ __forceinline__ float tr_G(float ax, float ay, float lambda_o, const f3& wi) { return 1 / (1 + lambda_o + tr_lambda(ax, ay, wi)); }
+__device__ __forceinline__ float tr_pdf(float ax, float ay, float lambda_o, const f3& wo, const f3& wh) {
+    return tr_D(ax, ay, wh) * (1 / (1 + lambda_o)) * absdot(wo, wh) / fabsf(wo.z);
+}
 
 // TrowbridgeReitzSample11, microfacet.cc:256-303.  The reference's normal-incidence branch compares
 // against a double literal and calls the double-precision ::cos/::sin; both are kept.
@@ -225,7 +232,7 @@ __device__ __forceinline__ f3 bsdf_fresnel(const Bsdf& b, float cosI) {  // bsdf
 
 // FMicrofacetReflection::Evalf_Local, bsdf.cc:35-50.  Out of line: it is needed by NEE and by Sample_Local.
 template <bool CONDUCTOR>
-__device__ __noinline__ f3 microfacet_eval(const Bsdf& b, const f3& wo, const f3& wi) {
+__device__ __noinline__ f3 microfacet_eval(const Bsdf& b, const f3& wo, const f3& wi, float lambda_o) {
     float cosO = fabsf(wo.z), cosI = fabsf(wi.z);
     f3 wh = wi + wo;
     if (cosI == 0 || cosO == 0) return mk3(0, 0, 0);
@@ -233,18 +240,24 @@ __device__ __noinline__ f3 microfacet_eval(const Bsdf& b, const f3& wo, const f3
     wh = normalize(wh);
     const float cosF = dot(wi, face_forward(wh, mk3(0, 0, 1)));
     f3 F = CONDUCTOR ? fresnel_conductor(fabsf(cosF), b.eta3, b.T) : splat(fresnel_dielectric(cosF, b.eta_i, b.eta_t));  // bsdf.cc:15-24
-    return cmul(b.R * tr_D(b.ax, b.ay, wh) * tr_G(b.ax, b.ay, wo, wi), F) / (4 * cosI * cosO);
+    return cmul(b.R * tr_D(b.ax, b.ay, wh) * tr_G(b.ax, b.ay, lambda_o, wi), F) / (4 * cosI * cosO);
 }
 
-__device__ __forceinline__ f3 bsdf_eval_local(const Bsdf& b, const f3& wo, const f3& wi) {
+// Lambda(wo) of a microfacet BSDF (0 for the others): computed once per shading vertex, see tr_G above.
+__device__ __forceinline__ float bsdf_lambda_o(const Bsdf& b, const f3& wo) {
+    return (b.kind == K_MICROFACET_CONDUCTOR || b.kind == K_MICROFACET_DIELECTRIC) ? tr_lambda(b.ax, b.ay, wo) : 0.f;
+}
+
+__device__ __forceinline__ f3 bsdf_eval_local(const Bsdf& b, const f3& wo, const f3& wi, float lambda_o) {
     if (b.kind == K_LAMBERT) {  // bsdf.h:347-355
         if (!same_hemisphere(wo, wi)) return mk3(0, 0, 0);
         return b.R * JPB_INV_PI;
     }
-    if (b.kind == K_MICROFACET_CONDUCTOR) return microfacet_eval<true>(b, wo, wi);
-    if (b.kind == K_MICROFACET_DIELECTRIC) return microfacet_eval<false>(b, wo, wi);
+    if (b.kind == K_MICROFACET_CONDUCTOR) return microfacet_eval<true>(b, wo, wi, lambda_o);
+    if (b.kind == K_MICROFACET_DIELECTRIC) return microfacet_eval<false>(b, wo, wi, lambda_o);
     return mk3(0, 0, 0);  // delta BSDFs, bsdf.h:405-408,468-471
 }
+__device__ __forceinline__ f3 bsdf_eval_local(const Bsdf& b, const f3& wo, const f3& wi) { return bsdf_eval_local(b, wo, wi, bsdf_lambda_o(b, wo)); }
 
 __device__ __forceinline__ float bsdf_pdf_local(const Bsdf& b, const f3& wo, const f3& wi) {
     if (b.kind == K_LAMBERT) return same_hemisphere(wo, wi) ? fabsf(wi.z) * JPB_INV_PI : 0.f;  // bsdf.h:357-360
@@ -256,7 +269,7 @@ __device__ __forceinline__ float bsdf_pdf_local(const Bsdf& b, const f3& wo, con
     return 0.f;
 }
 
-__device__ __forceinline__ BsdfSample bsdf_sample_local(const Bsdf& b, const f3& wo, float u0, float u1) {
+__device__ __forceinline__ BsdfSample bsdf_sample_local(const Bsdf& b, const f3& wo, float u0, float u1, float lambda_o) {
     BsdfSample s;
     s.f = mk3(0, 0, 0);
     s.wi = mk3(0, 0, 1);
@@ -309,10 +322,13 @@ __device__ __forceinline__ BsdfSample bsdf_sample_local(const Bsdf& b, const f3&
     f3 wi = reflect(wo, wh);
     if (!same_hemisphere(wo, wi)) return s;
     s.wi = wi;
-    s.f = bsdf_eval_local(b, wo, wi);
-    s.pdf = tr_pdf(b.ax, b.ay, wo, wh) / (4 * dot(wo, wh));
+    s.f = bsdf_eval_local(b, wo, wi, lambda_o);
+    s.pdf = tr_pdf(b.ax, b.ay, lambda_o, wo, wh) / (4 * dot(wo, wh));
     s.flags = BSDF_REFLECTION | BSDF_GLOSSY;
     return s;
+}
+__device__ __forceinline__ BsdfSample bsdf_sample_local(const Bsdf& b, const f3& wo, float u0, float u1) {
+    return bsdf_sample_local(b, wo, u0, u1, bsdf_lambda_o(b, wo));
 }
 
 }  // namespace jpbrt

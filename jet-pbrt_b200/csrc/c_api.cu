@@ -541,6 +541,7 @@ int jpbrt_clear_film(jpbrt_ctx* c) {
     if (!c) return set_error(nullptr, JPBRT_ERR_INVALID, "ctx is null");
     CU_CHECK(c, cudaSetDevice(c->device));
     CU_CHECK(c, cudaMemsetAsync(c->film.ptr, 0, c->film.count * sizeof(float), c->stream));
+    c->film_reduced = false;  // a cleared film is a new partial sum: the next read reduces again (also on a rank that then renders nothing)
     return 0;
 }
 

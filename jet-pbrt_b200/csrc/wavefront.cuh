@@ -519,6 +519,9 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
                 if (KIND == KIND_DELTA && bsdf.kind != K_SPECULAR) bsdf.kind = K_FRESNEL_SPECULAR;
                 const Frame frame = hit_frame(sc, slot, N);
                 const f3 wo_l = to_local(frame, wo);
+                // Lambda(wo) of the Smith term is the same for every light of the vertex and for the sampled direction: once
+                // (bit-identical values; ~20 % fewer instructions per light in the microfacet kernels)
+                const float lambda_o = (KIND == KIND_MF_CONDUCTOR || KIND == KIND_MF_DIELECTRIC) ? tr_lambda(bsdf.ax, bsdf.ay, wo_l) : 0.f;
                 if (KIND != KIND_DELTA) {  // integrator.cc:357-372
                     float4 lu = make_float4(0, 0, 0, 0);
                     int lu_block = -1;
@@ -535,7 +538,7 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
                         bool valid = !(is_black(ls.Li) || ls.pdf == 0.f);
                         f3 f = mk3(0, 0, 0);
                         if (valid) {
-                            f = bsdf_eval_local(bsdf, wo_l, to_local(frame, ls.wi));
+                            f = bsdf_eval_local(bsdf, wo_l, to_local(frame, ls.wi), lambda_o);
                             valid = !is_black(f);
                         }
                         if (valid && fits) {
@@ -562,8 +565,8 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
                     }
                 }
                 if (!WHITTED) {
-                    BsdfSample bs = bsdf_sample_local(bsdf, wo_l, u0.y, u0.z);  // integrator.cc:375
-                    bs.wi = to_world(frame, bs.wi);                               // bsdf.h:296-302
+                    BsdfSample bs = bsdf_sample_local(bsdf, wo_l, u0.y, u0.z, lambda_o);  // integrator.cc:375
+                    bs.wi = to_world(frame, bs.wi);                                          // bsdf.h:296-302
                     if (!(is_black(bs.f) || bs.pdf == 0.f)) {
                         const bool spec = (bs.flags & BSDF_SPECULAR) != 0;
                         bool survive = true;
