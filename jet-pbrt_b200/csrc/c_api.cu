@@ -27,6 +27,12 @@
 
 using namespace jpbrt;
 
+// resident blocks per SM the default traversal kernels are compiled for (6 = 40 registers; A/B builds: -DJPB_TRAV_MINB=7)
+#ifndef JPB_TRAV_MINB
+#define JPB_TRAV_MINB 6
+#endif
+constexpr int kTravMinBlocks = JPB_TRAV_MINB;
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -416,7 +422,7 @@ static int finish_upload(jpbrt_ctx* c, int device) {
         return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)));
     c->grid_generate = occupancy_grid(c, k_generate);
     c->grid_extend = occupancy_grid(c, k_extend<false, 5>);
-    c->grid_extend6 = occupancy_grid(c, k_extend<false, 6>);
+    c->grid_extend6 = occupancy_grid(c, k_extend<false, kTravMinBlocks>);
     c->grid_extend_c = occupancy_grid(c, k_extend<true, 5>);
     c->grid_logic = occupancy_grid(c, k_logic<false>);
     c->grid_logic_w = occupancy_grid(c, k_logic<true>);
@@ -432,7 +438,7 @@ static int finish_upload(jpbrt_ctx* c, int device) {
     c->grid_logic_fast = c->sm_count * jpbrt_shade_fast::occupancy_logic();
     c->grid_shade_lambert_fast = c->sm_count * jpbrt_shade_fast::occupancy_shade_lambert();
     c->grid_connect = occupancy_grid(c, k_connect<false, 5>);
-    c->grid_connect6 = occupancy_grid(c, k_connect<false, 6>);
+    c->grid_connect6 = occupancy_grid(c, k_connect<false, kTravMinBlocks>);
     c->grid_connect_c = occupancy_grid(c, k_connect<true, 5>);
     c->grid_finalize = occupancy_grid(c, k_finalize);
     rc = jpbrt_clear_film(c);
@@ -615,8 +621,8 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
         {
             StageTimer t(c, 1);
             if (count) k_extend<true, 5><<<c->grid_extend_c, kBlock, 0, c->stream>>>(p, it);
-            else if (sorting && it > 0) k_extend<false, 6, true><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
-            else if (c->opt_trav_blocks >= 6) k_extend<false, 6><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
+            else if (sorting && it > 0) k_extend<false, kTravMinBlocks, true><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
+            else if (c->opt_trav_blocks >= 6) k_extend<false, kTravMinBlocks><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
             else k_extend<false, 5><<<c->grid_extend, kBlock, 0, c->stream>>>(p, it);
             c->kernel_launches++;
         }
@@ -638,7 +644,7 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
             }
             StageTimer t(c, 3);
             if (count) k_connect<true, 5><<<c->grid_connect_c, kBlock, 0, c->stream>>>(p, it);
-            else k_connect<false, 6><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
+            else k_connect<false, kTravMinBlocks><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
             c->kernel_launches++;
             continue;
         }
@@ -662,7 +668,7 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
         if (it < c->n_iters - 1 || c->hs.has_null_material) {  // no NEE at bounce == maxDepth (integrator.cc:340)
             StageTimer t(c, 3);
             if (count) k_connect<true, 5><<<c->grid_connect_c, kBlock, 0, c->stream>>>(p, it);
-            else if (c->opt_trav_blocks >= 6) k_connect<false, 6><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
+            else if (c->opt_trav_blocks >= 6) k_connect<false, kTravMinBlocks><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
             else k_connect<false, 5><<<c->grid_connect, kBlock, 0, c->stream>>>(p, it);
             c->kernel_launches++;
         }
