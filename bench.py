@@ -17,7 +17,6 @@ The ONE JSON line rank 0 prints:
           flattened scene from pinned host memory, renders, reduces, finalizes, reads the film back (wall clock).
   strong: STRONG scaling -- the headline scene at 50 spp TOTAL and the 3840x2160 Cornell box at 4096 spp TOTAL
           (BASELINE configs[4]) split over the N ranks, with the film reduce timed on its own.
-  shade_math_fast: the headline workload again with the optional relaxed-arithmetic shade build (not the default).
   configs (N = 1): every other BASELINE config (cornell, large at 64 spp, glossy at 64 spp) with value / e2e / roofline /
           cpu_baseline / image error, measured by the same code.
   roofline : the closest-hit traversal kernel (k_extend) against ceilings MEASURED in this run on this GPU by
@@ -256,7 +255,7 @@ class Bench:
         return sc, ctx, upload_s
 
     # ---- one configuration --------------------------------------------------------------------------------------------
-    def measure(self, name, mode, steps, warmup, spp_override=0, full=True, sample_clocks=False, image_error=True, cpu=True, spp_warm=0, shade_math=0):
+    def measure(self, name, mode, steps, warmup, spp_override=0, full=True, sample_clocks=False, image_error=True, cpu=True, spp_warm=0):
         """mode "weak": every rank renders the config's spp (total = N x spp); "strong": the config's spp split over the ranks."""
         torch, np, pkg = self.torch, self.np, self.pkg
         cfg = list(CONFIGS[name])
@@ -264,8 +263,6 @@ class Bench:
             cfg[4] = spp_override
         scene_name, scale, w, h, spp, desc = cfg
         sc, ctx, upload_s = self.open(name, cfg)
-        if shade_math:
-            ctx.set_option("shade_math", shade_math)
         world, rank = self.world, self.rank
         if mode == "weak":
             begin, count, spp_total = rank * spp, spp, spp * world
@@ -554,12 +551,6 @@ def run_b200(args, emit):
     b.barrier()
     name = args.config
     head = b.measure(name, "weak", args.steps, args.warmup, spp_override=args.spp, full=True, sample_clocks=True)
-    # ---- the same headline workload with the relaxed-arithmetic shade build (option "shade_math" = 1; NOT the default: its BSDF
-    # values agree with the reference to 1e-5 for 99.9 % of inputs and to 3e-4 in the cancellation-prone tail, tests/test_gpu_shade_fast.py)
-    fast = None
-    if not args.quick:
-        f = b.measure(name, "weak", max(3, min(args.steps, 10)), 3, spp_override=args.spp, full=False, cpu=False, shade_math=1)
-        fast = {k: f.get(k) for k in ("value", "unit", "ms_per_step", "stages_ms_per_step", "steps")}
     # ---- strong scaling: fixed total work split over the ranks ----
     strong = {}
     if not args.quick:
@@ -601,8 +592,6 @@ def run_b200(args, emit):
         for k in ("cpu_baseline", "image_error_vs_cpu"):
             if k in head:
                 line[k] = head[k]
-        if fast:
-            line["shade_math_fast"] = fast
         if strong:
             line["strong"] = strong
         if configs:

@@ -145,12 +145,6 @@ int  jpbrt_render_multi(const jpbrt_scene_desc* desc, int integrator, int spp, u
  *   "stage_timing"     per-stage CUDA events (jpbrt_stats.ms_*); disables CUDA-graph replay
  *   "count_traversal"  node / primitive test counters (jpbrt_stats.box_tests ...); uses the counting kernel variants
  *   "use_graph"        replay a wavefront as one CUDA graph (default 1)
- *   "shade_math"       0 = the whole shade stage evaluates the reference's float expressions operation for operation (no FMA
- *                      contraction, IEEE division); 1 = k_logic and the LAMBERT shade kernel come from a second build with FMA
- *                      contraction + reciprocal-multiply division / sqrt (csrc/shade_fast.cu): measured within 3e-6 of the
- *                      reference's f / pdf / directions (north_star's bar: 1e-5), -12 % of Cornell's shade stage.  Microfacet and
- *                      delta vertices are shaded by the exact build in both modes (relaxed, their cancellation-prone expressions
- *                      do not keep 1e-5), and so is every intersection.  Default: 0, or JPBRT_SHADE_MATH=fast
  *   "sort_rays"        reorder the rays of bounces >= 1 by (origin cell, direction octant) before they are traced:
  *                      0 off, else cell bits per axis 1..6, +16 to include the octant
  *   traversal tunables "trav_blocks" (5 or 6 resident blocks per SM; other values are clamped), "refill_min" (idle lanes
@@ -159,8 +153,6 @@ int  jpbrt_render_multi(const jpbrt_scene_desc* desc, int integrator, int spp, u
  * The film is accumulated with float atomics: a render is reproducible up to float summation order (<= 1e-6 relative),
  * not bit for bit; the PATHS depend only on (seed, pixel, sample index). */
 int jpbrt_set_option(jpbrt_ctx* ctx, const char* name, long long value);
-/* Process-wide defaults: "shade_math" -- what new contexts start with and what the context-less jpbrt_unit_bsdf uses. */
-int jpbrt_set_default_option(const char* name, long long value);
 
 typedef struct jpbrt_stats {
     uint64_t samples;          /* camera paths started */

@@ -51,7 +51,7 @@ EXPORTS = [
     "jpbrt_unit_bsdf", "jpbrt_unit_bsdf_ex", "jpbrt_unit_light_sample", "jpbrt_unit_emitted", "jpbrt_unit_generate_rays",
     "jpbrt_unit_rng_block", "jpbrt_unit_philox_raw", "jpbrt_scene_info", "jpbrt_scene_builtin", "jpbrt_scene_get_desc",
     "jpbrt_comm_unique_id", "jpbrt_comm_init", "jpbrt_comm_rank", "jpbrt_comm_size", "jpbrt_reduce_film", "jpbrt_sample_partition",
-    "jpbrt_render_multi", "jpbrt_set_default_option", "jpbrt_load_obj_triangles", "jpbrt_scene_free", "jpbrt_save_image", "jpbrt_version", "jpbrt_device_count", "jpbrt_debug_flatten", "jpbrt_debug_ctx_table",
+    "jpbrt_render_multi", "jpbrt_load_obj_triangles", "jpbrt_scene_free", "jpbrt_save_image", "jpbrt_version", "jpbrt_device_count", "jpbrt_debug_flatten", "jpbrt_debug_ctx_table",
 ]
 
 
@@ -120,7 +120,6 @@ def _load():
     lib.jpbrt_sample_partition.argtypes = [I, I, I, IP, IP]
     lib.jpbrt_sample_partition.restype = None
     lib.jpbrt_render_multi.argtypes = [C.POINTER(SceneDesc), I, I, C.c_uint64, I, F, C.POINTER(C.c_double), C.POINTER(C.c_double)]
-    lib.jpbrt_set_default_option.argtypes = [C.c_char_p, C.c_longlong]
     lib.jpbrt_load_obj_triangles.argtypes = [C.c_char_p, I, F, C.c_float, F, C.c_longlong]
     lib.jpbrt_load_obj_triangles.restype = C.c_longlong
     return lib
@@ -415,10 +414,6 @@ def load_obj_triangles(filename: str, flip_handedness=False, offset=(0, 0, 0), s
     out = np.empty((n, 3, 3), np.float32)
     lib.jpbrt_load_obj_triangles(filename.encode(), int(flip_handedness), _f(off), scale, _f(out), n)
     return out
-
-
-def set_default_option(name: str, value: int):
-    _check(lib.jpbrt_set_default_option(name.encode(), value))
 
 
 def device_count() -> int:

@@ -21,7 +21,6 @@
 #include "bvh_build.cuh"
 #include "wavefront.cuh"
 #include "unit_shade.cuh"
-#include "shade_fast.h"
 
 #include <cub/device/device_scan.cuh>
 
@@ -36,13 +35,6 @@ constexpr int kTravMinBlocks = JPB_TRAV_MINB;
 namespace {
 
 thread_local std::string g_last_error;
-
-// Process-wide default of the "shade_math" option (0 exact, 1 fast): what new contexts start with and what the
-// context-less unit entry points (jpbrt_unit_bsdf) use.  Environment JPBRT_SHADE_MATH=fast|exact sets it at load.
-int g_default_shade_math = [] {
-    const char* v = getenv("JPBRT_SHADE_MATH");
-    return (v && (!strcmp(v, "fast") || !strcmp(v, "1"))) ? 1 : 0;
-}();
 
 int set_error(jpbrt_ctx* ctx, int code, const char* fmt, ...);
 
@@ -124,8 +116,6 @@ struct jpbrt_ctx {
     long long opt_band_pixels = 0;  // pixels per band of a wavefront (0 = default 2^20); >= the frame: no banding
     int opt_integrator = JPBRT_INTEGRATOR_PATH;  // jpbrt_integrator: which FIntegrator::Li the passes evaluate
     bool has_mirror = false;                     // Whitted traces a mirror vertex twice: the ray tree can grow
-    int opt_shade_math = g_default_shade_math;  // 0: the reference's float expressions bit for bit; 1: k_logic + the Lambert kernel relaxed (shade_fast.cu)
-    int grid_logic_fast = 0, grid_shade_lambert_fast = 0;
     int opt_sort_rays = 0;    // 0 off; else cell bits per axis (1..6) + 16 x (direction octant in the key)
     int opt_trav_blocks = 6;  // resident blocks per SM the traversal kernels are compiled for: 6 (40 registers, default) or 5 (48)
     unsigned kinds_present = 0;  // bit k set: some material of the scene can build BSDF kind k
@@ -435,8 +425,6 @@ static int finish_upload(jpbrt_ctx* c, int device) {
     c->grid_shade_w[1] = occupancy_grid(c, k_shade<1, true>);
     c->grid_shade_w[2] = occupancy_grid(c, k_shade<2, true>);
     c->grid_shade_w[3] = occupancy_grid(c, k_shade<3, true>);
-    c->grid_logic_fast = c->sm_count * jpbrt_shade_fast::occupancy_logic();
-    c->grid_shade_lambert_fast = c->sm_count * jpbrt_shade_fast::occupancy_shade_lambert();
     c->grid_connect = occupancy_grid(c, k_connect<false, 5>);
     c->grid_connect6 = occupancy_grid(c, k_connect<false, kTravMinBlocks>);
     c->grid_connect_c = occupancy_grid(c, k_connect<true, 5>);
@@ -562,19 +550,12 @@ int jpbrt_reset_stats(jpbrt_ctx* c) {
     return 0;
 }
 
-int jpbrt_set_default_option(const char* name, long long value) {
-    if (!name) return set_error(nullptr, JPBRT_ERR_INVALID, "null argument");
-    if (!strcmp(name, "shade_math")) { g_default_shade_math = value != 0; return 0; }
-    return set_error(nullptr, JPBRT_ERR_INVALID, "unknown default option '%s'", name);
-}
-
 int jpbrt_set_option(jpbrt_ctx* c, const char* name, long long value) {
     if (!c || !name) return set_error(c, JPBRT_ERR_INVALID, "null argument");
     if (!strcmp(name, "paths_in_flight")) { c->opt_paths_in_flight = value; return 0; }
     if (!strcmp(name, "stage_timing")) { c->opt_stage_timing = value != 0; return 0; }
     if (!strcmp(name, "count_traversal")) { c->opt_count_traversal = value != 0; return 0; }
     if (!strcmp(name, "trav_blocks")) { c->opt_trav_blocks = value >= 6 ? 6 : 5; return 0; }
-    if (!strcmp(name, "shade_math")) { c->opt_shade_math = value != 0; return 0; }
     if (!strcmp(name, "sort_rays")) {
         if (value != 0 && ((value & 15) < 1 || (value & 15) > 6 || (value >> 5) != 0)) return set_error(c, JPBRT_ERR_INVALID, "sort_rays: cell bits 1..6 (+16 for the direction octant), got %lld", value);
         c->opt_sort_rays = (int)value;
@@ -649,15 +630,10 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
             continue;
         }
         {
-            // option "shade_math" = 1: k_logic and the Lambert kernel come from the relaxed-arithmetic build (csrc/shade_fast.cu);
-            // the microfacet and delta kernels are the exact ones in both modes (their expressions do not keep 1e-5 when relaxed)
-            const bool relaxed = c->opt_shade_math != 0;
             StageTimer t(c, 2);
-            if (relaxed) jpbrt_shade_fast::launch_logic(&p, it, c->grid_logic_fast, c->stream);
-            else k_logic<false><<<c->grid_logic, kBlock, 0, c->stream>>>(p, it);
+            k_logic<false><<<c->grid_logic, kBlock, 0, c->stream>>>(p, it);
             if (it < c->n_iters - 1 || c->hs.has_null_material) {  // at bounce == maxDepth nothing is left to shade
-                if ((c->kinds_present & 1) && relaxed) jpbrt_shade_fast::launch_shade_lambert(&p, it, c->grid_shade_lambert_fast, c->stream);
-                else if (c->kinds_present & 1) k_shade<0><<<c->grid_shade[0], kBlock, 0, c->stream>>>(p, it);
+                if (c->kinds_present & 1) k_shade<0><<<c->grid_shade[0], kBlock, 0, c->stream>>>(p, it);
                 if (c->kinds_present & 2) k_shade<1><<<c->grid_shade[1], kBlock, 0, c->stream>>>(p, it);
                 if (c->kinds_present & 4) k_shade<2><<<c->grid_shade[2], kBlock, 0, c->stream>>>(p, it);
                 if (c->kinds_present & 8) k_shade<3><<<c->grid_shade[3], kBlock, 0, c->stream>>>(p, it);
@@ -711,7 +687,7 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
     const bool count = c->opt_count_traversal;
     // Graph replay needs a launch sequence that never changes: no per-launch events, no counting variant.
     const bool use_graph = c->opt_use_graph && !c->opt_stage_timing && !count;
-    const int graph_key = ((((c->opt_integrator * 16 + c->opt_trav_blocks) * 64 + (c->opt_refill_min + 1)) * 64 + (c->opt_min_inner + 1)) * 64 + c->opt_sort_rays) * 2 + c->opt_shade_math;
+    const int graph_key = (((c->opt_integrator * 16 + c->opt_trav_blocks) * 64 + (c->opt_refill_min + 1)) * 64 + (c->opt_min_inner + 1)) * 64 + c->opt_sort_rays;
     if (use_graph && (c->wave_graph == nullptr || c->wave_graph_key != graph_key)) {
         if (c->wave_graph) { cudaGraphExecDestroy(c->wave_graph); c->wave_graph = nullptr; }
         cudaGraph_t graph = nullptr;
@@ -1286,11 +1262,8 @@ int jpbrt_unit_bsdf(const jpbrt_material* mat, int device, int n, const float* n
     float *d_fe = a.Out<float>((size_t)n * 3), *d_pe = a.Out<float>(n), *d_swi = a.Out<float>((size_t)n * 3);
     float *d_sf = a.Out<float>((size_t)n * 3), *d_sp = a.Out<float>(n);
     int *d_fl = a.Out<int>(n), *d_dl = a.Out<int>(n);
-    if (a.err == cudaSuccess && n > 0) {
-        // the relaxed build only ever shades Lambert vertices: its unit kernel answers for matte materials, the exact one for the rest
-        if (g_default_shade_math && mat->type == JPBRT_MAT_MATTE) jpbrt_shade_fast::launch_unit_bsdf(unit_grid(n), d_m, n, d_n, d_wo, d_wi, d_u, d_ul, d_fe, d_pe, d_swi, d_sf, d_sp, d_fl, d_dl);
-        else k_unit_bsdf<<<unit_grid(n), kBlock>>>(d_m, n, d_n, d_wo, d_wi, d_u, d_ul, d_fe, d_pe, d_swi, d_sf, d_sp, d_fl, d_dl);
-    }
+    if (a.err == cudaSuccess && n > 0)
+        k_unit_bsdf<<<unit_grid(n), kBlock>>>(d_m, n, d_n, d_wo, d_wi, d_u, d_ul, d_fe, d_pe, d_swi, d_sf, d_sp, d_fl, d_dl);
     rc = finish_unit(nullptr, a);
     if (rc != 0) return rc;
     a.Back(f_eval3, d_fe, (size_t)n * 3); a.Back(pdf_eval, d_pe, n); a.Back(s_wi3, d_swi, (size_t)n * 3);
@@ -1329,10 +1302,7 @@ int jpbrt_unit_light_sample(jpbrt_ctx* c, int light, int n, const float* pos3, c
     Arena a;
     const float *d_p = a.In(pos3, (size_t)n * 3), *d_n = a.In(nrm3, (size_t)n * 3), *d_u = a.In(u2, (size_t)n * 2);
     float *d_lp = a.Out<float>((size_t)n * 3), *d_wi = a.Out<float>((size_t)n * 3), *d_pdf = a.Out<float>(n), *d_li = a.Out<float>((size_t)n * 3);
-    if (a.err == cudaSuccess && n > 0) {
-        if (c->opt_shade_math) jpbrt_shade_fast::launch_unit_light_sample(unit_grid(n), &c->dsc, light, n, d_p, d_n, d_u, d_lp, d_wi, d_pdf, d_li);
-        else k_unit_light_sample<<<unit_grid(n), kBlock>>>(c->dsc, light, n, d_p, d_n, d_u, d_lp, d_wi, d_pdf, d_li);
-    }
+    if (a.err == cudaSuccess && n > 0) k_unit_light_sample<<<unit_grid(n), kBlock>>>(c->dsc, light, n, d_p, d_n, d_u, d_lp, d_wi, d_pdf, d_li);
     int rc = finish_unit(c, a);
     if (rc != 0) return rc;
     a.Back(lpos3, d_lp, (size_t)n * 3); a.Back(wi3, d_wi, (size_t)n * 3); a.Back(pdf, d_pdf, n); a.Back(Li3, d_li, (size_t)n * 3);

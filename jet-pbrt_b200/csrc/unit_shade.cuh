@@ -1,6 +1,5 @@
 // unit_shade.cuh -- the shade stage's device functions (BSDF build / Evalf / Pdf / Sample, light sampling) on
-// caller-supplied arrays, for the parity tests.  A header because two translation units instantiate it: csrc/c_api.cu
-// (exact arithmetic, -fmad=false) and csrc/shade_fast.cu (option "shade_math" = fast).
+// caller-supplied arrays, for the parity tests (jpbrt_unit_bsdf, jpbrt_unit_light_sample in csrc/c_api.cu).
 #pragma once
 
 #include "bsdf.cuh"

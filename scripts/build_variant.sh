@@ -8,6 +8,5 @@ out=build/variants/$name
 mkdir -p $out
 make -s build/scene.o build/scenes_builtin.o build/capi_host.o build/render.o build/scene_flatten.o
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -fmad=false -Xcompiler -fPIC -Xcompiler -O2 "$@" -Xptxas -v -c csrc/c_api.cu -o $out/c_api.o 2> $out/ptxas.log
-make -s build/shade_fast.o
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libjetpbrt_b200.so build/scene.o build/scenes_builtin.o build/capi_host.o build/render.o build/scene_flatten.o $out/c_api.o build/shade_fast.o -Xcompiler -pthread -Xlinker --exclude-libs -Xlinker ALL
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libjetpbrt_b200.so build/scene.o build/scenes_builtin.o build/capi_host.o build/render.o build/scene_flatten.o $out/c_api.o -Xcompiler -pthread -Xlinker --exclude-libs -Xlinker ALL
 grep -E "k_shadeILi0ELb0|k_extendILb0ELi6" -A2 $out/ptxas.log | grep -E "Used|spill" | sed 's/ptxas info    ://'
