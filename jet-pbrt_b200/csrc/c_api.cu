@@ -324,7 +324,7 @@ WfParams make_params(jpbrt_ctx* c) {
     p.stats = c->dstats.ptr;
     p.args = c->pass_args.ptr;
     p.npix = c->hs.width * c->hs.height;
-    p.blocks_per_bounce = rng_blocks_per_bounce(c->dsc.n_lights);
+    p.blocks_per_bounce = rng_blocks_per_bounce(c->dsc.n_nee_lights);  // black lights own no sampler dimensions: nothing ever reads them
     p.shadow_capacity = (int)std::min<size_t>(c->sh_o.count, 0x7fffffff);
     // B200 sweep (profiles/r01_sweep_min_inner.txt): trees of thousands of nodes want min_inner 8 / refill 16 (bunny scene +14 %,
     // 5 M triangles +22 % over waiting for every lane); the 16- and 33-node trees of Cornell / glossy want 4 / 20 (+1 %).

@@ -5,10 +5,12 @@
 // (seed, pixel, sample index, block) through Philox4x32-10 (Salmon et al., SC'11), so a sample's
 // path does not depend on which GPU, pass or thread traces it.
 //
-// Dimension schedule, 4 numbers per block, B = 1 + ceil(nLights / 2):
+// Dimension schedule, 4 numbers per block, B = 1 + ceil(nNee / 2) where nNee counts the lights whose
+// colour is not black (a black light can never contribute, integrator.cc:362: its numbers would be drawn and thrown away):
 //   block 0                       : film jitter (x, y, -, -)            integrator.cc:100
 //   block 1 + b*B                 : bounce b: (lobe, bsdf.x, bsdf.y, rr) material.cc:14, integrator.cc:375,386
-//   block 1 + b*B + 1 + j/2       : bounce b: light j's (u.x, u.y) at words 2*(j%2)  integrator.cc:361
+//   block 1 + b*B + 1 + k/2       : bounce b: the k-th non-black light's (u.x, u.y) at words 2*(k%2)  integrator.cc:361
+// (Cornell: [black env, tri, tri] -> both triangle lights share ONE block: two Philox evaluations per vertex instead of three.)
 #pragma once
 
 #include <stdint.h>
@@ -43,6 +45,6 @@ __device__ __forceinline__ float4 rng_block(const RngKey& key, uint32_t pixel, u
     return make_float4(u32_to_unit(r.x), u32_to_unit(r.y), u32_to_unit(r.z), u32_to_unit(r.w));
 }
 
-__host__ __device__ __forceinline__ int rng_blocks_per_bounce(int n_lights) { return 1 + (n_lights + 1) / 2; }
+__host__ __device__ __forceinline__ int rng_blocks_per_bounce(int n_nee_lights) { return 1 + (n_nee_lights + 1) / 2; }
 
 }  // namespace jpbrt

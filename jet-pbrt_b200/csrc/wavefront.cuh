@@ -527,11 +527,11 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
                     int lu_block = -1;
                     for (int k = 0; k < sc.n_nee_lights; ++k) {  // black lights are skipped (integrator.cc:362), not sampled
                         const int j = __ldg(sc.nee_lights + k);
-                        if ((j >> 1) != lu_block) {
-                            lu_block = j >> 1;
+                        if ((k >> 1) != lu_block) {  // the k-th non-black light's pair: block k/2, words 2*(k%2)  (rng.cuh)
+                            lu_block = k >> 1;
                             lu = rng_block(key, (uint32_t)pixel, (uint32_t)sample, blk + 1u + (uint32_t)lu_block, node);
                         }
-                        const float ux = (j & 1) ? lu.z : lu.x, uy = (j & 1) ? lu.w : lu.y;
+                        const float ux = (k & 1) ? lu.z : lu.x, uy = (k & 1) ? lu.w : lu.y;
                         const long long si = (long long)k * n_vertices + kind_base + qi;  // this (vertex, light)'s slot
                         const bool fits = si < p.shadow_capacity;
                         const LightSample ls = sample_light(sc, j, P, N, ux, uy);
