@@ -37,7 +37,8 @@ def test_same_paths_as_counter_oracle(pkg, port, gpu, name, scale, res, spp):
     # extension rays are fewer only by the final, contribution-free segment the GPU does not trace
     assert abs(st["shaded_vertices"] - cnt["vertices"]) <= 2e-3 * cnt["vertices"]
     assert abs(st["shadow_rays"] - cnt["shadow_rays"]) <= 2e-3 * cnt["shadow_rays"]
-    assert st["extension_rays"] <= cnt["ext_rays"] and st["extension_rays"] >= 0.6 * cnt["ext_rays"]
+    # (<= up to the same 2e-3: a path whose roulette draw sits within a rounding error of q lives one bounce longer on one side)
+    assert 0.6 * cnt["ext_rays"] <= st["extension_rays"] <= (1 + 2e-3) * cnt["ext_rays"]
     assert st["box_tests"] > 0 and st["prim_tests"] > 0
     ctx.close()
 
