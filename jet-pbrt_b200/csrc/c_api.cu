@@ -331,7 +331,7 @@ WfParams make_params(jpbrt_ctx* c) {
     const bool tiny_tree = c->dsc.n_nodes <= 64;
     p.refill_min = c->opt_refill_min > 0 ? c->opt_refill_min : (tiny_tree ? 20 : 16);
     p.min_inner = c->opt_min_inner >= 0 ? c->opt_min_inner : (tiny_tree ? 4 : 8);
-    const bool sorting = c->opt_sort_rays != 0 && c->sort_kr.ptr && (c->opt_integrator == JPBRT_INTEGRATOR_PATH || c->opt_integrator == JPBRT_INTEGRATOR_PATH_RECURSIVE);
+    const bool sorting = c->opt_sort_rays != 0 && c->sort_kr.ptr && c->hs.bvh_depth <= kMaxBvhDepth && (c->opt_integrator == JPBRT_INTEGRATOR_PATH || c->opt_integrator == JPBRT_INTEGRATOR_PATH_RECURSIVE);
     if (sorting) {
         p.sort_bins = c->sort_bins.ptr;
         p.sort_start = c->sort_start.ptr;
@@ -588,6 +588,9 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
     const bool whitted = c->opt_integrator == JPBRT_INTEGRATOR_WHITTED;
     const bool debug = c->opt_integrator == JPBRT_INTEGRATOR_DEBUG;
     const bool sorting = p.sort_bins != nullptr;
+    // the 6-block traversal kernels run WITHOUT the full-stack test of every push (intersect.cuh: GUARD): only for trees whose
+    // depth the uploader verified; a deeper tree (test hook) takes the guarded 5-block kernels, which count what they lose
+    const bool fast6 = c->opt_trav_blocks >= 6 && c->hs.bvh_depth <= kMaxBvhDepth;
     for (int it = 0; it < (debug ? 1 : c->n_iters); ++it) {
         if (sorting && it > 0) {
             // reordering: bins were counted while bounce it-1 appended its rays; prefix-sum them, place every ray, clear the bins
@@ -602,8 +605,8 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
         {
             StageTimer t(c, 1);
             if (count) k_extend<true, 5><<<c->grid_extend_c, kBlock, 0, c->stream>>>(p, it);
-            else if (sorting && it > 0) k_extend<false, kTravMinBlocks, true><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
-            else if (c->opt_trav_blocks >= 6) k_extend<false, kTravMinBlocks><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
+            else if (sorting && it > 0 && fast6) k_extend<false, kTravMinBlocks, true><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
+            else if (fast6) k_extend<false, kTravMinBlocks><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
             else k_extend<false, 5><<<c->grid_extend, kBlock, 0, c->stream>>>(p, it);
             c->kernel_launches++;
         }
@@ -625,7 +628,8 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
             }
             StageTimer t(c, 3);
             if (count) k_connect<true, 5><<<c->grid_connect_c, kBlock, 0, c->stream>>>(p, it);
-            else k_connect<false, kTravMinBlocks><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
+            else if (fast6) k_connect<false, kTravMinBlocks><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
+            else k_connect<false, 5><<<c->grid_connect, kBlock, 0, c->stream>>>(p, it);
             c->kernel_launches++;
             continue;
         }
@@ -644,7 +648,7 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
         if (it < c->n_iters - 1 || c->hs.has_null_material) {  // no NEE at bounce == maxDepth (integrator.cc:340)
             StageTimer t(c, 3);
             if (count) k_connect<true, 5><<<c->grid_connect_c, kBlock, 0, c->stream>>>(p, it);
-            else if (c->opt_trav_blocks >= 6) k_connect<false, kTravMinBlocks><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
+            else if (fast6) k_connect<false, kTravMinBlocks><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
             else k_connect<false, 5><<<c->grid_connect, kBlock, 0, c->stream>>>(p, it);
             c->kernel_launches++;
         }

@@ -153,6 +153,10 @@ constexpr int kTravBlock = 256;        // threads per block of every kernel that
 #ifndef JPB_SMEM_STACK
 #define JPB_SMEM_STACK 0
 #endif
+// GUARD (template parameter of the walk): test every push against the end of the stack and count what does not fit.  The
+// uploader bounds the depth of every tree it installs (c_api.cu: kMaxBvhDepth < kTraversalStack), and a walk's stack never
+// holds more entries than the tree has levels, so the production kernels run unguarded; the COUNT variants, the 5-block
+// variants and any scene installed with a deeper tree (test hook JPBRT_TEST_ALLOW_DEEP_BVH) keep the guard and its counter.
 constexpr int kSmemStack = JPB_SMEM_STACK;
 static_assert(kSmemStack >= 0 && kSmemStack < kTraversalStack, "JPB_SMEM_STACK out of range");
 
@@ -174,11 +178,12 @@ struct TravStack {
     __device__ __forceinline__ void init() const {
         if (kSmemStack > 0) sm[0] = kTravDone; else lm[0] = kTravDone;
     }
+    template <bool GUARD>
     __device__ __forceinline__ void push(int& sp, int v) const {
         if (kSmemStack > 0 && sp < kSmemStack) {
             sm[sp * kTravBlock] = v;
             ++sp;
-        } else if (sp < kTraversalStack) {
+        } else if (!GUARD || sp < kTraversalStack) {
             lm[sp - kSmemStack] = v;
             ++sp;
         } else if (dropped) {
@@ -227,7 +232,7 @@ struct TravCounts {
 #ifndef JPB_ANYHIT_UNORDERED
 #define JPB_ANYHIT_UNORDERED 1
 #endif
-template <bool COUNT, bool ANY_HIT = false>
+template <bool COUNT, bool ANY_HIT = false, bool GUARD = true>
 __device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, const TravStack& stk, TravCounts& cnt, unsigned step_mask) {
     const float widen = 1.0000004f;  // 1 + 2*gamma(3): pbrt's conservative slab bound
     const Float4* np = sc.nodes + (size_t)t.cur * kNodeStride;
@@ -255,11 +260,13 @@ __device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, cons
     const bool hr = rtn <= rtf * widen;
     const int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
     const bool both = hl && hr;
+    // the nearer child first, left on ties (the reference's order, bvh.h:99-100): right_first = both ? ltn > rtn : hr, spelled
+    // as one predicate expression (4 fewer instructions per step than the select chain the ternary compiled to)
     const bool right_first = (JPB_ANYHIT_UNORDERED && ANY_HIT) ? !hl  // occlusion only: any order finds the same boolean
-                                                               : (both ? !(ltn <= rtn) : hr);  // the nearer child first; left on ties (the reference's order, bvh.h:99-100)
+                                                               : (hr & (!hl | (ltn > rtn)));
     const int near = right_first ? cr : cl;
     const int far = right_first ? cl : cr;
-    if (both) stk.push(t.sp, far);  // (prefetching the far child measured 3-6 % slower)
+    if (both) stk.push<GUARD>(t.sp, far);  // (prefetching the far child measured 3-6 % slower)
     t.cur = (hl || hr) ? near : stk.pop(t.sp);
 }
 
@@ -296,6 +303,7 @@ __device__ __forceinline__ void trav_leaf_step(const DevScene& sc, Trav& t, cons
     }
     t.cur = stk.pop(t.sp);
 }
+
 
 // The leaf phase with the primitive tests SPREAD OVER THE WARP (JPB_LEAF_SHARE, round 2).  In the per-lane form above a lane
 // tests its own leaf's 1-4 primitives one after the other: ncu shows ~11 lanes in the first test and ~8 in the later ones,
@@ -371,10 +379,14 @@ __device__ __forceinline__ void trav_leaf_phase_shared(const DevScene& sc, Trav&
 // fewer than min_inner? any lane at a leaf?) are ~15 of the ~85 instructions of a step; taking two steps per vote -- a lane
 // that reaches a leaf on the first sits out the second -- measured +1.5-2 % on all scenes (bunny 1,543 -> 1,568 Msamples/s at
 // 48 spp, Cornell 1,076 -> 1,090, glossy 186 -> 190), three steps per vote gives the gain back (profiles/ab/r02_ab_unroll.log).
+// SPECULATIVE WALK (Aila & Laine's postponed leaf: a lane that reaches a leaf stashes it and keeps stepping through inner nodes
+// until its next leaf, so that more lanes are busy in both phases) -- built in round 2, measured, removed: k_extend +4 %
+// (bunny), +6 % (Cornell), +8 % (5 M triangles) SLOWER, k_connect +2-5 %, glossy -1.6 % (profiles/ab/r02_ab_speculative_lean.log):
+// the nodes walked before the postponed leaf's hit shortens the ray are wasted, and the extra state costs spills at 40 registers.
 #ifndef JPB_NODE_UNROLL
 #define JPB_NODE_UNROLL 2
 #endif
-template <bool ANY_HIT, bool COUNT, typename IO>
+template <bool ANY_HIT, bool COUNT, bool GUARD = true, typename IO>
 __device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* work, const IO& io, int refill_min, int min_inner,
                                                TravCounts& cnt, unsigned long long* dropped = nullptr) {
     const unsigned full = 0xffffffffu;
@@ -425,7 +437,7 @@ __device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* w
 #pragma unroll
             for (int u = 0; u < JPB_NODE_UNROLL; ++u) {
                 const unsigned step_mask = COUNT ? (u == 0 ? m_inner : __ballot_sync(full, trav_at_inner(t))) : 0u;
-                if (trav_at_inner(t)) trav_node_step<COUNT, ANY_HIT>(sc, t, stk, cnt, step_mask);
+                if (trav_at_inner(t)) trav_node_step<COUNT, ANY_HIT, GUARD>(sc, t, stk, cnt, step_mask);
             }
         }
         const unsigned leaf_mask = COUNT ? __ballot_sync(full, trav_at_leaf(t)) : 0u;

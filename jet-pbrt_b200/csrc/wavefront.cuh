@@ -12,7 +12,7 @@
 // Queues ARE the records: survivors of `shade` are written contiguously into the other half of a
 // ping-pong buffer at positions handed out by one warp-aggregated atomicAdd per warp
 // (__ballot_sync + __popc), so every stage reads and writes fully coalesced 16-byte lanes.
-// Shadow rays go to static 48-byte slots (origin+tmax, dir+pixel, contribution), one per (vertex, light).
+// Shadow rays go to static 48-byte slots (origin+tmax, dir, contribution+pixel), one per (vertex, light).
 // All radiance goes straight to the float film with RED.ADD.F32 (no per-path radiance state).
 //
 // The same stages serve the reference's other integrators as MODES of the pipeline:
@@ -195,7 +195,8 @@ struct ExtendIO {
 };
 
 // MINB = resident blocks per SM the register allocation must allow (5: 48 registers, 6: 40; measured on B200:
-// 6 is 1-3 % faster on all scenes, 8 = 32 registers spills and is 15-25 % slower).
+// 6 is 1-3 % faster on all scenes, 8 = 32 registers spills and is 15-25 % slower).  The 6-block kernels also drop the
+// full-stack test of every push (intersect.cuh: GUARD) and are launched only for trees of verified depth (c_api.cu: fast6).
 template <bool COUNT, int MINB, bool PERM = false>
 __global__ void __launch_bounds__(kBlock, MINB) k_extend(const __grid_constant__ WfParams p, int it) {
     const int n = min(p.counters[CNT_RAYS * p.counter_stride + it], p.queue_capacity);
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_extend(const __grid_constant__
     TravCounts cnt;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.stats + ST_EXT_RAYS, (unsigned long long)n);
     ExtendIO<PERM> io{p.ray_o[buf], p.ray_d[buf], p.hit, p.perm};
-    traverse_queue<false, COUNT>(p.sc, n, work, io, p.refill_min, p.min_inner, cnt, p.stats + ST_STACK_DROPPED);
+    traverse_queue<false, COUNT, COUNT || MINB < 6>(p.sc, n, work, io, p.refill_min, p.min_inner, cnt, p.stats + ST_STACK_DROPPED);
     if (COUNT) {
         warp_stat_add(p.stats + ST_BOX, cnt.box);
         warp_stat_add(p.stats + ST_PRIM, cnt.prim);
@@ -220,21 +221,30 @@ __global__ void __launch_bounds__(kBlock, MINB) k_extend(const __grid_constant__
 // lambert | conductor | dielectric kind queues) and non-black light k own slot k * n_vertices + v, so
 // k_shade needs no atomics to emit them and the slots of one light are contiguous (coalesced writes,
 // and coherent rays for k_connect).  A slot whose sample cannot contribute holds tmax < 0.
+// Both halves of a shadow record are fetched together (round 1 fetched the direction only after testing o.w), and the
+// contribution record carries its pixel, so that delivery is one load.  Measured on B200 (profiles/ab/
+// r02_ab_connect_io_shade_prefetch.log): dependent vs parallel fetch, an L2 prefetch of the contribution when the ray is
+// taken, and a cp.async copy of it into shared memory (no global load at delivery) are all within +-0.3 % on k_connect --
+// the memory latency of the ray records is hidden by the other 47 warps of the SM; the simplest form stays.
 struct ConnectIO {
     const WfParams* p;
     unsigned* n_traced;
     __device__ __forceinline__ bool load(int i, f3& o, f3& d, float& tmin, float& tmax) const {
         const float4 so = ld_stream(&p->sh_o[i]);
+        const float4 sd = ld_stream(&p->sh_d[i]);
         if (so.w < 0.f) return false;
         o = mk3(so);
-        d = mk3(ld_stream(&p->sh_d[i]));
+        d = mk3(sd);
         tmin = JPBRT_RAY_TMIN;  // scene.h:38
         tmax = so.w;            // dist - 0.001
         ++*n_traced;
         return true;
     }
     __device__ __forceinline__ void store(int i, int slot, float) const {
-        if (slot < 0) film_add(*p, __float_as_int(ld_stream(&p->sh_d[i]).w), mk3(ld_stream(&p->sh_c[i])));  // integrator.cc:367-370
+        if (slot < 0) {  // unoccluded: integrator.cc:367-370
+            const float4 c = ld_stream(&p->sh_c[i]);
+            film_add(*p, __float_as_int(c.w), mk3(c));
+        }
     }
 };
 
@@ -251,7 +261,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_connect(const __grid_constant_
     TravCounts cnt;
     unsigned traced = 0;
     ConnectIO io{&p, &traced};
-    traverse_queue<true, COUNT>(p.sc, n, work, io, p.refill_min, p.min_inner, cnt, p.stats + ST_STACK_DROPPED);
+    traverse_queue<true, COUNT, COUNT || MINB < 6>(p.sc, n, work, io, p.refill_min, p.min_inner, cnt, p.stats + ST_STACK_DROPPED);
     warp_stat_add(p.stats + ST_SHADOW_RAYS, traced);
     if (COUNT) {
         warp_stat_add(p.stats + ST_SH_BOX, cnt.box);
@@ -463,6 +473,9 @@ __global__ void __launch_bounds__(kBlock, JPB_LOGIC_MIN_BLOCKS) k_logic(const __
 
 // Resident blocks per SM: 2 (111 registers) -> 3 (80) measured 5-9 % faster, 3 -> 4 (64 registers, the same ~150 bytes
 // of spills, which come from the out-of-line calls) another 3 % (profiles/ab/r01_ab_shade.log)
+#ifndef JPB_SHADE_PREFETCH
+#define JPB_SHADE_PREFETCH 1  // measured: shade stage -3.8 % (bunny), -3.5 % (Cornell), -0.6 % (glossy); profiles/ab/r02_ab_connect_io_shade_prefetch.log
+#endif
 #ifndef JPB_SHADE_MIN_BLOCKS
 #define JPB_SHADE_MIN_BLOCKS 4
 #endif
@@ -490,6 +503,17 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
         for (int c = 0; c < nchunks; ++c) {
             if (fetch_base + 32 * c >= n) break;
             const int qi = fetch_base + 32 * c + lane_id();
+#if JPB_SHADE_PREFETCH
+            // the NEXT chunk's records on their way to L2 while this chunk is shaded (queue -> index -> four records is a chain of
+            // dependent DRAM round trips otherwise)
+            if (c + 1 < nchunks && qi + 32 < n) {
+                const int in = ld_stream(&queue[qi + 32]);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&p.ray_o[buf][in]));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&p.ray_d[buf][in]));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&p.ray_b[buf][in]));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&p.hit[in]));
+            }
+#endif
             bool alive = false, alive2 = false;  // alive2: a mirror's second ray in the Whitted mode
             // The continuation ray's record is DEFINED only where the path survives (and zeroed, late, where it does not): a
             // zero-initialisation up here kept 16 words alive across the whole light loop -- in local memory at 64 registers
@@ -554,8 +578,8 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
                             const float tmax = dist - 0.001f;
                             if (tmax > 0.f) {
                                 st_stream(&p.sh_o[si], make_float4(P.x, P.y, P.z, tmax));
-                                st_stream(&p.sh_d[si], make_float4(sdir.x, sdir.y, sdir.z, ro.w));
-                                st_stream(&p.sh_c[si], make_float4(contrib.x, contrib.y, contrib.z, 0.f));
+                                st_stream(&p.sh_d[si], make_float4(sdir.x, sdir.y, sdir.z, 0.f));
+                                st_stream(&p.sh_c[si], make_float4(contrib.x, contrib.y, contrib.z, ro.w));  // .w: the pixel
                             } else {
                                 st_stream(&p.sh_o[si], make_float4(0.f, 0.f, 0.f, -1.f));
                                 film_add(p, pixel, contrib);
