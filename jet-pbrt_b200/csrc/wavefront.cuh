@@ -351,13 +351,22 @@ __global__ void __launch_bounds__(kBlock) k_permute(const __grid_constant__ WfPa
 #ifndef JPB_CHUNKS_PER_FETCH
 #define JPB_CHUNKS_PER_FETCH 8
 #endif
+#ifndef JPB_GUIDED_FETCH
+#define JPB_GUIDED_FETCH 64  // 0: the fetch size is fixed per launch (round 1); N: chunks = left / (warps * N), re-evaluated at every fetch
+#endif
 constexpr int kChunksPerFetch = JPB_CHUNKS_PER_FETCH;  // work is fetched up to 256 items at a time: fewer atomics on the hot queue cursors
 
-// Items per fetch: 256 while the queue is long, shrinking to 32 when it is short relative to the number of
-// resident warps, so that late, small iterations still spread over the whole chip.
-__device__ __forceinline__ int chunks_for(int n) {
+// Items per fetch: 256 while much of the queue is left, shrinking to 32 as it drains (guided self-scheduling: `left` is what
+// remained when this warp last looked at the cursor), so that the big fetches that keep the cursor's atomics cheap are not
+// what the last warps of a launch are still working through -- a 256-vertex fetch is 70-100 us of shading (16 lights: ~1 ms),
+// and every launch used to end with the chip waiting for a few of them.  Late, small iterations (left small from the
+// start) spread over the whole chip the same way.
+// Measured on B200 (profiles/ab/r02_ab_guided_fetch.log, shade stage, fixed -> guided): bunny 7.48 -> 7.37 ms, glossy (16 lights
+// per vertex) 23.25 -> 22.41 ms, and 21.74 ms when the fetches shrink twice as early (`heavy`: scenes with >= 8 lights to sample).
+__device__ __forceinline__ int chunks_for(int left, bool heavy = false) {
     const int total_warps = (gridDim.x * blockDim.x) >> 5;
-    return max(1, min(kChunksPerFetch, n / (total_warps * 64)));
+    const int per_warp = JPB_GUIDED_FETCH ? (heavy ? 2 * JPB_GUIDED_FETCH : JPB_GUIDED_FETCH) : 64;
+    return max(1, min(kChunksPerFetch, left / (total_warps * per_warp)));
 }
 
 __device__ __forceinline__ int warp_fetch_n(int* counter, int amount) {
@@ -376,11 +385,13 @@ __global__ void __launch_bounds__(kBlock, JPB_LOGIC_MIN_BLOCKS) k_logic(const __
     int* work = p.counters + CNT_W_SHADE * p.counter_stride + it;
     int* next_count = p.counters + CNT_RAYS * p.counter_stride + it + 1;
     const int buf = it & 1, nbuf = buf ^ 1;
-    const int nchunks = chunks_for(n);
+    int nchunks = chunks_for(n);
     const RngKey key{p.args->k0, p.args->k1};
     for (;;) {
         const int base = warp_fetch_n(work, 32 * nchunks);
         if (base >= n) break;
+        const int fetched = nchunks;
+        if (JPB_GUIDED_FETCH) nchunks = chunks_for(n - base);  // the NEXT fetch of this warp
         int kinds[kChunksPerFetch];
         unsigned masks[kChunksPerFetch][NUM_KINDS];
 #pragma unroll
@@ -389,7 +400,7 @@ __global__ void __launch_bounds__(kBlock, JPB_LOGIC_MIN_BLOCKS) k_logic(const __
             bool alive = false;
             int kind = -1;
             float4 no = make_float4(0, 0, 0, 0), nd = no, nbeta = no;
-            if (c < nchunks && i < n) {
+            if (c < fetched && i < n) {
                 const float4 rd = ld_stream(&p.ray_d[buf][i]);
                 const float2 h = ld_stream(&p.hit[i]);
                 const int fl = __float_as_int(rd.w);
@@ -494,11 +505,14 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
     for (int k = 0; k < NUM_KINDS; ++k)
         if (k < KIND) kind_base += p.counters[(CNT_Q0 + k) * p.counter_stride + it];
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.stats + ST_VERTICES, (unsigned long long)n);
-    const int nchunks = chunks_for(n);
+    const bool heavy = KIND != KIND_DELTA && sc.n_nee_lights >= 8;
+    int next_chunks = chunks_for(n, heavy);
     const RngKey key{p.args->k0, p.args->k1};
     for (;;) {
+        const int nchunks = next_chunks;
         const int fetch_base = warp_fetch_n(work, 32 * nchunks);
         if (fetch_base >= n) break;
+        if (JPB_GUIDED_FETCH) next_chunks = chunks_for(n - fetch_base, heavy);
 #pragma unroll 1
         for (int c = 0; c < nchunks; ++c) {
             if (fetch_base + 32 * c >= n) break;
