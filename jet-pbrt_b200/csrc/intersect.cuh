@@ -383,6 +383,9 @@ __device__ __forceinline__ void trav_leaf_phase_shared(const DevScene& sc, Trav&
 // until its next leaf, so that more lanes are busy in both phases) -- built in round 2, measured, removed: k_extend +4 %
 // (bunny), +6 % (Cornell), +8 % (5 M triangles) SLOWER, k_connect +2-5 %, glossy -1.6 % (profiles/ab/r02_ab_speculative_lean.log):
 // the nodes walked before the postponed leaf's hit shortens the ray are wasted, and the extra state costs spills at 40 registers.
+// EARLY REFILL (cutting a node phase short to deliver results and take new rays once 8 / 12 / 16 / 20 / 24 lanes have finished
+// inside it -- most rays end in a node phase): measured and removed, k_extend +1-5 %, k_connect +1-4 % slower at every threshold
+// (profiles/ab/r02_ab_early_refill.log): a refill costs the warp more issue slots than the idle lanes it fills give back.
 #ifndef JPB_NODE_UNROLL
 #define JPB_NODE_UNROLL 2
 #endif
