@@ -16,6 +16,9 @@ enum { LIGHT_ENV = 0, LIGHT_AREA = 1, LIGHT_POINT = 2, LIGHT_DIR = 3 };
 struct LightSample {
     f3 pos, wi, Li;
     float pdf;
+    // dist > 0: wi IS (pos - P) / dist with dist = length(pos - P), bit for bit -- the direction and distance of the shadow ray
+    // (FScene::Occluded recomputes exactly these, scene.h:36-47), so that k_shade does not normalise the same vector again
+    float dist;
 };
 
 __device__ __forceinline__ f3 uniform_sphere_sample(float ux, float uy) {  // sampling.h:80-87
@@ -41,6 +44,7 @@ __device__ __forceinline__ LightSample sample_light(const DevScene& sc, int li, 
     s.wi = mk3(0, 0, 0);
     s.Li = mk3(0, 0, 0);
     s.pdf = 0.f;
+    s.dist = 0.f;
     if (type == LIGHT_ENV) {  // light.h:265-287
         float theta = uy * JPB_PI, phi = ux * 2 * JPB_PI;
         float cosTheta = jp_cosf(theta), sinTheta = jp_sinf(theta);
@@ -54,9 +58,12 @@ __device__ __forceinline__ LightSample sample_light(const DevScene& sc, int li, 
     if (type == LIGHT_POINT) {  // light.h:95-124
         const f3 lp = mk3(ldg4(L + 1));
         s.pos = lp;
-        s.wi = normalize(lp - P);
+        const f3 w = lp - P;
+        const float d2 = length2(w);
+        s.dist = sqrtf(d2);
+        s.wi = w / s.dist;  // normalize(lp - P)
         s.pdf = 1.f;
-        s.Li = color / length2(lp - P);
+        s.Li = color / d2;
         return s;
     }
     if (type == LIGHT_DIR) {  // light.h:153-162
@@ -73,6 +80,10 @@ __device__ __forceinline__ LightSample sample_light(const DevScene& sc, int li, 
     const float inv_area = l1.w;  // 1 / Area()
     f3 lpos, lnrm;
     float pdf;
+    // The reference normalises (lpos - P) in SampleDirection, again in Sample_Li and a third time in FScene::Occluded: the same
+    // expression on the same operands -- computed once here (wn, dist, dist2) and reused, values unchanged.
+    f3 wn = mk3(0, 0, 0);
+    float dist = 0.f, dist2 = -1.f;  // dist2 < 0: (lpos - P) not looked at yet
     if (shape_type == SHAPE_SPHERE) {
         const float radius = l2.w;
         const f3 dcp = P - p0;
@@ -81,11 +92,13 @@ __device__ __forceinline__ LightSample sample_light(const DevScene& sc, int li, 
             lpos = p0 + radius * dir;
             lnrm = normalize(dir);
             pdf = inv_area;
-            f3 wi = lpos - P;
-            if (length2(wi) == 0) pdf = 0;
+            const f3 w = lpos - P;
+            dist2 = length2(w);
+            if (dist2 == 0) pdf = 0;
             else {
-                wi = normalize(wi);
-                pdf *= length2(lpos - P) / absdot(N, -wi);
+                dist = sqrtf(dist2);
+                wn = w / dist;  // normalize(w)
+                pdf *= dist2 / absdot(N, -wn);
             }
             if (isinf(pdf)) pdf = 0;
         } else {  // cone sampling: shape.h:606-643
@@ -131,22 +144,32 @@ __device__ __forceinline__ LightSample sample_light(const DevScene& sc, int li, 
             lpos = p0 + l2.w * (fr.s * sx + fr.t * sy);
         }
         pdf = inv_area;
-        f3 wi = lpos - P;
-        float dist2 = length2(wi);
+        const f3 w = lpos - P;
+        dist2 = length2(w);
         if (dist2 == 0) pdf = 0;
         else {
-            wi = normalize(wi);
-            pdf *= dist2 / absdot(lnrm, -wi);
+            dist = sqrtf(dist2);
+            wn = w / dist;  // normalize(w)
+            pdf *= dist2 / absdot(lnrm, -wn);
             if (isinf(pdf)) pdf = 0;
         }
     }
     // FAreaLight::Sample_Li, light.h:199-216
     s.pdf = pdf;
     s.pos = lpos;
-    if (pdf == 0 || length2(lpos - P) == 0) {
+    if (dist2 < 0.f) {  // (cone sampling of a sphere light: not normalised above)
+        const f3 w = lpos - P;
+        dist2 = length2(w);
+        if (dist2 != 0) {
+            dist = sqrtf(dist2);
+            wn = w / dist;
+        }
+    }
+    if (pdf == 0 || dist2 == 0) {
         s.Li = mk3(0, 0, 0);
     } else {
-        s.wi = normalize(lpos - P);
+        s.wi = wn;
+        s.dist = dist;
         s.Li = area_L(color, lnrm, -s.wi);
     }
     return s;

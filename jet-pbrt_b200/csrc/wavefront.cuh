@@ -584,9 +584,13 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
                         }
                         if (valid && fits) {
                             // FScene::Occluded(isect, ls.pos): scene.h:36-47
-                            const f3 v = ls.pos - P;
-                            const float dist = length(v);
-                            const f3 sdir = v / dist;
+                            f3 sdir = ls.wi;       // area and point lights: the light sample already holds
+                            float dist = ls.dist;  //   normalize(pos - P) and |pos - P| (light.cuh)
+                            if (!(dist > 0.f)) {   // environment / directional lights: pos = P + wi * 2R, normalised again as the reference does
+                                const f3 v = ls.pos - P;
+                                dist = length(v);
+                                sdir = v / dist;
+                            }
                             const f3 contrib = cmul(cmul(beta, f), ls.Li) * absdot(ls.wi, N) / ls.pdf;  // integrator.cc:369
                             // a degenerate distance (tmax <= 0 or NaN) can hit nothing: the sample is unoccluded
                             const float tmax = dist - 0.001f;
