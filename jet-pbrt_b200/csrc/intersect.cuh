@@ -386,6 +386,12 @@ __device__ __forceinline__ void trav_leaf_phase_shared(const DevScene& sc, Trav&
 // EARLY REFILL (cutting a node phase short to deliver results and take new rays once 8 / 12 / 16 / 20 / 24 lanes have finished
 // inside it -- most rays end in a node phase): measured and removed, k_extend +1-5 %, k_connect +1-4 % slower at every threshold
 // (profiles/ab/r02_ab_early_refill.log): a refill costs the warp more issue slots than the idle lanes it fills give back.
+// CLAIM-AHEAD (ray indices handed out from 32-ray chunks claimed one chunk ahead, so that no warp waits for the round trip of the
+// work cursor's atomicAdd -- ncu attributes 5-6 % (bunny) to 19 % (Cornell k_connect) of the stall samples to the shuffle behind
+// it): measured and removed, k_extend +1-3 %, k_connect +0.7-2.5 % SLOWER (profiles/ab/r02_ab_claim_ahead.log).  The kernels are
+// bound by issue slots and the L1 pipe, not by latency: while one warp waits for its claim the SM's other 47 issue, and the
+// chunk bookkeeping's instructions and spills cost more than the wait.  (The same holds for the ray records' DRAM latency: see
+// ConnectIO in wavefront.cuh.)
 #ifndef JPB_NODE_UNROLL
 #define JPB_NODE_UNROLL 2
 #endif
