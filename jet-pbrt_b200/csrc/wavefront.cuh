@@ -482,13 +482,13 @@ __global__ void __launch_bounds__(kBlock, JPB_LOGIC_MIN_BLOCKS) k_logic(const __
     }
 }
 
-// Resident blocks per SM: 2 (111 registers) -> 3 (80) measured 5-9 % faster, 3 -> 4 (64 registers, the same ~150 bytes
-// of spills, which come from the out-of-line calls) another 3 % (profiles/ab/r01_ab_shade.log)
-#ifndef JPB_SHADE_PREFETCH
-#define JPB_SHADE_PREFETCH 1  // measured: shade stage -3.8 % (bunny), -3.5 % (Cornell), -0.6 % (glossy); profiles/ab/r02_ab_connect_io_shade_prefetch.log
-#endif
+// Resident blocks per SM.  Round 1: 2 (111 registers) -> 3 (80) measured 5-9 % faster, 3 -> 4 (64 registers) another 3 %
+// (profiles/ab/r01_ab_shade.log).  Round 2, with the next chunk's records prefetched and the light sample's direction computed
+// once, latency is less of the story and the 64-register build's spills more: 3 blocks (80 registers, a third of the spill
+// traffic) is 1-4 % faster than 4 on all three scenes, 5 blocks (48 registers) 5-7 % slower; two lights per trip of the NEE loop
+// (ILP across lights) is +-3 % either way (profiles/ab/r02_ab_shade_ilp_blocks.log).
 #ifndef JPB_SHADE_MIN_BLOCKS
-#define JPB_SHADE_MIN_BLOCKS 4
+#define JPB_SHADE_MIN_BLOCKS 3
 #endif
 template <int KIND, bool WHITTED = false>
 __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ WfParams p, int it) {
@@ -566,6 +566,7 @@ __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __
                 if (KIND != KIND_DELTA) {  // integrator.cc:357-372
                     float4 lu = make_float4(0, 0, 0, 0);
                     int lu_block = -1;
+#pragma unroll kLightUnroll
                     for (int k = 0; k < sc.n_nee_lights; ++k) {  // black lights are skipped (integrator.cc:362), not sampled
                         const int j = __ldg(sc.nee_lights + k);
                         if ((k >> 1) != lu_block) {  // the k-th non-black light's pair: block k/2, words 2*(k%2)  (rng.cuh)
