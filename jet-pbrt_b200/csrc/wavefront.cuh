@@ -490,6 +490,15 @@ __global__ void __launch_bounds__(kBlock, JPB_LOGIC_MIN_BLOCKS) k_logic(const __
 #ifndef JPB_SHADE_MIN_BLOCKS
 #define JPB_SHADE_MIN_BLOCKS 3
 #endif
+#ifndef JPB_LIGHT_UNROLL
+#define JPB_LIGHT_UNROLL 1
+#endif
+constexpr int kLightUnroll = JPB_LIGHT_UNROLL;  // lights per trip of k_shade's NEE loop (A/B builds)
+// The next chunk's path records are prefetched to L2 while the current chunk is shaded: shade stage -3.8 % (bunny scene),
+// -3.5 % (Cornell), -0.6 % (glossy); profiles/ab/r02_ab_connect_io_shade_prefetch.log
+#ifndef JPB_SHADE_PREFETCH
+#define JPB_SHADE_PREFETCH 1
+#endif
 template <int KIND, bool WHITTED = false>
 __global__ void __launch_bounds__(kBlock, JPB_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ WfParams p, int it) {
     const DevScene& sc = p.sc;
