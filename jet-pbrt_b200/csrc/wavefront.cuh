@@ -375,6 +375,8 @@ __device__ __forceinline__ int warp_fetch_n(int* counter, int amount) {
     return __shfl_sync(kFull, base, 0);
 }
 
+// (k_logic waits on memory -- ncu: IPC 1.6, long-scoreboard stalls -- yet prefetching all chunks of a fetch before the first is
+// looked at measured +-0, as did 3 or 6 resident blocks: profiles/ab/r02_ab_logic.log)
 #ifndef JPB_LOGIC_MIN_BLOCKS
 #define JPB_LOGIC_MIN_BLOCKS 4  // 64 registers; 5-6 blocks (48 / 40 registers) measured equal (profiles/ab/r01_ab_shade.log)
 #endif
