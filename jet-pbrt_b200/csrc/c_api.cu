@@ -194,10 +194,10 @@ int occupancy_grid(jpbrt_ctx* c, K kernel) {
 }
 
 // Page-lock the flattened host arrays so that (re)uploads are true asynchronous DMA transfers.
-template <typename T>
-void pin_vector(jpbrt_ctx* c, std::vector<T>& v) {
+template <typename V>
+void pin_vector(jpbrt_ctx* c, V& v) {
     if (v.empty()) return;
-    if (cudaHostRegister(v.data(), v.size() * sizeof(T), cudaHostRegisterDefault) == cudaSuccess) c->pinned.push_back(v.data());
+    if (cudaHostRegister(v.data(), v.size() * sizeof(typename V::value_type), cudaHostRegisterDefault) == cudaSuccess) c->pinned.push_back(v.data());
     else cudaGetLastError();
 }
 

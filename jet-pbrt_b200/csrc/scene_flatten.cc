@@ -7,8 +7,11 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <future>
 #include <limits>
+#include <memory>
+#include <new>
 #include <thread>
 
 #include "../../include/jetpbrt_b200.h"
@@ -37,6 +40,8 @@ constexpr float kPi = (float)3.14159265358979323846;
 
 struct Box {
     float mn[3], mx[3];
+    struct Uninitialised {};
+    explicit Box(Uninitialised) {}  // (for arrays whose every element is assigned before it is read)
     Box() {
         for (int a = 0; a < 3; ++a) { mn[a] = std::numeric_limits<float>::max(); mx[a] = std::numeric_limits<float>::lowest(); }
     }
@@ -176,8 +181,11 @@ namespace {
 
 struct TmpNode {
     Box box;
-    int left = -1, right = -1;  // inner
-    int first = 0, count = 0;   // leaf when count > 0
+    int left, right;   // inner
+    int first, count;  // leaf when count > 0
+    // No initialisation: the builder sizes its node array for the worst case (2 N) up front and every node it hands out is
+    // filled in completely by Build(); constructing 10 M empty nodes first was 0.3 s of a 5 M-primitive build.
+    TmpNode() : box(Box::Uninitialised{}) {}
 };
 
 // Build knobs; overridable for experiments through the environment: JPBRT_BVH_LEAF (max primitives per
@@ -187,6 +195,21 @@ struct TmpNode {
 static int EnvInt(const char* name, int def) {
     const char* v = getenv(name);
     return v ? atoi(v) : def;
+}
+
+// fn(begin, end, part) over [0, n) cut into at most `parts` contiguous pieces, one std::thread each (the caller's included).
+// Every use below combines the pieces' results with min / max / integer sums only, so the outcome does not depend on the cut.
+template <typename F>
+static void ParallelFor(size_t n, int parts, F&& fn) {
+    parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, parts), n >> 14));
+    if (parts <= 1) { fn((size_t)0, n, 0); return; }
+    const size_t chunk = (n + parts - 1) / parts;
+    std::vector<std::thread> th;
+    th.reserve(parts - 1);
+    for (int t = 1; t < parts; ++t)
+        th.emplace_back([&fn, t, chunk, n]() { fn(std::min(n, t * chunk), std::min(n, (t + 1) * chunk), t); });
+    fn((size_t)0, std::min(n, chunk), 0);
+    for (auto& x : th) x.join();
 }
 
 struct Builder {
@@ -199,40 +222,70 @@ struct Builder {
     int sweep_hi = EnvInt("JPBRT_BVH_SWEEP_HI", 65536);  // (scenes of more than 2^18 primitives: bins only -- the sweep doubles a 5 M build for < 2 %)
     int sweep_max = EnvInt("JPBRT_BVH_SWEEP", 0);  // experiments: also sweep sets of at most this many primitives
     const std::vector<Box>& pb;
-    std::vector<float> cx, cy, cz;
-    std::vector<int> idx;
+    BigVec<float> cx, cy, cz;
+    BigVec<int> idx;
     std::vector<TmpNode> nodes;
     std::atomic<int> next{0};
     std::atomic<int> threads_left;
+    int nthreads;  // host threads the build may use: subtree tasks (threads_left) and data-parallel passes over big sets
     bool force_median = false;  // object-median splits only: the fallback for trees SAH leaves deeper than the traversal stack
     bool chain_test = EnvInt("JPBRT_TEST_CHAIN_BVH", 0) != 0;  // TEST HOOK: one primitive peeled off per level (a tree as deep
                                                                // as the scene is large), to exercise the kernels' stack-overflow counter
 
-    explicit Builder(const std::vector<Box>& prim_boxes, int nthreads) : pb(prim_boxes), threads_left(nthreads) {
+    explicit Builder(const std::vector<Box>& prim_boxes, int nthreads_) : pb(prim_boxes), threads_left(nthreads_), nthreads(nthreads_) {
         size_t n = pb.size();
         cx.resize(n); cy.resize(n); cz.resize(n); idx.resize(n);
-        for (size_t i = 0; i < n; ++i) {
-            cx[i] = 0.5f * (pb[i].mn[0] + pb[i].mx[0]);
-            cy[i] = 0.5f * (pb[i].mn[1] + pb[i].mx[1]);
-            cz[i] = 0.5f * (pb[i].mn[2] + pb[i].mx[2]);
-            idx[i] = (int)i;
-        }
+        ParallelFor(n, nthreads, [&](size_t b, size_t e, int) {
+            for (size_t i = b; i < e; ++i) {
+                cx[i] = 0.5f * (pb[i].mn[0] + pb[i].mx[0]);
+                cy[i] = 0.5f * (pb[i].mn[1] + pb[i].mx[1]);
+                cz[i] = 0.5f * (pb[i].mn[2] + pb[i].mx[2]);
+                idx[i] = (int)i;
+            }
+        });
         nodes.resize(std::max<size_t>(2 * n, 2));
         if (n > (size_t)1 << 18) sweep_hi = 0;
     }
     float C(int axis, int i) const { return axis == 0 ? cx[i] : (axis == 1 ? cy[i] : cz[i]); }
     int Alloc() { return next.fetch_add(1); }
 
-    void Build(int node, int first, int last) {
+    // Sets of at least kParallelSet primitives (the top few levels of a multi-million-primitive tree, where there are fewer
+    // subtrees than host threads) are bounded and binned by several threads at once: a share of the build's threads
+    // proportional to the set's share of the scene.
+    static constexpr int kParallelSet = 1 << 18;
+    int WidthFor(int count) const {
+        if (count < kParallelSet) return 1;
+        return (int)std::max<long long>(1, (long long)nthreads * count / (long long)std::max<size_t>(1, pb.size()));
+    }
+
+    void Build(int node, int first, int last, const Box* known_box = nullptr, const Box* known_cbox = nullptr) {
         TmpNode& N = nodes[node];
         Box box, cbox;
-        for (int i = first; i < last; ++i) {
-            int p = idx[i];
-            box.Add(pb[p]);
-            cbox.Add(H3(cx[p], cy[p], cz[p]));
+        int count = last - first;
+        if (known_box) {  // the parent's bins already hold this set's bounds
+            box = *known_box;
+            cbox = *known_cbox;
+        } else if (const int width = WidthFor(count); width > 1) {
+            std::vector<Box> pbx(width), pcb(width);
+            ParallelFor((size_t)count, width, [&](size_t b, size_t e, int t) {
+                Box bx, cb;
+                for (size_t i = first + b; i < first + e; ++i) {
+                    int p = idx[i];
+                    bx.Add(pb[p]);
+                    cb.Add(H3(cx[p], cy[p], cz[p]));
+                }
+                pbx[t] = bx;
+                pcb[t] = cb;
+            });
+            for (int t = 0; t < width; ++t) { box.Add(pbx[t]); cbox.Add(pcb[t]); }
+        } else {
+            for (int i = first; i < last; ++i) {
+                int p = idx[i];
+                box.Add(pb[p]);
+                cbox.Add(H3(cx[p], cy[p], cz[p]));
+            }
         }
         N.box = box;
-        int count = last - first;
         if (chain_test && !force_median) {
             if (count == 1) { N.first = first; N.count = 1; return; }
             int l = Alloc(), r = Alloc();
@@ -251,7 +304,8 @@ struct Builder {
             if (leaf) { N.first = first; N.count = count; return; }
         }
         int axis = -1, mid = -1;
-        if (!force_median) BestSplitCost(first, last, box, cbox, &axis, &mid);
+        ChildBounds kids;
+        if (!force_median) BestSplitCost(first, last, box, cbox, &axis, &mid, &kids);
         if (mid <= first || mid >= last) {  // degenerate (coincident centroids): median by index
             int a = 0;
             float ext = -1;
@@ -259,20 +313,25 @@ struct Builder {
             mid = first + count / 2;
             std::nth_element(idx.begin() + first, idx.begin() + mid, idx.begin() + last,
                              [&](int l, int r) { return C(a, l) < C(a, r); });
+            kids.known = false;
         }
         int l = Alloc(), r = Alloc();
         N.left = l;
         N.right = r;
         N.count = 0;
         if (count > 1 << 15 && threads_left.fetch_sub(1) > 0) {
-            auto fut = std::async(std::launch::async, [this, l, first, mid]() { Build(l, first, mid); });
-            Build(r, mid, last);
+            const Box *lb = kids.known ? &kids.box[0] : nullptr, *lc = kids.known ? &kids.cbox[0] : nullptr;
+            const Box *rb = kids.known ? &kids.box[1] : nullptr, *rc = kids.known ? &kids.cbox[1] : nullptr;
+            auto fut = std::async(std::launch::async, [this, l, first, mid, lb, lc]() { Build(l, first, mid, lb, lc); });
+            Build(r, mid, last, rb, rc);
             fut.get();
             threads_left.fetch_add(1);
         } else {
             if (count > 1 << 15) threads_left.fetch_add(1);
-            Build(l, first, mid);
-            Build(r, mid, last);
+            const Box *lb = kids.known ? &kids.box[0] : nullptr, *lc = kids.known ? &kids.cbox[0] : nullptr;
+            const Box *rb = kids.known ? &kids.box[1] : nullptr, *rc = kids.known ? &kids.cbox[1] : nullptr;
+            Build(l, first, mid, lb, lc);
+            Build(r, mid, last, rb, rc);
         }
     }
 
@@ -309,9 +368,18 @@ struct Builder {
         return best;
     }
 
+    // Bounds of the two sides of a split, handed to the children so that they need not walk their primitives for them.
+    struct ChildBounds {
+        bool known = false;
+        Box box[2], cbox[2];
+    };
+
     // Binned SAH over the three axes.  Returns the best cost (in primitive-test units, traversal
-    // step = 1); if axis/mid are given, partitions idx[first,last) and reports the split.
-    float BestSplitCost(int first, int last, const Box& box, const Box& cbox, int* out_axis, int* out_mid) {
+    // step = 1); if axis/mid are given, partitions idx[first,last) and reports the split -- and, through `kids`, the
+    // primitive and centroid bounds of both sides, which are unions of the winning axis's bins.
+    // ONE pass over the set fills the bins of all three axes (the pass is a gather of 36 bytes per primitive from three
+    // arrays: memory-bound, and it used to run once per axis after a separate pass for the bounds).
+    float BestSplitCost(int first, int last, const Box& box, const Box& cbox, int* out_axis, int* out_mid, ChildBounds* kids = nullptr) {
         constexpr int kMaxBins = 256;
         const int NB = (last - first) > 1024 ? std::min(kMaxBins, std::max(2, bins_big)) : 16;
         int count = last - first;
@@ -319,18 +387,71 @@ struct Builder {
         float best = std::numeric_limits<float>::infinity();
         int best_axis = -1, best_bin = -1;
         float parent_area = std::max(box.HalfArea(), 1e-30f);
-        for (int a = 0; a < 3; ++a) {
-            float lo = cbox.mn[a], ext = cbox.mx[a] - cbox.mn[a];
-            if (!(ext > 0)) continue;
-            float scale = (float)NB / ext;
-            Box bb[kMaxBins];
-            int bc[kMaxBins] = {0};
-            for (int i = first; i < last; ++i) {
-                int p = idx[i];
-                int b = std::min(NB - 1, std::max(0, (int)((C(a, p) - lo) * scale)));
-                bb[b].Add(pb[p]);
-                bc[b]++;
+        const bool want_kids = kids != nullptr && out_axis != nullptr;
+        struct Bins {
+            alignas(Box) unsigned char bb_raw[3][sizeof(Box) * kMaxBins];  // primitive bounds per (axis, bin)
+            alignas(Box) unsigned char cb_raw[3][sizeof(Box) * kMaxBins];  // centroid bounds per (axis, bin): only with want_kids
+            int bc[3][kMaxBins];
+            Box* bb(int a) { return reinterpret_cast<Box*>(bb_raw[a]); }
+            Box* cb(int a) { return reinterpret_cast<Box*>(cb_raw[a]); }
+            void Init(int nb, bool centroids) {  // (only the bins in use: most calls are for a few primitives and 16 bins)
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < nb; ++b) {
+                        new (&bb(a)[b]) Box();
+                        if (centroids) new (&cb(a)[b]) Box();
+                        bc[a][b] = 0;
+                    }
             }
+        };
+        float lo3[3], scale3[3];
+        bool use[3];
+        for (int a = 0; a < 3; ++a) {
+            lo3[a] = cbox.mn[a];
+            const float ext = cbox.mx[a] - cbox.mn[a];
+            use[a] = ext > 0;
+            scale3[a] = use[a] ? (float)NB / ext : 0.f;
+        }
+        auto fill = [&](Bins& B, size_t b0, size_t e0) {
+            for (size_t i = b0; i < e0; ++i) {
+                const int p = idx[i];
+                const Box& pbx = pb[p];
+                const H3 c(cx[p], cy[p], cz[p]);
+                const float cc[3] = {c.x, c.y, c.z};
+                for (int a = 0; a < 3; ++a) {
+                    if (!use[a]) continue;
+                    const int b = std::min(NB - 1, std::max(0, (int)((cc[a] - lo3[a]) * scale3[a])));
+                    B.bb(a)[b].Add(pbx);
+                    if (want_kids) B.cb(a)[b].Add(c);
+                    B.bc[a][b]++;
+                }
+            }
+        };
+        Bins bins;
+        bins.Init(NB, want_kids);
+        if (const int width = WidthFor(count); width > 1) {  // big sets: several threads, each into its own bins
+            std::vector<std::unique_ptr<Bins>> part(width);
+            ParallelFor((size_t)count, width, [&](size_t b0, size_t e0, int t) {
+                part[t].reset(new Bins);
+                part[t]->Init(NB, want_kids);
+                fill(*part[t], first + b0, first + e0);
+            });
+            for (int t = 0; t < width; ++t) {
+                if (!part[t]) continue;
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < NB; ++b)
+                        if (part[t]->bc[a][b]) {
+                            bins.bb(a)[b].Add(part[t]->bb(a)[b]);
+                            if (want_kids) bins.cb(a)[b].Add(part[t]->cb(a)[b]);
+                            bins.bc[a][b] += part[t]->bc[a][b];
+                        }
+            }
+        } else {
+            fill(bins, (size_t)first, (size_t)last);
+        }
+        for (int a = 0; a < 3; ++a) {
+            if (!use[a]) continue;
+            const Box* bb = bins.bb(a);
+            const int* bc = bins.bc[a];
             float right_area[kMaxBins];
             int right_cnt[kMaxBins];
             Box acc;
@@ -353,14 +474,22 @@ struct Builder {
         }
         if (out_axis && best_axis >= 0) {
             int a = best_axis;
-            float lo = cbox.mn[a], ext = cbox.mx[a] - cbox.mn[a];
-            float scale = (float)NB / ext;
+            const float lo = lo3[a], scale = scale3[a];
             auto it = std::partition(idx.begin() + first, idx.begin() + last, [&](int p) {
                 int b = std::min(NB - 1, std::max(0, (int)((C(a, p) - lo) * scale)));
                 return b <= best_bin;
             });
             *out_axis = a;
             *out_mid = (int)(it - idx.begin());
+            if (want_kids) {
+                for (int b = 0; b < NB; ++b) {
+                    if (!bins.bc[a][b]) continue;
+                    const int side = b <= best_bin ? 0 : 1;
+                    kids->box[side].Add(bins.bb(a)[b]);
+                    kids->cbox[side].Add(bins.cb(a)[b]);
+                }
+                kids->known = true;
+            }
         } else if (out_axis) {
             *out_axis = -1;
             *out_mid = -1;
@@ -511,6 +640,15 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, Bv
 
     HostScene& hs = *out;
     hs = HostScene();
+    // JPBRT_FLATTEN_TIMING=1: phase times on stderr (where a 5 M-primitive upload spends its host seconds)
+    const bool timing = EnvInt("JPBRT_FLATTEN_TIMING", 0) != 0;
+    auto t_phase = std::chrono::steady_clock::now();
+    auto phase = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[flatten] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_phase).count());
+        t_phase = now;
+    };
     hs.max_depth = d->max_depth;
     hs.width = d->camera.width;
     hs.height = d->camera.height;
@@ -557,20 +695,39 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, Bv
 
     // primitives -> slots (pre-BVH order), bounds
     const int N = d->n_primitives;
-    std::vector<Float4> pre_slots((size_t)N * kSlotStride), pre_nrm(N);
+    BigVec<Float4> pre_slots((size_t)N * kSlotStride), pre_nrm(N);  // (uninitialised: every element is written below)
     std::vector<Box> boxes(N);
     Box world;
-    for (int i = 0; i < N; ++i) {
-        const jpbrt_primitive& p = d->primitives[i];
-        if (p.shape < 0 || p.shape >= d->n_shapes) return fail(JPBRT_ERR_INVALID, "primitive references a missing shape");
-        if (p.material >= d->n_materials) return fail(JPBRT_ERR_INVALID, "primitive references a missing material");
-        if (p.light >= d->n_lights) return fail(JPBRT_ERR_INVALID, "primitive references a missing light");
-        if (p.material < 0) hs.has_null_material = true;
-        if (!MakeSlot(d->shapes[p.shape], i, &pre_slots[(size_t)i * kSlotStride], &pre_nrm[i], boxes[i].mn, boxes[i].mx))
-            return fail(JPBRT_ERR_INVALID, "unknown shape type");
-        world.Add(boxes[i]);  // FScene::CalculateWorldBound, scene.cc:35-45
+    const int nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+    {
+        std::vector<Box> part_world(nthreads);
+        std::atomic<int> bad{0}, null_material{0};  // bad: the first kind of invalid reference any thread met
+        ParallelFor((size_t)N, nthreads, [&](size_t b, size_t e, int t) {
+            Box w;
+            for (size_t i = b; i < e; ++i) {
+                const jpbrt_primitive& p = d->primitives[i];
+                int code = 0;
+                if (p.shape < 0 || p.shape >= d->n_shapes) code = 1;
+                else if (p.material >= d->n_materials) code = 2;
+                else if (p.light >= d->n_lights) code = 3;
+                else if (!MakeSlot(d->shapes[p.shape], (int)i, &pre_slots[i * kSlotStride], &pre_nrm[i], boxes[i].mn, boxes[i].mx)) code = 4;
+                if (code) { int none = 0; bad.compare_exchange_strong(none, code); return; }
+                if (p.material < 0) null_material.store(1, std::memory_order_relaxed);
+                w.Add(boxes[i]);  // FScene::CalculateWorldBound, scene.cc:35-45
+            }
+            part_world[t] = w;
+        });
+        switch (bad.load()) {
+        case 1: return fail(JPBRT_ERR_INVALID, "primitive references a missing shape");
+        case 2: return fail(JPBRT_ERR_INVALID, "primitive references a missing material");
+        case 3: return fail(JPBRT_ERR_INVALID, "primitive references a missing light");
+        case 4: return fail(JPBRT_ERR_INVALID, "unknown shape type");
+        }
+        if (null_material.load()) hs.has_null_material = true;
+        for (const Box& w : part_world) world.Add(w);
     }
     for (int a = 0; a < 3; ++a) { hs.world_min[a] = world.mn[a]; hs.world_max[a] = world.mx[a]; }
+    phase("primitive records + boxes");
     {  // FBounds3::BoundingSphere (geometry.h:307-311) as used by FEnvironmentLight::Preprocess (light.cc:26-33)
         H3 mn(world.mn), mx(world.mx);
         H3 c = mn + (mx - mn) * 0.5f;  // Lerp(u, v, t) = u + t * (v - u), geometry.h:137
@@ -635,8 +792,8 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, Bv
     // ray origins are the camera position or points on surfaces: include the camera in the magnitude
     for (int a = 0; a < 3; ++a) maxabs = std::max(maxabs, std::fabs(d->camera.pos[a]));
     const float pad = 4e-6f * maxabs + 1e-30f;
-    int nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
     Builder bld(boxes, nthreads);
+    phase("builder setup (centroids)");
     int root = -1;
     if (build && N >= 2) {
         // external (GPU) builder: a binary radix tree over the Morton-sorted primitives; cut it into our leaves here
@@ -645,7 +802,7 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, Bv
         std::string berr;
         if (build(build_user, reinterpret_cast<const float*>(boxes.data()), N, &built, &berr) && (int)built.order.size() == N &&
             (int)built.nodes.size() == N - 1) {
-            bld.idx = built.order;
+            bld.idx.assign(built.order.begin(), built.order.end());
             bld.nodes.clear();
             bld.nodes.reserve((size_t)2 * N);
             struct Todo { int built_ref; int tmp; int depth; };
@@ -686,7 +843,8 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, Bv
             if (max_depth > 60) {  // deeper than the traversal stack (pathological duplicate centroids): use the SAH builder
                 hs.bvh_builder = 0;
                 root = -1;
-                bld.nodes.assign(std::max<size_t>(2 * (size_t)N, 2), TmpNode());
+                bld.nodes.clear();
+        bld.nodes.resize(std::max<size_t>(2 * (size_t)N, 2));
                 for (int i = 0; i < N; ++i) bld.idx[i] = i;
                 bld.next = 0;
             }
@@ -697,7 +855,9 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, Bv
     if (root < 0) {
         root = bld.Alloc();
         bld.Build(root, 0, N);
+        bld.nodes.resize((size_t)bld.next.load());  // the nodes handed out (the rest of the 2 N were never written)
     }
+    phase("tree build");
     // Insertion-based optimisation of the topology: two passes for scenes of 1,025 .. 2^17 primitives (JPBRT_BVH_REINSERT
     // overrides the number of passes for any scene up to 2^18).  Measured on B200 (profiles/ab/r01_ab_reinsert.log): the
     // bunny scene's surface-area cost drops 6.98 -> 5.48 and the step is 2.7 % faster for ~0.1 s more build; Cornell
@@ -723,37 +883,56 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, Bv
     // sentinel); a deeper tree would silently lose far children.  SAH on skewed input (long chains of nested or
     // near-coincident primitives) can exceed that: such a tree is rebuilt with object-median splits, whose depth is
     // ceil(log2(N / leaf)) <= 31.  The kernels additionally COUNT any push that finds the stack full (stack_overflows).
-    auto tree_depth = [&](int r) {
-        int deepest = 0;
-        std::vector<std::pair<int, int>> st{{r, 1}};
-        while (!st.empty()) {
-            auto [n, dep] = st.back();
-            st.pop_back();
-            deepest = std::max(deepest, dep);
-            if (bld.nodes[n].count == 0) { st.push_back({bld.nodes[n].left, dep + 1}); st.push_back({bld.nodes[n].right, dep + 1}); }
+    // One pass over the finished topology: depth, inner nodes per subtree (the layout below places every node from these
+    // counts alone) and the largest leaf.  The top levels fan out over host threads.
+    std::vector<int> inner_below;  // per tmp node: inner nodes in its subtree, itself included (0 for a leaf)
+    std::atomic<int> largest_leaf{0};
+    std::function<int(int, int)> measure = [&](int n, int level) -> int {  // returns the subtree's depth in levels
+        const TmpNode& T = bld.nodes[n];
+        if (T.count > 0) {
+            int seen = largest_leaf.load(std::memory_order_relaxed);
+            while (T.count > seen && !largest_leaf.compare_exchange_weak(seen, T.count)) {}
+            inner_below[n] = 0;
+            return 1;
         }
-        return deepest;
+        int dl, dr;
+        if (level < 4 && nthreads > 1) {
+            auto fut = std::async(std::launch::async, [&measure, &T, level]() { return measure(T.left, level + 1); });
+            dr = measure(T.right, level + 1);
+            dl = fut.get();
+        } else {
+            dl = measure(T.left, level + 1);
+            dr = measure(T.right, level + 1);
+        }
+        inner_below[n] = 1 + inner_below[T.left] + inner_below[T.right];
+        return 1 + std::max(dl, dr);
+    };
+    auto tree_depth = [&](int r) {
+        inner_below.assign(bld.nodes.size(), 0);
+        largest_leaf.store(0);
+        return measure(r, 0);
     };
     hs.bvh_depth = tree_depth(root);
     const int depth_limit = std::max(1, std::min(kMaxBvhDepth, EnvInt("JPBRT_BVH_MAX_DEPTH", kMaxBvhDepth)));  // (lowered by tests)
     const bool allow_deep = EnvInt("JPBRT_TEST_ALLOW_DEEP_BVH", 0) != 0;  // tests of the kernels' overflow counter only
     if (hs.bvh_depth > depth_limit && !allow_deep) {
-        bld.nodes.assign(std::max<size_t>(2 * (size_t)N, 2), TmpNode());
+        bld.nodes.clear();
+        bld.nodes.resize(std::max<size_t>(2 * (size_t)N, 2));
         for (int i = 0; i < N; ++i) bld.idx[i] = i;
         bld.next = 0;
         bld.force_median = true;
         root = bld.Alloc();
         bld.Build(root, 0, N);
+        bld.nodes.resize((size_t)bld.next.load());
         hs.bvh_depth = tree_depth(root);
         hs.bvh_builder = 2;
         if (hs.bvh_depth > kMaxBvhDepth) return fail(JPBRT_ERR_UNSUPPORTED, "BVH deeper than the traversal stack even with median splits");
     }
 
+    phase("reinsertion / depth check");
     // flatten: inner nodes depth-first, leaves reference idx ranges (== slot ranges)
-    std::vector<Float4>& fn = hs.nodes;
+    auto& fn = hs.nodes;
     fn.clear();
-    struct Item { int tmp; int flat; };
-    std::vector<Item> stack;
     auto box_of = [&](int tmp, float mn[3], float mx[3]) {
         const Box& b = bld.nodes[tmp].box;
         for (int a = 0; a < 3; ++a) { mn[a] = b.mn[a] - pad; mx[a] = b.mx[a] + pad; }
@@ -771,52 +950,79 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, Bv
         fn[f * kNodeStride + 3] = Float4{IntAsFloat(LeafRef(bld.nodes[root].first, bld.nodes[root].count)), IntAsFloat(LeafRef(0, 0)), 0, 0};
         hs.max_leaf_prims = bld.nodes[root].count;
     } else {
-        stack.push_back(Item{root, emit_inner()});
-        while (!stack.empty()) {
-            Item it = stack.back();
-            stack.pop_back();
-            const TmpNode& T = bld.nodes[it.tmp];
-            int refs[2];
-            int kids[2] = {T.left, T.right};
-            float mn[2][3], mx[2][3];
-            int child_flat[2] = {-1, -1};
-            for (int k = 0; k < 2; ++k) {
-                const TmpNode& K = bld.nodes[kids[k]];
-                box_of(kids[k], mn[k], mx[k]);
-                if (K.count > 0) { refs[k] = LeafRef(K.first, K.count); hs.max_leaf_prims = std::max(hs.max_leaf_prims, K.count); }
-                else { child_flat[k] = emit_inner(); refs[k] = child_flat[k]; }
+        // The order is that of a depth-first walk that hands both children of a node their indices when the node is visited
+        // (siblings adjacent, the left subtree before the right): the node visited after A earlier allocations puts its inner
+        // children at 1 + A (and 2 + A).  A follows from the subtree counts -- A(left) = A + c, A(right) = A + c + (inner
+        // nodes below the left child), c = the node's inner children -- so subtrees are laid out independently, in parallel.
+        fn.resize((size_t)inner_below[root] * kNodeStride);  // (uninitialised: the layout writes every node)
+        hs.max_leaf_prims = largest_leaf.load();
+        std::function<void(int, int, int, int)> layout = [&](int tmp, int flat, int A, int level) {
+            for (;;) {
+                const TmpNode& T = bld.nodes[tmp];
+                const int kids[2] = {T.left, T.right};
+                const bool inner[2] = {bld.nodes[kids[0]].count == 0, bld.nodes[kids[1]].count == 0};
+                const int child_flat[2] = {1 + A, 1 + A + (inner[0] ? 1 : 0)};
+                int refs[2];
+                float mn[2][3], mx[2][3];
+                for (int k = 0; k < 2; ++k) {
+                    const TmpNode& K = bld.nodes[kids[k]];
+                    box_of(kids[k], mn[k], mx[k]);
+                    refs[k] = inner[k] ? child_flat[k] : LeafRef(K.first, K.count);
+                }
+                fn[(size_t)flat * kNodeStride + 0] = Float4{mn[0][0], mn[0][1], mn[0][2], mx[0][0]};
+                fn[(size_t)flat * kNodeStride + 1] = Float4{mx[0][1], mx[0][2], mn[1][0], mn[1][1]};
+                fn[(size_t)flat * kNodeStride + 2] = Float4{mn[1][2], mx[1][0], mx[1][1], mx[1][2]};
+                fn[(size_t)flat * kNodeStride + 3] = Float4{IntAsFloat(refs[0]), IntAsFloat(refs[1]), 0, 0};
+                const int c = (inner[0] ? 1 : 0) + (inner[1] ? 1 : 0);
+                const int A_left = A + c, A_right = A + c + (inner[0] ? inner_below[kids[0]] - 1 : 0);
+                if (inner[0] && inner[1]) {
+                    if (level < 4 && nthreads > 1) {
+                        auto fut = std::async(std::launch::async, [&layout, k = kids[0], f = child_flat[0], A_left, level]() { layout(k, f, A_left, level + 1); });
+                        layout(kids[1], child_flat[1], A_right, level + 1);
+                        fut.get();
+                        return;
+                    }
+                    layout(kids[0], child_flat[0], A_left, level + 1);
+                    tmp = kids[1]; flat = child_flat[1]; A = A_right; ++level;  // (tail call)
+                } else if (inner[0]) {
+                    tmp = kids[0]; flat = child_flat[0]; A = A_left; ++level;
+                } else if (inner[1]) {
+                    tmp = kids[1]; flat = child_flat[1]; A = A_right; ++level;
+                } else {
+                    return;
+                }
             }
-            fn[it.flat * kNodeStride + 0] = Float4{mn[0][0], mn[0][1], mn[0][2], mx[0][0]};
-            fn[it.flat * kNodeStride + 1] = Float4{mx[0][1], mx[0][2], mn[1][0], mn[1][1]};
-            fn[it.flat * kNodeStride + 2] = Float4{mn[1][2], mx[1][0], mx[1][1], mx[1][2]};
-            fn[it.flat * kNodeStride + 3] = Float4{IntAsFloat(refs[0]), IntAsFloat(refs[1]), 0, 0};
-            // push right first so the left subtree is laid out right after its parent
-            if (child_flat[1] >= 0) stack.push_back(Item{kids[1], child_flat[1]});
-            if (child_flat[0] >= 0) stack.push_back(Item{kids[0], child_flat[0]});
-        }
+        };
+        layout(root, 0, 0, 0);
     }
     hs.bvh_build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    phase("node layout");
 
     // slots in leaf order
     hs.slots.resize((size_t)N * kSlotStride);
     hs.slot_nrm.resize(N);
     hs.slot_ml.resize(N);
     hs.prim_slot.resize(N);
-    hs.slot_frame.assign((size_t)N * kFrameStride, Float4{0, 0, 0, 0});
-    for (int s = 0; s < N; ++s) {
-        int p = bld.idx[s];
-        if (d->shapes[d->primitives[p].shape].type != JPBRT_SHAPE_SPHERE) {
-            H3 fs, ft, fn;
-            FrameST(H3(pre_nrm[p].x, pre_nrm[p].y, pre_nrm[p].z), &fs, &ft, &fn);
-            hs.slot_frame[(size_t)s * kFrameStride + 0] = Float4{fs.x, fs.y, fs.z, 0};
-            hs.slot_frame[(size_t)s * kFrameStride + 1] = Float4{ft.x, ft.y, ft.z, 0};
-            hs.slot_frame[(size_t)s * kFrameStride + 2] = Float4{fn.x, fn.y, fn.z, 0};
+    hs.slot_frame.resize((size_t)N * kFrameStride);
+    ParallelFor((size_t)N, nthreads, [&](size_t b, size_t e, int) {
+        for (size_t s = b; s < e; ++s) {
+            const int p = bld.idx[s];
+            if (d->shapes[d->primitives[p].shape].type != JPBRT_SHAPE_SPHERE) {
+                H3 fs, ft, fnn;
+                FrameST(H3(pre_nrm[p].x, pre_nrm[p].y, pre_nrm[p].z), &fs, &ft, &fnn);
+                hs.slot_frame[s * kFrameStride + 0] = Float4{fs.x, fs.y, fs.z, 0};
+                hs.slot_frame[s * kFrameStride + 1] = Float4{ft.x, ft.y, ft.z, 0};
+                hs.slot_frame[s * kFrameStride + 2] = Float4{fnn.x, fnn.y, fnn.z, 0};
+            } else {  // (a sphere's frame depends on the hit point: the kernels build it, csrc/intersect.cuh hit_frame)
+                for (int k = 0; k < kFrameStride; ++k) hs.slot_frame[s * kFrameStride + k] = Float4{0, 0, 0, 0};
+            }
+            for (int k = 0; k < kSlotStride; ++k) hs.slots[s * kSlotStride + k] = pre_slots[(size_t)p * kSlotStride + k];
+            hs.slot_nrm[s] = pre_nrm[p];
+            hs.slot_ml[s] = Int2{d->primitives[p].material, d->primitives[p].light};
+            hs.prim_slot[p] = (int)s;
         }
-        for (int k = 0; k < kSlotStride; ++k) hs.slots[(size_t)s * kSlotStride + k] = pre_slots[(size_t)p * kSlotStride + k];
-        hs.slot_nrm[s] = pre_nrm[p];
-        hs.slot_ml[s] = Int2{d->primitives[p].material, d->primitives[p].light};
-        hs.prim_slot[p] = s;
-    }
+    });
+    phase("slots in leaf order");
     return 0;
 }
 
