@@ -201,6 +201,25 @@ void pin_vector(jpbrt_ctx* c, V& v) {
     else cudaGetLastError();
 }
 
+// slot_frame[s] = FFrame(normal of slot s) (geometry.h:344-377) for flat shapes, derived ON THE DEVICE from the uploaded
+// normals: the same IEEE expressions the host used to evaluate (make_frame, dmath.cuh; this file is compiled without FMA
+// contraction), so the values are bit-identical -- and 48 of the 244 bytes per primitive never cross PCIe.
+__global__ void __launch_bounds__(kBlock) k_make_frames(const Float4* __restrict__ slot_nrm, Float4* __restrict__ slot_frame, int n) {
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const float4 nr = ldg4(slot_nrm + s);
+        const int type = __float_as_int(nr.w) & ((1 << kTypeBits) - 1);
+        float4 f0 = make_float4(0, 0, 0, 0), f1 = f0, f2 = f0;  // a sphere's frame depends on the hit point (hit_frame)
+        if (type != SHAPE_SPHERE) {
+            const Frame f = make_frame(mk3(nr));
+            f0 = make_float4(f.s.x, f.s.y, f.s.z, 0.f);
+            f1 = make_float4(f.t.x, f.t.y, f.t.z, 0.f);
+            f2 = make_float4(f.n.x, f.n.y, f.n.z, 0.f);
+        }
+        float4* out = reinterpret_cast<float4*>(slot_frame + (size_t)s * kFrameStride);
+        out[0] = f0; out[1] = f1; out[2] = f2;
+    }
+}
+
 int upload_arrays(jpbrt_ctx* c, size_t* bytes) {
     HostScene& hs = c->hs;
     CU_CHECK(c, c->nodes.Upload(hs.nodes.data(), hs.nodes.size(), c->stream));
@@ -211,7 +230,12 @@ int upload_arrays(jpbrt_ctx* c, size_t* bytes) {
     CU_CHECK(c, c->lights.Upload(hs.lights.data(), hs.lights.size(), c->stream));
     CU_CHECK(c, c->inf_lights.Upload(hs.inf_lights.data(), hs.inf_lights.size(), c->stream));
     CU_CHECK(c, c->prim_slot.Upload(hs.prim_slot.data(), hs.prim_slot.size(), c->stream));
-    CU_CHECK(c, c->slot_frame.Upload(hs.slot_frame.data(), hs.slot_frame.size(), c->stream));
+    {
+        const int n = (int)hs.slot_nrm.size();
+        k_make_frames<<<std::min(148 * 8, (n + kBlock - 1) / kBlock), kBlock, 0, c->stream>>>(c->slot_nrm.ptr, c->slot_frame.ptr, n);
+        CU_CHECK(c, cudaGetLastError());
+        c->kernel_launches++;
+    }
     CU_CHECK(c, c->nee_lights.Upload(hs.nee_lights.data(), hs.nee_lights.size(), c->stream));
     if (bytes) *bytes = hs.Bytes();
     return 0;
@@ -367,7 +391,7 @@ static int finish_upload(jpbrt_ctx* c, int device) {
         (e = c->slot_nrm.Alloc(hs.slot_nrm.size())) != cudaSuccess || (e = c->slot_ml.Alloc(hs.slot_ml.size())) != cudaSuccess ||
         (e = c->materials.Alloc(hs.materials.size())) != cudaSuccess || (e = c->lights.Alloc(hs.lights.size())) != cudaSuccess ||
         (e = c->inf_lights.Alloc(hs.inf_lights.size())) != cudaSuccess || (e = c->prim_slot.Alloc(hs.prim_slot.size())) != cudaSuccess ||
-        (e = c->slot_frame.Alloc(hs.slot_frame.size())) != cudaSuccess || (e = c->nee_lights.Alloc(hs.nee_lights.size())) != cudaSuccess ||
+        (e = c->slot_frame.Alloc(hs.slot_nrm.size() * kFrameStride)) != cudaSuccess || (e = c->nee_lights.Alloc(hs.nee_lights.size())) != cudaSuccess ||
         (e = c->pixel_order.Alloc(hs.pixel_order.size())) != cudaSuccess ||
         (e = c->film.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess ||
         (e = c->film_final.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess || (e = c->dstats.Alloc(ST_COUNT)) != cudaSuccess ||
@@ -375,7 +399,7 @@ static int finish_upload(jpbrt_ctx* c, int device) {
         return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)));
     pin_vector(c, hs.nodes); pin_vector(c, hs.slots); pin_vector(c, hs.slot_nrm); pin_vector(c, hs.slot_ml);
     pin_vector(c, hs.materials); pin_vector(c, hs.lights); pin_vector(c, hs.inf_lights); pin_vector(c, hs.prim_slot);
-    pin_vector(c, hs.slot_frame); pin_vector(c, hs.nee_lights);
+    pin_vector(c, hs.nee_lights);
     rc = upload_arrays(c, nullptr);
     if (rc == 0 && c->pixel_order.Upload(hs.pixel_order.data(), hs.pixel_order.size(), c->stream) != cudaSuccess)
         rc = set_error(c, JPBRT_ERR_CUDA, "pixel order upload failed");

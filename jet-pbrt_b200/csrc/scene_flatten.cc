@@ -1003,19 +1003,9 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, Bv
     hs.slot_nrm.resize(N);
     hs.slot_ml.resize(N);
     hs.prim_slot.resize(N);
-    hs.slot_frame.resize((size_t)N * kFrameStride);
     ParallelFor((size_t)N, nthreads, [&](size_t b, size_t e, int) {
         for (size_t s = b; s < e; ++s) {
             const int p = bld.idx[s];
-            if (d->shapes[d->primitives[p].shape].type != JPBRT_SHAPE_SPHERE) {
-                H3 fs, ft, fnn;
-                FrameST(H3(pre_nrm[p].x, pre_nrm[p].y, pre_nrm[p].z), &fs, &ft, &fnn);
-                hs.slot_frame[s * kFrameStride + 0] = Float4{fs.x, fs.y, fs.z, 0};
-                hs.slot_frame[s * kFrameStride + 1] = Float4{ft.x, ft.y, ft.z, 0};
-                hs.slot_frame[s * kFrameStride + 2] = Float4{fnn.x, fnn.y, fnn.z, 0};
-            } else {  // (a sphere's frame depends on the hit point: the kernels build it, csrc/intersect.cuh hit_frame)
-                for (int k = 0; k < kFrameStride; ++k) hs.slot_frame[s * kFrameStride + k] = Float4{0, 0, 0, 0};
-            }
             for (int k = 0; k < kSlotStride; ++k) hs.slots[s * kSlotStride + k] = pre_slots[(size_t)p * kSlotStride + k];
             hs.slot_nrm[s] = pre_nrm[p];
             hs.slot_ml[s] = Int2{d->primitives[p].material, d->primitives[p].light};

@@ -33,7 +33,8 @@ template <class T>
 using BigVec = std::vector<T, DefaultInitAllocator<T>>;
 
 struct HostScene {
-    BigVec<Float4> nodes, slots, slot_nrm, slot_frame;  // per node / per primitive
+    BigVec<Float4> nodes, slots, slot_nrm;  // per node / per primitive (the shading frames of flat shapes are derived from
+                                            // slot_nrm on the device: c_api.cu k_make_frames)
     std::vector<Float4> materials, lights;
     BigVec<Int2> slot_ml;
     BigVec<int> prim_slot;
@@ -51,7 +52,7 @@ struct HostScene {
     int bvh_depth = 0;    // levels of the tree (root = 1); at most kMaxBvhDepth
     double bvh_device_seconds = 0;  // GPU builder only: upload of the boxes + kernels + download of the tree
     size_t Bytes() const {
-        return (nodes.size() + slots.size() + slot_nrm.size() + materials.size() + lights.size() + slot_frame.size()) * sizeof(Float4) +
+        return (nodes.size() + slots.size() + slot_nrm.size() + materials.size() + lights.size()) * sizeof(Float4) +
                slot_ml.size() * sizeof(Int2) + (inf_lights.size() + prim_slot.size() + nee_lights.size()) * sizeof(int);  // pixel_order is film state, not scene
     }
 };
