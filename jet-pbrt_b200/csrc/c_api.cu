@@ -189,6 +189,12 @@ void drain_events(jpbrt_ctx* c) {
 template <typename K>
 int occupancy_grid(jpbrt_ctx* c, K kernel) {
     int per_sm = 0;
+    // A/B hook: JPBRT_CARVEOUT = preferred shared-memory share of the unified L1 / shared array in percent (0 = all of it to L1).
+    // Measured (profiles/ab/r02_ab_carveout.log): unset == 0 (the kernels use no shared memory to speak of and already get the
+    // whole array as L1); 25 % costs the bunny scene's traversal 1 %, 50 % costs 3-4 %.
+    if (const char* v = getenv("JPBRT_CARVEOUT")) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(v)) != cudaSuccess) cudaGetLastError();
+    }
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0) != cudaSuccess || per_sm <= 0) per_sm = 1;
     return c->sm_count * per_sm;
 }
