@@ -149,7 +149,9 @@ int  jpbrt_render_multi(const jpbrt_scene_desc* desc, int integrator, int spp, u
  *                      0 off, else cell bits per axis 1..6, +16 to include the octant
  *   traversal tunables "trav_blocks" (5 or 6 resident blocks per SM; other values are clamped), "refill_min" (idle lanes
  *                      that trigger a refill, 1..32, -1 automatic), "min_inner" (lanes at inner nodes below which a warp's
- *                      node phase ends, 0..32, -1 automatic)
+ *                      node phase ends, 0..32, -1 automatic), "node_format" (-1 automatic, 0 64-byte float BVH nodes,
+ *                      1 32-byte nodes quantised to a 16-bit grid over the scene bounds -- one load per node step, boxes
+ *                      rounded outwards; resident for trees of at most 2^20 nodes, automatic from 1,024 nodes)
  * The film is accumulated with float atomics: a render is reproducible up to float summation order (<= 1e-6 relative),
  * not bit for bit; the PATHS depend only on (seed, pixel, sample index). */
 int jpbrt_set_option(jpbrt_ctx* ctx, const char* name, long long value);

@@ -78,7 +78,7 @@ struct jpbrt_ctx {
     std::string error;
     HostScene hs;
     // scene on the device
-    DevBuf<Float4> nodes, slots, slot_nrm, materials, lights, slot_frame;
+    DevBuf<Float4> nodes, qnodes, slots, slot_nrm, materials, lights, slot_frame;
     DevBuf<Int2> slot_ml;
     DevBuf<int> inf_lights, prim_slot, nee_lights, pixel_order;
     DevScene dsc{};
@@ -104,7 +104,7 @@ struct jpbrt_ctx {
     // one wavefront (generate + all iterations) captured as a CUDA graph; rebuilt when an option that changes the
     // launch sequence changes
     cudaGraphExec_t wave_graph = nullptr;
-    int wave_graph_key = -1;
+    long long wave_graph_key = -1;
     unsigned long long wave_graph_launches = 0;
     bool opt_use_graph = true;
     // options
@@ -116,6 +116,8 @@ struct jpbrt_ctx {
     long long opt_band_pixels = 0;  // pixels per band of a wavefront (0 = default 2^20); >= the frame: no banding
     int opt_integrator = JPBRT_INTEGRATOR_PATH;  // jpbrt_integrator: which FIntegrator::Li the passes evaluate
     bool has_mirror = false;                     // Whitted traces a mirror vertex twice: the ray tree can grow
+    int opt_node_format = -1;  // -1 automatic, 0 64-byte float nodes, 1 32-byte quantised nodes (if the scene uploaded them)
+    bool has_qnodes = false;   // the quantised copy of the tree is resident (scenes of at most kQNodesMaxNodes nodes)
     int opt_sort_rays = 0;    // 0 off; else cell bits per axis (1..6) + 16 x (direction octant in the key)
     int opt_trav_blocks = 6;  // resident blocks per SM the traversal kernels are compiled for: 6 (40 registers, default) or 5 (48)
     unsigned kinds_present = 0;  // bit k set: some material of the scene can build BSDF kind k
@@ -186,6 +188,19 @@ void drain_events(jpbrt_ctx* c) {
     c->pending_events.clear();
 }
 
+// Which node format the production traversal kernels walk.  Quantised 32-byte nodes halve the node loads -- what the L1 pipe,
+// the traversal kernels' bound, spends most of its time on -- at the price of 12 PRMT per node step and boxes rounded outwards by
+// up to 3 grid cells.  Measured (profiles/ab/r02_ab_qnodes.log): bunny scene (10 k nodes) k_connect -5.9 %; trees of 15 / 33
+// nodes (Cornell, glossy) +5-9 % slower; 5 M triangles k_extend -4 %, but there the fatter boxes also admit primitives whose
+// (reference-exact, float-sloppy at t ~ 1000) edge tests accept rays that miss their bounds by more than the float nodes'
+// padding -- 0.17 % of camera rays find a different first hit than with the float nodes.  Automatic = trees of 1,024 to 2^20 nodes.
+constexpr int kQNodesMinNodes = 1024;  // (kQNodesMaxNodes: scene_flatten.h -- larger trees get no quantised copy at all)
+static bool use_qnodes(const jpbrt_ctx* c) {
+    if (!c->has_qnodes || c->opt_node_format == 0) return false;
+    if (c->opt_node_format == 1) return true;
+    return (int)(c->hs.nodes.size() / kNodeStride) >= kQNodesMinNodes;
+}
+
 template <typename K>
 int occupancy_grid(jpbrt_ctx* c, K kernel) {
     int per_sm = 0;
@@ -229,6 +244,7 @@ __global__ void __launch_bounds__(kBlock) k_make_frames(const Float4* __restrict
 int upload_arrays(jpbrt_ctx* c, size_t* bytes) {
     HostScene& hs = c->hs;
     CU_CHECK(c, c->nodes.Upload(hs.nodes.data(), hs.nodes.size(), c->stream));
+    if (c->has_qnodes) CU_CHECK(c, c->qnodes.Upload(hs.qnodes.data(), hs.qnodes.size(), c->stream));
     CU_CHECK(c, c->slots.Upload(hs.slots.data(), hs.slots.size(), c->stream));
     CU_CHECK(c, c->slot_nrm.Upload(hs.slot_nrm.data(), hs.slot_nrm.size(), c->stream));
     CU_CHECK(c, c->slot_ml.Upload(hs.slot_ml.data(), hs.slot_ml.size(), c->stream));
@@ -243,7 +259,7 @@ int upload_arrays(jpbrt_ctx* c, size_t* bytes) {
         c->kernel_launches++;
     }
     CU_CHECK(c, c->nee_lights.Upload(hs.nee_lights.data(), hs.nee_lights.size(), c->stream));
-    if (bytes) *bytes = hs.Bytes();
+    if (bytes) *bytes = hs.Bytes() + (c->has_qnodes ? hs.qnodes.size() * sizeof(Float4) : 0);
     return 0;
 }
 
@@ -393,7 +409,9 @@ static int finish_upload(jpbrt_ctx* c, int device) {
         return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError())));
     HostScene& hs = c->hs;
     cudaError_t e = cudaSuccess;
-    if ((e = c->nodes.Alloc(hs.nodes.size())) != cudaSuccess || (e = c->slots.Alloc(hs.slots.size())) != cudaSuccess ||
+    // The quantised copy of the tree rides along for scenes whose trees are neither tiny nor huge (see use_qnodes()).
+    c->has_qnodes = hs.nodes.size() / kNodeStride <= (size_t)kQNodesMaxNodes && !hs.qnodes.empty();
+    if ((e = c->nodes.Alloc(hs.nodes.size())) != cudaSuccess || (e = c->qnodes.Alloc(c->has_qnodes ? hs.qnodes.size() : 1)) != cudaSuccess || (e = c->slots.Alloc(hs.slots.size())) != cudaSuccess ||
         (e = c->slot_nrm.Alloc(hs.slot_nrm.size())) != cudaSuccess || (e = c->slot_ml.Alloc(hs.slot_ml.size())) != cudaSuccess ||
         (e = c->materials.Alloc(hs.materials.size())) != cudaSuccess || (e = c->lights.Alloc(hs.lights.size())) != cudaSuccess ||
         (e = c->inf_lights.Alloc(hs.inf_lights.size())) != cudaSuccess || (e = c->prim_slot.Alloc(hs.prim_slot.size())) != cudaSuccess ||
@@ -403,7 +421,9 @@ static int finish_upload(jpbrt_ctx* c, int device) {
         (e = c->film_final.Alloc((size_t)hs.width * hs.height * 3)) != cudaSuccess || (e = c->dstats.Alloc(ST_COUNT)) != cudaSuccess ||
         (e = c->pass_args.Alloc(1)) != cudaSuccess)
         return fail(set_error(nullptr, JPBRT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e)));
-    pin_vector(c, hs.nodes); pin_vector(c, hs.slots); pin_vector(c, hs.slot_nrm); pin_vector(c, hs.slot_ml);
+    pin_vector(c, hs.nodes);
+    if (c->has_qnodes) pin_vector(c, hs.qnodes);
+    pin_vector(c, hs.slots); pin_vector(c, hs.slot_nrm); pin_vector(c, hs.slot_ml);
     pin_vector(c, hs.materials); pin_vector(c, hs.lights); pin_vector(c, hs.inf_lights); pin_vector(c, hs.prim_slot);
     pin_vector(c, hs.nee_lights);
     rc = upload_arrays(c, nullptr);
@@ -412,7 +432,8 @@ static int finish_upload(jpbrt_ctx* c, int device) {
     if (rc != 0) { g_last_error = c->error; return fail(rc); }
     DevScene& d = c->dsc;
     d.pixel_order = c->pixel_order.ptr;
-    d.nodes = c->nodes.ptr; d.slots = c->slots.ptr; d.slot_nrm = c->slot_nrm.ptr; d.slot_ml = c->slot_ml.ptr;
+    d.nodes = c->nodes.ptr; d.qnodes = c->qnodes.ptr; d.slots = c->slots.ptr;
+    for (int a = 0; a < 3; ++a) { d.q_origin[a] = hs.q_origin[a]; d.q_cell[a] = hs.q_cell[a]; } d.slot_nrm = c->slot_nrm.ptr; d.slot_ml = c->slot_ml.ptr;
     d.materials = c->materials.ptr; d.lights = c->lights.ptr; d.inf_lights = c->inf_lights.ptr; d.prim_slot = c->prim_slot.ptr;
     d.slot_frame = c->slot_frame.ptr; d.nee_lights = c->nee_lights.ptr;
     d.n_nee_lights = (int)hs.nee_lights.size();
@@ -599,6 +620,7 @@ int jpbrt_set_option(jpbrt_ctx* c, const char* name, long long value) {
         return 0;
     }
     if (!strcmp(name, "min_inner")) { c->opt_min_inner = (int)std::max(-1ll, std::min(32ll, value)); return 0; }
+    if (!strcmp(name, "node_format")) { c->opt_node_format = (int)std::max(-1ll, std::min(1ll, value)); return 0; }
     if (!strcmp(name, "refill_min")) { c->opt_refill_min = (int)std::max(-1ll, std::min(32ll, value)); return 0; }
     return set_error(c, JPBRT_ERR_INVALID, "unknown option '%s'", name);
 }
@@ -621,6 +643,7 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
     // the 6-block traversal kernels run WITHOUT the full-stack test of every push (intersect.cuh: GUARD): only for trees whose
     // depth the uploader verified; a deeper tree (test hook) takes the guarded 5-block kernels, which count what they lose
     const bool fast6 = c->opt_trav_blocks >= 6 && c->hs.bvh_depth <= kMaxBvhDepth;
+    const bool qn = fast6 && use_qnodes(c);  // (the counting, 5-block and reordering variants walk the float nodes)
     for (int it = 0; it < (debug ? 1 : c->n_iters); ++it) {
         if (sorting && it > 0) {
             // reordering: bins were counted while bounce it-1 appended its rays; prefix-sum them, place every ray, clear the bins
@@ -636,6 +659,7 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
             StageTimer t(c, 1);
             if (count) k_extend<true, 5><<<c->grid_extend_c, kBlock, 0, c->stream>>>(p, it);
             else if (sorting && it > 0 && fast6) k_extend<false, kTravMinBlocks, true><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
+            else if (qn) k_extend<false, kTravMinBlocks, false, true><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
             else if (fast6) k_extend<false, kTravMinBlocks><<<c->grid_extend6, kBlock, 0, c->stream>>>(p, it);
             else k_extend<false, 5><<<c->grid_extend, kBlock, 0, c->stream>>>(p, it);
             c->kernel_launches++;
@@ -658,6 +682,7 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
             }
             StageTimer t(c, 3);
             if (count) k_connect<true, 5><<<c->grid_connect_c, kBlock, 0, c->stream>>>(p, it);
+            else if (qn) k_connect<false, kTravMinBlocks, true><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
             else if (fast6) k_connect<false, kTravMinBlocks><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
             else k_connect<false, 5><<<c->grid_connect, kBlock, 0, c->stream>>>(p, it);
             c->kernel_launches++;
@@ -678,6 +703,7 @@ static int queue_wavefront(jpbrt_ctx* c, bool count) {
         if (it < c->n_iters - 1 || c->hs.has_null_material) {  // no NEE at bounce == maxDepth (integrator.cc:340)
             StageTimer t(c, 3);
             if (count) k_connect<true, 5><<<c->grid_connect_c, kBlock, 0, c->stream>>>(p, it);
+            else if (qn) k_connect<false, kTravMinBlocks, true><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
             else if (fast6) k_connect<false, kTravMinBlocks><<<c->grid_connect6, kBlock, 0, c->stream>>>(p, it);
             else k_connect<false, 5><<<c->grid_connect, kBlock, 0, c->stream>>>(p, it);
             c->kernel_launches++;
@@ -721,7 +747,7 @@ int jpbrt_render_pass(jpbrt_ctx* c, int sample_begin, int sample_count, uint64_t
     const bool count = c->opt_count_traversal;
     // Graph replay needs a launch sequence that never changes: no per-launch events, no counting variant.
     const bool use_graph = c->opt_use_graph && !c->opt_stage_timing && !count;
-    const int graph_key = (((c->opt_integrator * 16 + c->opt_trav_blocks) * 64 + (c->opt_refill_min + 1)) * 64 + (c->opt_min_inner + 1)) * 64 + c->opt_sort_rays;
+    const long long graph_key = (((((long long)c->opt_integrator * 16 + c->opt_trav_blocks) * 64 + (c->opt_refill_min + 1)) * 64 + (c->opt_min_inner + 1)) * 64 + c->opt_sort_rays) * 4 + (c->opt_node_format + 1);
     if (use_graph && (c->wave_graph == nullptr || c->wave_graph_key != graph_key)) {
         if (c->wave_graph) { cudaGraphExecDestroy(c->wave_graph); c->wave_graph = nullptr; }
         cudaGraph_t graph = nullptr;

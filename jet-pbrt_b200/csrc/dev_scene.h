@@ -20,6 +20,9 @@ namespace jpbrt {
 //            n2 = (Rmin.z Rmax.x Rmax.y Rmax.z) n3 = (int left, int right, -, -)
 // child reference >= 0: inner node index;  < 0: leaf, ~ref = (first_slot << 4) | count
 constexpr int kNodeStride = 4;
+// ---- quantised node (32 B): q0 = (Lmin.x|Lmin.y<<16, Lmin.z|Lmax.x<<16, Lmax.y|Lmax.z<<16, Rmin.x|Rmin.y<<16)
+//                             q1 = (Rmin.z|Rmax.x<<16, Rmax.y|Rmax.z<<16, int left, int right);  plane = q_origin + q * q_cell
+constexpr int kQNodeStride = 2;
 constexpr int kLeafCountBits = 4;
 constexpr int kMaxLeafPrims = 4;
 
@@ -60,6 +63,7 @@ struct Int2 { int x, y; };
 // Passed to kernels by value (pointers are device pointers).
 struct DevScene {
     const Float4* nodes;
+    const Float4* qnodes;  // the same tree with 32-byte quantised nodes (intersect.cuh: JPB_QNODES)
     const Float4* slots;
     const Float4* slot_nrm;
     const Int2*   slot_ml;
@@ -74,6 +78,7 @@ struct DevScene {
     int max_depth;
     int max_leaf_prims;  // most primitives any leaf holds (<= kMaxLeafPrims unless JPBRT_BVH_LEAF asked for more)
     int width, height;
+    float q_origin[3], q_cell[3];  // the quantised nodes' grid
     float world_radius;  // FEnvironmentLight::worldRadius (light.cc:26-33)
     DevCamera cam;
 };

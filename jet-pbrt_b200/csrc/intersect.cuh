@@ -141,24 +141,26 @@ constexpr int kTraversalStack = 64;     // deepest node stack a ray can use (ent
 constexpr int kTravDone = 0x7fffffff;  // `cur` value of a lane whose stack is empty (or that found an any-hit)
 constexpr int kTravBlock = 256;        // threads per block of every kernel that traverses (wavefront.cuh: kBlock)
 
-// Where the node stack lives.  Round 1's ncu profile showed the local-memory stack as a quarter of the traversal kernels'
-// load/store instructions, with its push / pop branches running at 5.5 / 1.9 of 32 lanes, so round 2 built the obvious
-// alternative: the first JPB_SMEM_STACK entries of every lane's stack in SHARED memory, laid out [entry][thread] (lane l
-// always hits bank l: one conflict-free wavefront per push or pop whatever the 32 depths are), deeper entries spilling to
-// the local array.  Measured on B200 (profiles/ab/r02_ab_stack.log, 48 spp): shared depth 8 / 12 / 16 is 4-5 % SLOWER than
-// the all-local stack on every scene (bunny k_extend 13.09 vs 12.52 ms, k_connect 12.25 vs 11.84; Cornell 11.16 vs 10.49):
-// the local stack's lines live in L1 anyway (interleaved per lane, so a converged push is one wavefront too), while the
-// shared variant pays two extra address instructions per access and takes 48-96 KB per SM away from L1.  Default: 0 = the
-// whole stack in local memory; the shared variant stays buildable for A/B runs (-DJPB_SMEM_STACK=8).
-#ifndef JPB_SMEM_STACK
-#define JPB_SMEM_STACK 0
-#endif
+// Where the node stack lives: LOCAL memory, interleaved per lane by the hardware (a converged push is one L1 wavefront).
+// Round 2 built the obvious alternative -- the first 8 / 12 / 16 entries of every lane's stack in SHARED memory, [entry][thread]
+// (conflict-free at any mix of depths), deeper entries spilling to local -- and measured it 4-5 % SLOWER on every scene
+// (profiles/ab/r02_ab_stack.log: bunny k_extend 13.09 vs 12.52 ms, k_connect 12.25 vs 11.84): two more address instructions
+// per access and 48-96 KB per SM taken from L1.  (The variant lived behind -DJPB_SMEM_STACK until the pointer stack below.)
+//
 // GUARD (template parameter of the walk): test every push against the end of the stack and count what does not fit.  The
 // uploader bounds the depth of every tree it installs (c_api.cu: kMaxBvhDepth < kTraversalStack), and a walk's stack never
 // holds more entries than the tree has levels, so the production kernels run unguarded; the COUNT variants, the 5-block
 // variants and any scene installed with a deeper tree (test hook JPBRT_TEST_ALLOW_DEEP_BVH) keep the guard and its counter.
-constexpr int kSmemStack = JPB_SMEM_STACK;
-static_assert(kSmemStack >= 0 && kSmemStack < kTraversalStack, "JPB_SMEM_STACK out of range");
+
+// QUANTISED NODES (template parameter QN of the walk): a 32-byte node -- twelve 16-bit plane indices on a grid over the (padded) scene bounds + the two
+// child references -- fetched with ONE 256-bit load instead of two.  The planes are rebuilt without a conversion instruction:
+// PRMT puts the 16 bits under the exponent of 2^23 (float 8388608 + q), and the ray's slab constants absorb the offset:
+// t = (8388608 + q) * (cell * inv) + ((origin - o) * inv - 8388608 * cell * inv).  The cancellation costs up to one cell of
+// plane position, so the uploader rounds every box outwards by 2 more cells (scene_flatten.cc); boxes only prune, hits are
+// the primitive tests', so the images cannot change -- only how many boxes a ray enters.
+// Measured on B200 (profiles/ab/r02_ab_qnodes.log): bunny scene k_connect -5.9 %, k_extend +-0; 5 M triangles k_extend -4 %,
+// k_connect +0.4 %; Cornell / glossy (trees of 15 / 33 nodes that live in L1 whatever their size) +5-9 % SLOWER: the decode's 12
+// PRMT are pure cost there.  QN is therefore a template parameter of the walk and the library picks per scene (c_api.cu).
 
 // Per-lane traversal state.  The BVH walk is a state machine so that a warp can (a) run the inner-node
 // step and the leaf step in separate, converged phases (while-while traversal) and (b) hand a finished
@@ -166,50 +168,57 @@ static_assert(kSmemStack >= 0 && kSmemStack < kTraversalStack, "JPB_SMEM_STACK o
 struct Trav {
     f3 o, d, inv, oi;
     float tmin, tmax;
-    int cur, sp, hit;
+    int cur, hit;
+    int* top;  // one past the newest entry of this lane's node stack
 };  // the node stack is separate (shared + local arrays) so that these scalars stay in registers
 
 // This lane's node stack.  Entry 0 is a sentinel (kTravDone) that is never overwritten: popping an empty stack yields
 // "done" without a compare.
+// The stack position is a POINTER into the lane's local array (round 2: with an index the compiler spent an LEA per push and
+// per pop and branched around the push; with the pointer the push is one predicated STL + IADD: 54 instead of 62 instructions
+// per node step -- for 0.3 % of the kernels' time, which is how the L1 pipe, not the issue rate, was found to be their bound).
 struct TravStack {
-    int* sm;  // &shared[0][threadIdx.x]; entry e is sm[e * kTravBlock]
-    int* lm;  // local spill, entries kSmemStack .. kTraversalStack-1
+    int* lm;  // the lane's stack, kTraversalStack entries of local memory
     unsigned long long* dropped;  // stats counter of pushes that found the stack full (never in the five configs)
-    __device__ __forceinline__ void init() const {
-        if (kSmemStack > 0) sm[0] = kTravDone; else lm[0] = kTravDone;
-    }
+    __device__ __forceinline__ void init() const { lm[0] = kTravDone; }
     template <bool GUARD>
-    __device__ __forceinline__ void push(int& sp, int v) const {
-        if (kSmemStack > 0 && sp < kSmemStack) {
-            sm[sp * kTravBlock] = v;
-            ++sp;
-        } else if (!GUARD || sp < kTraversalStack) {
-            lm[sp - kSmemStack] = v;
-            ++sp;
-        } else if (dropped) {
-            atomicAdd(dropped, 1ull);  // the far child is lost: counted, reported as invalid_contributions / stack_overflows
-        }
+    __device__ __forceinline__ void push(int*& top, int v) const {
+        if (!GUARD || top < lm + kTraversalStack) *top++ = v;
+        else if (dropped) atomicAdd(dropped, 1ull);  // the far child is lost: counted, reported as invalid_contributions / stack_overflows
     }
-    __device__ __forceinline__ int pop(int& sp) const {
-        --sp;
-        if (kSmemStack > 0 && sp < kSmemStack) return sm[sp * kTravBlock];
-        return lm[sp - kSmemStack];
-    }
+    __device__ __forceinline__ int pop(int*& top) const { return *--top; }
 };
 
-__device__ __forceinline__ void trav_init(Trav& t, const f3& o, const f3& d, float tmin, float tmax) {
+// One axis of the quantised walk's slab constants.  plane(q) = origin + q * cell;  t(q) = (8388608 + q) * cinv + oiq  with
+// cinv = cell * inv and oiq = (origin - o) * inv - 8388608 * cinv.  If 8388608 * cinv leaves the float range (a direction
+// component of ~1e-34, or a scene spanning 30 orders of magnitude) both constants become NaN: FMNMX ignores NaN operands, so the
+// axis drops out of the slab test -- conservative -- instead of producing planes at -inf that would reject every box.
+__device__ __forceinline__ void quant_axis(float origin, float cell, float o, float inv, float& cinv, float& oiq) {
+    cinv = cell * inv;
+    oiq = __fmaf_rn(origin - o, inv, -8388608.f * cinv);
+    if (!(fabsf(oiq) <= 3.4028234664e38f)) cinv = oiq = __int_as_float(0x7fc00000);
+}
+
+template <bool QN = false>
+__device__ __forceinline__ void trav_init(const DevScene& sc, Trav& t, const f3& o, const f3& d, float tmin, float tmax) {
     t.o = o;
     t.d = d;
-    t.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-    // slab distances as one explicit FMA each: bound * inv - o * inv.  Its rounding error (about one ulp of
-    // |o * inv|) is covered by the padding baked into every stored box (4e-6 * the largest ray-origin
-    // coordinate, scene_flatten.cc) plus the 2*gamma(3) widening of tfar.
-    t.oi = mk3(-(o.x * t.inv.x), -(o.y * t.inv.y), -(o.z * t.inv.z));
+    const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    if (QN) {
+        quant_axis(sc.q_origin[0], sc.q_cell[0], o.x, inv.x, t.inv.x, t.oi.x);
+        quant_axis(sc.q_origin[1], sc.q_cell[1], o.y, inv.y, t.inv.y, t.oi.y);
+        quant_axis(sc.q_origin[2], sc.q_cell[2], o.z, inv.z, t.inv.z, t.oi.z);
+    } else {
+        t.inv = inv;
+        // slab distances as one explicit FMA each: bound * inv - o * inv.  Its rounding error (about one ulp of
+        // |o * inv|) is covered by the padding baked into every stored box (4e-6 * the largest ray-origin
+        // coordinate, scene_flatten.cc) plus the 2*gamma(3) widening of tfar.
+        t.oi = mk3(-(o.x * t.inv.x), -(o.y * t.inv.y), -(o.z * t.inv.z));
+    }
     t.tmin = tmin;
     t.tmax = tmax;
     t.cur = 0;  // root (always an inner node, scene_flatten.cc)
-    t.sp = 1;   // above the sentinel
-    t.hit = -1;
+    t.hit = -1;  // (t.top: set by the caller, which owns the stack)
 }
 
 __device__ __forceinline__ bool trav_at_inner(const Trav& t) { return (unsigned)t.cur < (unsigned)kTravDone; }
@@ -232,33 +241,53 @@ struct TravCounts {
 #ifndef JPB_ANYHIT_UNORDERED
 #define JPB_ANYHIT_UNORDERED 1
 #endif
-template <bool COUNT, bool ANY_HIT = false, bool GUARD = true>
+template <bool COUNT, bool ANY_HIT = false, bool GUARD = true, bool QN = false>
 __device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, const TravStack& stk, TravCounts& cnt, unsigned step_mask) {
     const float widen = 1.0000004f;  // 1 + 2*gamma(3): pbrt's conservative slab bound
-    const Float4* np = sc.nodes + (size_t)t.cur * kNodeStride;
-    float4 n0, n1, n2, n3;
-    ldg8<kWideNodeLoads>(np, n0, n1);
-    ldg8<kWideNodeLoads>(np + 2, n2, n3);
+    float lx0, ly0, lz0, lx1, ly1, lz1, rx0, ry0, rz0, rx1, ry1, rz1;  // the twelve planes: left min/max, right min/max
+    int cl, cr;
+    if (QN) {
+        float4 q0, q1;
+        ldg8<true>(sc.qnodes + (size_t)t.cur * kQNodeStride, q0, q1);
+        const unsigned w0 = __float_as_uint(q0.x), w1 = __float_as_uint(q0.y), w2 = __float_as_uint(q0.z);
+        const unsigned w3 = __float_as_uint(q0.w), w4 = __float_as_uint(q1.x), w5 = __float_as_uint(q1.y);
+        const unsigned two23 = 0x4B000000u;  // 8388608.f: a 16-bit q in its low mantissa bits reads 8388608 + q
+        lx0 = __uint_as_float(__byte_perm(w0, two23, 0x7610)); ly0 = __uint_as_float(__byte_perm(w0, two23, 0x7632));
+        lz0 = __uint_as_float(__byte_perm(w1, two23, 0x7610)); lx1 = __uint_as_float(__byte_perm(w1, two23, 0x7632));
+        ly1 = __uint_as_float(__byte_perm(w2, two23, 0x7610)); lz1 = __uint_as_float(__byte_perm(w2, two23, 0x7632));
+        rx0 = __uint_as_float(__byte_perm(w3, two23, 0x7610)); ry0 = __uint_as_float(__byte_perm(w3, two23, 0x7632));
+        rz0 = __uint_as_float(__byte_perm(w4, two23, 0x7610)); rx1 = __uint_as_float(__byte_perm(w4, two23, 0x7632));
+        ry1 = __uint_as_float(__byte_perm(w5, two23, 0x7610)); rz1 = __uint_as_float(__byte_perm(w5, two23, 0x7632));
+        cl = __float_as_int(q1.z);
+        cr = __float_as_int(q1.w);
+    } else {
+        const Float4* np = sc.nodes + (size_t)t.cur * kNodeStride;
+        float4 n0, n1, n2, n3;
+        ldg8<kWideNodeLoads>(np, n0, n1);
+        ldg8<kWideNodeLoads>(np + 2, n2, n3);
+        // left box: min = (n0.x n0.y n0.z), max = (n0.w n1.x n1.y);  right box: min = (n1.z n1.w n2.x), max = (n2.y n2.z n2.w)
+        lx0 = n0.x; ly0 = n0.y; lz0 = n0.z; lx1 = n0.w; ly1 = n1.x; lz1 = n1.y;
+        rx0 = n1.z; ry0 = n1.w; rz0 = n2.x; rx1 = n2.y; ry1 = n2.z; rz1 = n2.w;
+        cl = __float_as_int(n3.x);
+        cr = __float_as_int(n3.y);
+    }
     if (COUNT) {
         cnt.box += 2;
         const unsigned same = __match_any_sync(step_mask, t.cur);  // the lanes of this step that sit on the same node
         if ((threadIdx.x & 31) == __ffs(same) - 1) cnt.node_fetch += 1;
     }
-    // left box: min = (n0.x n0.y n0.z), max = (n0.w n1.x n1.y)
-    float a0 = __fmaf_rn(n0.x, t.inv.x, t.oi.x), a1 = __fmaf_rn(n0.w, t.inv.x, t.oi.x);
-    float b0 = __fmaf_rn(n0.y, t.inv.y, t.oi.y), b1 = __fmaf_rn(n1.x, t.inv.y, t.oi.y);
-    float c0 = __fmaf_rn(n0.z, t.inv.z, t.oi.z), c1 = __fmaf_rn(n1.y, t.inv.z, t.oi.z);
+    float a0 = __fmaf_rn(lx0, t.inv.x, t.oi.x), a1 = __fmaf_rn(lx1, t.inv.x, t.oi.x);
+    float b0 = __fmaf_rn(ly0, t.inv.y, t.oi.y), b1 = __fmaf_rn(ly1, t.inv.y, t.oi.y);
+    float c0 = __fmaf_rn(lz0, t.inv.z, t.oi.z), c1 = __fmaf_rn(lz1, t.inv.z, t.oi.z);
     const float ltn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), t.tmin));
     const float ltf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), t.tmax));
-    // right box: min = (n1.z n1.w n2.x), max = (n2.y n2.z n2.w)
-    a0 = __fmaf_rn(n1.z, t.inv.x, t.oi.x); a1 = __fmaf_rn(n2.y, t.inv.x, t.oi.x);
-    b0 = __fmaf_rn(n1.w, t.inv.y, t.oi.y); b1 = __fmaf_rn(n2.z, t.inv.y, t.oi.y);
-    c0 = __fmaf_rn(n2.x, t.inv.z, t.oi.z); c1 = __fmaf_rn(n2.w, t.inv.z, t.oi.z);
+    a0 = __fmaf_rn(rx0, t.inv.x, t.oi.x); a1 = __fmaf_rn(rx1, t.inv.x, t.oi.x);
+    b0 = __fmaf_rn(ry0, t.inv.y, t.oi.y); b1 = __fmaf_rn(ry1, t.inv.y, t.oi.y);
+    c0 = __fmaf_rn(rz0, t.inv.z, t.oi.z); c1 = __fmaf_rn(rz1, t.inv.z, t.oi.z);
     const float rtn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), t.tmin));
     const float rtf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), t.tmax));
     const bool hl = ltn <= ltf * widen;
     const bool hr = rtn <= rtf * widen;
-    const int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
     const bool both = hl && hr;
     // the nearer child first, left on ties (the reference's order, bvh.h:99-100): right_first = both ? ltn > rtn : hr, spelled
     // as one predicate expression (4 fewer instructions per step than the select chain the ternary compiled to)
@@ -266,8 +295,8 @@ __device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, cons
                                                                : (hr & (!hl | (ltn > rtn)));
     const int near = right_first ? cr : cl;
     const int far = right_first ? cl : cr;
-    if (both) stk.push<GUARD>(t.sp, far);  // (prefetching the far child measured 3-6 % slower)
-    t.cur = (hl || hr) ? near : stk.pop(t.sp);
+    if (both) stk.push<GUARD>(t.top, far);  // (prefetching the far child measured 3-6 % slower)
+    t.cur = (hl || hr) ? near : stk.pop(t.top);
 }
 
 // One leaf: test its (<= 4) primitives, then pop.
@@ -291,7 +320,7 @@ __device__ __forceinline__ void trav_leaf_step(const DevScene& sc, Trav& t, cons
                 if (intersect_slot(sc.slots + (size_t)s * kSlotStride, sc.slot_nrm + s, t.o, t.d, t.tmin, t.tmax)) { t.hit = s; found = true; }
             }
         }
-        t.cur = (ANY_HIT && found) ? kTravDone : stk.pop(t.sp);
+        t.cur = (ANY_HIT && found) ? kTravDone : stk.pop(t.top);
         return;
     }
     for (int k = 0; k < n; ++k) {
@@ -301,7 +330,7 @@ __device__ __forceinline__ void trav_leaf_step(const DevScene& sc, Trav& t, cons
             if (ANY_HIT) { t.cur = kTravDone; return; }
         }
     }
-    t.cur = stk.pop(t.sp);
+    t.cur = stk.pop(t.top);
 }
 
 
@@ -360,7 +389,7 @@ __device__ __forceinline__ void trav_leaf_phase_shared(const DevScene& sc, Trav&
             const float r = __uint_as_float(items[off + k]);
             if (r < t.tmax) { t.tmax = r; t.hit = first + k; found = true; }
         }
-        t.cur = (ANY_HIT && found) ? kTravDone : stk.pop(t.sp);
+        t.cur = (ANY_HIT && found) ? kTravDone : stk.pop(t.top);
     }
     __syncwarp();  // the list is rewritten by the next phase
 }
@@ -395,20 +424,19 @@ __device__ __forceinline__ void trav_leaf_phase_shared(const DevScene& sc, Trav&
 #ifndef JPB_NODE_UNROLL
 #define JPB_NODE_UNROLL 2
 #endif
-template <bool ANY_HIT, bool COUNT, bool GUARD = true, typename IO>
+template <bool ANY_HIT, bool COUNT, bool GUARD = true, bool QN = false, typename IO>
 __device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* work, const IO& io, int refill_min, int min_inner,
                                                TravCounts& cnt, unsigned long long* dropped = nullptr) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    __shared__ int s_stack[(kSmemStack > 0 ? kSmemStack : 1) * kTravBlock];
     __shared__ unsigned s_items[JPB_LEAF_SHARE ? kTravBlock * kMaxLeafPrims : 1];  // per warp: 32 * kMaxLeafPrims leaf-phase items
     const bool share_leaves = JPB_LEAF_SHARE && !COUNT && sc.n_slots < (1 << 27) && sc.max_leaf_prims <= kMaxLeafPrims;
-    int l_stack[kTraversalStack - kSmemStack];
-    const TravStack stk{s_stack + threadIdx.x, l_stack, dropped};
+    int l_stack[kTraversalStack];
+    const TravStack stk{l_stack, dropped};
     stk.init();
     Trav t;
     t.cur = kTravDone;
-    t.sp = 1;
+    t.top = l_stack + 1;
     int idx = -1;
     bool exhausted = false;
     for (;;) {
@@ -424,7 +452,8 @@ __device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* w
                     f3 o, d;
                     float tmin, tmax;
                     if (io.load(i, o, d, tmin, tmax)) {
-                        trav_init(t, o, d, tmin, tmax);
+                        trav_init<QN>(sc, t, o, d, tmin, tmax);
+                        t.top = l_stack + 1;  // above the sentinel
                         idx = i;
                     }
                 }
@@ -446,7 +475,7 @@ __device__ __forceinline__ void traverse_queue(const DevScene& sc, int n, int* w
 #pragma unroll
             for (int u = 0; u < JPB_NODE_UNROLL; ++u) {
                 const unsigned step_mask = COUNT ? (u == 0 ? m_inner : __ballot_sync(full, trav_at_inner(t))) : 0u;
-                if (trav_at_inner(t)) trav_node_step<COUNT, ANY_HIT, GUARD>(sc, t, stk, cnt, step_mask);
+                if (trav_at_inner(t)) trav_node_step<COUNT, ANY_HIT, GUARD, QN>(sc, t, stk, cnt, step_mask);
             }
         }
         const unsigned leaf_mask = COUNT ? __ballot_sync(full, trav_at_leaf(t)) : 0u;

@@ -995,6 +995,53 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, Bv
         };
         layout(root, 0, 0, 0);
     }
+    {
+        // Quantised copy of the tree (intersect.cuh JPB_QNODES): every plane of every (padded) child box as a 16-bit index on a
+        // grid over the padded scene bounds, rounded OUTWARDS and then moved out by kSlack more cells -- the kernels rebuild a
+        // plane as (2^23 + q) * (cell / d) + const, whose cancellation can misplace it by up to one cell.
+        constexpr int kSlack = 2;
+        constexpr double kCells = 65520.0;  // planes of scene geometry fall in [4, 65524]; with rounding + slack in [1, 65527]
+        double org[3], cell[3];
+        for (int a = 0; a < 3; ++a) {
+            const double lo = (double)world.mn[a] - (double)pad, hi = (double)world.mx[a] + (double)pad;
+            const float cf = (float)(std::max(hi - lo, 1e-30) / kCells);
+            const float of = (float)(lo - 4.0 * (double)cf);
+            hs.q_cell[a] = cf;   // the kernels use exactly these floats: the indices below are computed against them
+            hs.q_origin[a] = of;
+            org[a] = (double)of;
+            cell[a] = (double)cf;
+        }
+        const size_t n_nodes = fn.size() / kNodeStride;
+        hs.qnodes.clear();
+        if (n_nodes <= (size_t)kQNodesMaxNodes) hs.qnodes.resize(n_nodes * kQNodeStride);
+        auto q_lo = [&](float v, int a) -> unsigned {
+            if (!(v > -std::numeric_limits<float>::infinity())) return 0u;
+            if (v == std::numeric_limits<float>::infinity()) return 65535u;
+            const double q = std::floor(((double)v - org[a]) / cell[a]) - kSlack;
+            return (unsigned)std::min(65535.0, std::max(0.0, q));
+        };
+        auto q_hi = [&](float v, int a) -> unsigned {
+            if (!(v < std::numeric_limits<float>::infinity())) return 65535u;
+            if (v == -std::numeric_limits<float>::infinity()) return 0u;
+            const double q = std::ceil(((double)v - org[a]) / cell[a]) + kSlack;
+            return (unsigned)std::min(65535.0, std::max(0.0, q));
+        };
+        auto as_float = [](unsigned u) { float f; memcpy(&f, &u, 4); return f; };
+        ParallelFor(hs.qnodes.empty() ? 0 : n_nodes, nthreads, [&](size_t b, size_t e, int) {
+            for (size_t i = b; i < e; ++i) {
+                const Float4* n = &fn[i * kNodeStride];
+                // n0 = (Lmin.xyz, Lmax.x) n1 = (Lmax.yz, Rmin.xy) n2 = (Rmin.z, Rmax.xyz) n3 = (left, right, -, -)
+                const unsigned lmn[3] = {q_lo(n[0].x, 0), q_lo(n[0].y, 1), q_lo(n[0].z, 2)};
+                const unsigned lmx[3] = {q_hi(n[0].w, 0), q_hi(n[1].x, 1), q_hi(n[1].y, 2)};
+                const unsigned rmn[3] = {q_lo(n[1].z, 0), q_lo(n[1].w, 1), q_lo(n[2].x, 2)};
+                const unsigned rmx[3] = {q_hi(n[2].y, 0), q_hi(n[2].z, 1), q_hi(n[2].w, 2)};
+                Float4* q = &hs.qnodes[i * kQNodeStride];
+                q[0] = Float4{as_float(lmn[0] | (lmn[1] << 16)), as_float(lmn[2] | (lmx[0] << 16)), as_float(lmx[1] | (lmx[2] << 16)),
+                              as_float(rmn[0] | (rmn[1] << 16))};
+                q[1] = Float4{as_float(rmn[2] | (rmx[0] << 16)), as_float(rmx[1] | (rmx[2] << 16)), n[3].x, n[3].y};
+            }
+        });
+    }
     hs.bvh_build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     phase("node layout");
 

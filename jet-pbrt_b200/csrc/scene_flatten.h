@@ -33,6 +33,8 @@ template <class T>
 using BigVec = std::vector<T, DefaultInitAllocator<T>>;
 
 struct HostScene {
+    BigVec<Float4> qnodes;         // the same tree, 32-byte quantised nodes (dev_scene.h kQNodeStride) on the grid below
+    float q_origin[3]{}, q_cell[3]{};
     BigVec<Float4> nodes, slots, slot_nrm;  // per node / per primitive (the shading frames of flat shapes are derived from
                                             // slot_nrm on the device: c_api.cu k_make_frames)
     std::vector<Float4> materials, lights;
@@ -60,6 +62,9 @@ struct HostScene {
 // Deepest tree the traversal kernels can walk without losing a subtree: their node stack holds 64 entries, one of them
 // the sentinel (csrc/intersect.cuh), and a ray has at most one pending subtree per level below the root.
 constexpr int kMaxBvhDepth = 62;
+
+// Trees of more nodes than this get no quantised copy (HostScene::qnodes stays empty): see use_qnodes() in c_api.cu.
+constexpr int kQNodesMaxNodes = 1 << 20;
 
 // BVH topology handed to the flattener by an external builder (the GPU LBVH builder, csrc/bvh_build.cuh): a binary
 // radix tree over the primitives in `order`.  Inner node i covers order[first..last]; a child reference >= 0 is an

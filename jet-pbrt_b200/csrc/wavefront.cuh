@@ -197,7 +197,7 @@ struct ExtendIO {
 // MINB = resident blocks per SM the register allocation must allow (5: 48 registers, 6: 40; measured on B200:
 // 6 is 1-3 % faster on all scenes, 8 = 32 registers spills and is 15-25 % slower).  The 6-block kernels also drop the
 // full-stack test of every push (intersect.cuh: GUARD) and are launched only for trees of verified depth (c_api.cu: fast6).
-template <bool COUNT, int MINB, bool PERM = false>
+template <bool COUNT, int MINB, bool PERM = false, bool QN = false>
 __global__ void __launch_bounds__(kBlock, MINB) k_extend(const __grid_constant__ WfParams p, int it) {
     const int n = min(p.counters[CNT_RAYS * p.counter_stride + it], p.queue_capacity);
     int* work = p.counters + CNT_W_EXTEND * p.counter_stride + it;
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_extend(const __grid_constant__
     TravCounts cnt;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) atomicAdd(p.stats + ST_EXT_RAYS, (unsigned long long)n);
     ExtendIO<PERM> io{p.ray_o[buf], p.ray_d[buf], p.hit, p.perm};
-    traverse_queue<false, COUNT, COUNT || MINB < 6>(p.sc, n, work, io, p.refill_min, p.min_inner, cnt, p.stats + ST_STACK_DROPPED);
+    traverse_queue<false, COUNT, COUNT || MINB < 6, QN>(p.sc, n, work, io, p.refill_min, p.min_inner, cnt, p.stats + ST_STACK_DROPPED);
     if (COUNT) {
         warp_stat_add(p.stats + ST_BOX, cnt.box);
         warp_stat_add(p.stats + ST_PRIM, cnt.prim);
@@ -253,7 +253,7 @@ __device__ __forceinline__ int nee_vertex_count(const WfParams& p, int it) {
            p.counters[(CNT_Q0 + 2) * p.counter_stride + it];
 }
 
-template <bool COUNT, int MINB>
+template <bool COUNT, int MINB, bool QN = false>
 __global__ void __launch_bounds__(kBlock, MINB) k_connect(const __grid_constant__ WfParams p, int it) {
     const long long slots = (long long)nee_vertex_count(p, it) * p.sc.n_nee_lights;
     const int n = (int)(slots < p.shadow_capacity ? slots : p.shadow_capacity);
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_connect(const __grid_constant_
     TravCounts cnt;
     unsigned traced = 0;
     ConnectIO io{&p, &traced};
-    traverse_queue<true, COUNT, COUNT || MINB < 6>(p.sc, n, work, io, p.refill_min, p.min_inner, cnt, p.stats + ST_STACK_DROPPED);
+    traverse_queue<true, COUNT, COUNT || MINB < 6, QN>(p.sc, n, work, io, p.refill_min, p.min_inner, cnt, p.stats + ST_STACK_DROPPED);
     warp_stat_add(p.stats + ST_SHADOW_RAYS, traced);
     if (COUNT) {
         warp_stat_add(p.stats + ST_SH_BOX, cnt.box);

@@ -310,3 +310,24 @@ def test_ray_reordering_does_not_change_the_film(pkg, gpu, name, scale):
         assert st["invalid_contributions"] == 0
         np.testing.assert_allclose(got, plain, rtol=2e-5, atol=1e-6)
     ctx.close()
+
+
+@pytest.mark.parametrize("name,scale,res", [("bunny", 1.0, 256), ("bunny", 0.5, 160), ("large", 0.05, 128), ("cornell", 1.0, 128)])
+def test_quantised_nodes_render_the_same_film(pkg, gpu, name, scale, res):
+    """Option "node_format": the production kernels walk either the 64-byte float nodes or the 32-byte nodes quantised to a
+    16-bit grid (one load per node step; boxes rounded OUTWARDS).  Boxes only prune: the same rays find the same hits,
+    and the same work is done -- only the number of boxes entered may differ."""
+    sc = pkg.HostScene.builtin(name, res, res, scale)
+    ctx = pkg.Context(sc)
+    films, stats = {}, {}
+    for fmt in (0, 1):
+        ctx.clear_film(); ctx.reset_stats()
+        ctx.set_option("node_format", fmt)
+        ctx.render_pass(0, 4, seed=17)
+        films[fmt] = ctx.read_film(finalize=False)
+        stats[fmt] = ctx.stats()
+        assert stats[fmt]["invalid_contributions"] == 0
+    for k in ("samples", "extension_rays", "shadow_rays", "shaded_vertices"):
+        assert stats[0][k] == stats[1][k], k
+    np.testing.assert_allclose(films[1], films[0], rtol=2e-5, atol=1e-6)
+    ctx.close()
