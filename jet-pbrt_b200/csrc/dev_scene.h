@@ -27,7 +27,7 @@ constexpr int kLeafCountBits = 4;
 constexpr int kMaxLeafPrims = 4;
 
 // ---- slot: q0.w carries the tag = type | (primitive_index << 2)
-//   triangle : q0 = p0, q1 = p1, q2 = p2
+//   triangle : q0 = p0, q1 = p1, q2 = p2, q3 = stored normal (a copy of slot_nrm: no third fetch for an accepted candidate)
 //   rectangle: q0 = p0, q1 = p1, q2 = p2, q3 = p3
 //   sphere   : q0 = centre, q1.x = radius
 //   disk     : q0 = position, q1 = normal(xyz) radius(w)

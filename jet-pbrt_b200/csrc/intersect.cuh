@@ -54,7 +54,7 @@ __device__ __forceinline__ bool intersect_slot(const Float4* __restrict__ slot, 
         const f3 v0 = cross(oc, ob), v1 = cross(ob, oa), v2 = cross(oa, oc);
         const float v0d = dot(v0, d), v1d = dot(v1, d), v2d = dot(v2, d);
         if (((v0d < 0) && (v1d < 0) && (v2d < 0)) || ((v0d >= 0) && (v1d >= 0) && (v2d >= 0))) {
-            const f3 n = mk3(ldg4(nrm_rec));
+            const f3 n = mk3(q3);  // the stored normal: a copy rides in the slot's fourth quarter (scene_flatten.cc MakeSlot)
             const float dist = dot(n, oa) / dot(n, d);
             if ((dist > tmin) && (dist < tmax)) { tmax = dist; return true; }
         }
@@ -177,6 +177,8 @@ struct Trav {
 // The stack position is a POINTER into the lane's local array (round 2: with an index the compiler spent an LEA per push and
 // per pop and branched around the push; with the pointer the push is one predicated STL + IADD: 54 instead of 62 instructions
 // per node step -- for 0.3 % of the kernels' time, which is how the L1 pipe, not the issue rate, was found to be their bound).
+// (Caching the newest entry in a register, so that a push followed by a pop touches no memory: measured 3-6 % SLOWER -- the
+// extra register costs spills at 40 registers; profiles/ab/r02_ab_normal_in_slot_tos.log.)
 struct TravStack {
     int* lm;  // the lane's stack, kTraversalStack entries of local memory
     unsigned long long* dropped;  // stats counter of pushes that found the stack full (never in the five configs)

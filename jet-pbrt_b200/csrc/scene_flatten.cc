@@ -91,6 +91,8 @@ bool MakeSlot(const jpbrt_shape& sh, int prim_index, Float4 q[4], Float4* nrm, f
         q[0] = Float4{p0.x, p0.y, p0.z, tagf};
         q[1] = Float4{p1.x, p1.y, p1.z, 0};
         q[2] = Float4{p2.x, p2.y, p2.z, 0};
+        q[3] = Float4{n.x, n.y, n.z, 0};  // the stored normal rides in the record's spare quarter: the second 256-bit load of the
+                                          // triangle test brings it along, and an accepted candidate needs no third fetch
         break;
     case JPBRT_SHAPE_RECTANGLE:  // shape.h:383-393, 449-455
         n = (p1 - p0).Cross(p2 - p0).Normalize();
