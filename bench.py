@@ -82,11 +82,12 @@ def run_peaks(device):
         return None
 
 
-def gather_peak_at(peaks, working_set_bytes):
-    """Divergent 64-byte-record gather bandwidth at a working-set size: log-interpolated between the measured sizes."""
+def gather_peak_at(peaks, working_set_bytes, key="divergent_gbs"):
+    """Divergent 64-byte-record (key "divergent32_gbs": 32-byte-record) gather bandwidth at a working-set size:
+    log-interpolated between the measured sizes."""
     import math
 
-    pts = [(g["working_set_bytes"], g["divergent_gbs"]) for g in peaks["gather64"]]
+    pts = [(g["working_set_bytes"], g.get(key, g["divergent_gbs"])) for g in peaks["gather64"]]
     if working_set_bytes <= pts[0][0]:
         return pts[0][1]
     for (a, fa), (b, fb) in zip(pts, pts[1:]):
@@ -404,7 +405,10 @@ class Bench:
         box, prim = cst["box_tests"] / rays, cst["prim_tests"] / rays
         nodef, primf = cst["node_fetches"] / rays, cst["prim_fetches"] / rays
         lane_bytes = 32.0 * box + 48.0 * prim + 48.0          # every lane's tests as if each were a fetch
-        warp_bytes = 64.0 * nodef + 48.0 * primf + 48.0       # distinct records per warp step + ray in (32+8... 48 B) per ray
+        node_bytes = float(st.get("node_bytes") or 64)       # what a node step FETCHES: 64 (float nodes) or 32 (quantised nodes, mid-size trees)
+        warp_bytes = 64.0 * nodef + 48.0 * primf + 48.0       # ALGORITHMIC: two 24-byte boxes + two child references per distinct node,
+        #                                                        48 B per distinct primitive, ray in / hit out -- whatever the encoding
+        fetched_bytes = node_bytes * nodef + 48.0 * primf + 48.0
         ext_ms = st["ms_extend"]
         n_rays = st["extension_rays"]
         achieved = n_rays * warp_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
@@ -412,7 +416,10 @@ class Bench:
         hbm, hbm_src = measured_hbm_peak()
         r = {"kernel": "k_extend (closest-hit BVH traversal)", "unit": "GB/s", "achieved": achieved,
              "kernel_ms_per_step": ext_ms / steps, "rays_per_step": int(n_rays / steps),
-             "what": "bytes of the DISTINCT 64-byte node / 48-byte primitive records each warp step fetches + 48 B ray/hit per ray, per second of k_extend",
+             "what": "ALGORITHMIC bytes per second of k_extend: the DISTINCT node records (two child boxes + references = 64 B) and 48-byte primitive records "
+                     "each warp step needs + 48 B ray/hit per ray.  Mid-size trees are walked through 32-byte QUANTISED nodes (node_bytes): the same boxes in half "
+                     "the bytes -- see as_fetched for the bytes actually requested",
+             "node_bytes": int(node_bytes),
              "distinct_bytes_per_ray": warp_bytes, "node_fetches_per_ray": nodef, "prim_fetches_per_ray": primf,
              "per_lane_survey8d": {"bytes_per_ray": lane_bytes, "box_tests_per_ray": box, "prim_tests_per_ray": prim, "gbs": lane_gbs,
                                    "note": "32 B per box test + 48 B per primitive test + 48 B per ray, every lane counted (lanes on the same node share a fetch)"},
@@ -434,10 +441,19 @@ class Bench:
                 level, peak = "L2", gather_peak_at(self.peaks, ws)
             else:  # the scene exceeds L2: no gather can beat the L2-resident rate; how much of it comes from DRAM is ncu's to say
                 level, peak = "L2 (upper bound: the scene exceeds the 126 MB L2; a uniformly random gather over it reaches only %.0f GB/s)" % gather_peak_at(self.peaks, ws), l2_peak
-            r.update({"bound": f"issue + {level} gather of 64-byte records (scene working set {ws / 1e6:.1f} MB); ncu: IPC ~2.9 of 4 at ~16-24 of 32 lanes, L1/TEX ~75 % busy, DRAM < 10 %",
+            if node_bytes == 32 and "divergent32_gbs" in self.peaks["gather64"][0]:
+                # what the quantised walk actually requests, against the ceiling of that mix: 32-byte records are ONE 256-bit load each;
+                # the ceiling of the mix = the bytes over the time each part would take at its own ceiling
+                peak32 = gather_peak_at(self.peaks, ws, "divergent32_gbs") if ws > (128 << 10) else self.peaks["gather64"][0]["divergent32_gbs"]
+                t_min = node_bytes * nodef / peak32 + (48.0 * primf + 48.0) / peak
+                fetched_gbs = n_rays * fetched_bytes / (ext_ms * 1e-3) / 1e9 if ext_ms > 0 else 0.0
+                r["as_fetched"] = {"bytes_per_ray": fetched_bytes, "gbs": fetched_gbs, "peak": fetched_bytes / t_min, "frac": fetched_gbs / (fetched_bytes / t_min),
+                                   "gather_peak_32_byte_records_gbs": peak32, "gather_peak_64_byte_records_gbs": peak,
+                                   "what": "the same with the node records at the 32 bytes they are fetched as, against the gather ceiling of that mix of 32- and 64-byte records"}
+            r.update({"bound": f"issue + {level} gather of node and primitive records (scene working set {ws / 1e6:.1f} MB); ncu: IPC ~2.8 of 4 at ~15-21 of 32 lanes, DRAM < 10 %; with float nodes the L1/TEX pipe is the tighter of the two (77-84 % busy: 13 % fewer instructions per node step bought 0.3 %), with quantised nodes the issue rate (L1/TEX 46-56 %, IPC 2.9-3.0)",
                       "peak": peak, "frac": achieved / peak if peak else None,
-                      "peak_source": "measured in this run by jet-pbrt_b200/build/peaks_l2 (scripts/peaks_l2.cu): divergent gather of 64-byte records (one per lane, two 256-bit loads) "
-                                     "at the scene's working-set size",
+                      "peak_source": "measured in this run by jet-pbrt_b200/build/peaks_l2 (scripts/peaks_l2.cu): divergent gather of 64-byte records (one per lane, two 256-bit loads) and of 32-byte records (one load) "
+                                     "at the scene's working-set size; with quantised nodes the ceiling is that of the mix",
                       "gather_peaks_gbs": {"l1_resident": l1_peak, "l2_resident": l2_peak, "dram_random": dram_peak,
                                            "uniform_all_lanes_same_record": max(x["uniform_gbs"] for x in self.peaks["gather64"])},
                       "issue_peak_warp_ginst_s": self.peaks.get("ffma_warp_ginst_s"),

@@ -182,6 +182,8 @@ typedef struct jpbrt_stats {
     /* with "count_traversal": DISTINCT node / primitive records fetched per warp step (lanes of a warp that sit on the same
      * node share one fetch) -- what the memory system has to deliver, as opposed to the per-lane test counts above */
     uint64_t node_fetches, prim_fetches, shadow_node_fetches, shadow_prim_fetches;
+    uint64_t node_bytes;       /* size of the BVH node record the production traversal kernels fetch per node step: 64 (float
+                                * boxes) or 32 (boxes quantised to a 16-bit grid, option "node_format") */
 } jpbrt_stats;
 int jpbrt_get_stats(jpbrt_ctx* ctx, jpbrt_stats* out);
 

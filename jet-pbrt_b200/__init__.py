@@ -36,7 +36,7 @@ class Stats(C.Structure):
                 ("bvh_device_seconds", C.c_double), ("dropped_rays", C.c_uint64), ("stack_overflows", C.c_uint64),
                 ("nee_dropped", C.c_uint64), ("bvh_depth", C.c_uint64), ("ms_reduce", C.c_double),
                 ("node_fetches", C.c_uint64), ("prim_fetches", C.c_uint64), ("shadow_node_fetches", C.c_uint64),
-                ("shadow_prim_fetches", C.c_uint64)]
+                ("shadow_prim_fetches", C.c_uint64), ("node_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -880,6 +880,7 @@ int jpbrt_get_stats(jpbrt_ctx* c, jpbrt_stats* out) {
     out->prim_fetches = h[ST_PRIM_FETCH];
     out->shadow_node_fetches = h[ST_SH_NODE_FETCH];
     out->shadow_prim_fetches = h[ST_SH_PRIM_FETCH];
+    out->node_bytes = (c->opt_trav_blocks >= 6 && c->hs.bvh_depth <= kMaxBvhDepth && use_qnodes(c)) ? 32 : 64;
     out->invalid_contributions = h[ST_INVALID] + h[ST_DROPPED] + h[ST_STACK_DROPPED] + h[ST_NEE_DROPPED];
     out->dropped_rays = h[ST_DROPPED];
     out->stack_overflows = h[ST_STACK_DROPPED];

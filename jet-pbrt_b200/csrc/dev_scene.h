@@ -20,8 +20,8 @@ namespace jpbrt {
 //            n2 = (Rmin.z Rmax.x Rmax.y Rmax.z) n3 = (int left, int right, -, -)
 // child reference >= 0: inner node index;  < 0: leaf, ~ref = (first_slot << 4) | count
 constexpr int kNodeStride = 4;
-// ---- quantised node (32 B): q0 = (Lmin.x|Lmin.y<<16, Lmin.z|Lmax.x<<16, Lmax.y|Lmax.z<<16, Rmin.x|Rmin.y<<16)
-//                             q1 = (Rmin.z|Rmax.x<<16, Rmax.y|Rmax.z<<16, int left, int right);  plane = q_origin + q * q_cell
+// ---- quantised node (32 B): q0 = (Lmin.x|Lmax.x<<16, Lmin.y|Lmax.y<<16, Lmin.z|Lmax.z<<16, Rmin.x|Rmax.x<<16)
+//                             q1 = (Rmin.y|Rmax.y<<16, Rmin.z|Rmax.z<<16, int left, int right);  plane = q_origin + q * q_cell
 constexpr int kQNodeStride = 2;
 constexpr int kLeafCountBits = 4;
 constexpr int kMaxLeafPrims = 4;

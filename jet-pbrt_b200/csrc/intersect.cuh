@@ -165,11 +165,17 @@ constexpr int kTravBlock = 256;        // threads per block of every kernel that
 // Per-lane traversal state.  The BVH walk is a state machine so that a warp can (a) run the inner-node
 // step and the leaf step in separate, converged phases (while-while traversal) and (b) hand a finished
 // lane a new ray while the other lanes keep walking (ray replacement) -- see traverse_queue() below.
+#ifndef JPB_QN_SELECT
+#define JPB_QN_SELECT 1  // quantised walk: near / far planes picked by a per-ray PRMT selector (0: both distances + min / max, A/B)
+#endif
 struct Trav {
     f3 o, d, inv, oi;
     float tmin, tmax;
     int cur, hit;
     int* top;  // one past the newest entry of this lane's node stack
+#if JPB_QN_SELECT
+    unsigned selx, sely, selz;  // quantised walk: PRMT selector of the NEAR plane of each axis (low half = min if the ray runs up the axis)
+#endif
 };  // the node stack is separate (shared + local arrays) so that these scalars stay in registers
 
 // This lane's node stack.  Entry 0 is a sentinel (kTravDone) that is never overwritten: popping an empty stack yields
@@ -210,6 +216,12 @@ __device__ __forceinline__ void trav_init(const DevScene& sc, Trav& t, const f3&
         quant_axis(sc.q_origin[0], sc.q_cell[0], o.x, inv.x, t.inv.x, t.oi.x);
         quant_axis(sc.q_origin[1], sc.q_cell[1], o.y, inv.y, t.inv.y, t.oi.y);
         quant_axis(sc.q_origin[2], sc.q_cell[2], o.z, inv.z, t.inv.z, t.oi.z);
+#if JPB_QN_SELECT
+        // the plane a ray meets first on an axis is the box's min if it runs up the axis, its max if it runs down
+        t.selx = d.x < 0.f ? 0x7632u : 0x7610u;
+        t.sely = d.y < 0.f ? 0x7632u : 0x7610u;
+        t.selz = d.z < 0.f ? 0x7632u : 0x7610u;
+#endif
     } else {
         t.inv = inv;
         // slab distances as one explicit FMA each: bound * inv - o * inv.  Its rounding error (about one ulp of
@@ -246,50 +258,93 @@ struct TravCounts {
 template <bool COUNT, bool ANY_HIT = false, bool GUARD = true, bool QN = false>
 __device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, const TravStack& stk, TravCounts& cnt, unsigned step_mask) {
     const float widen = 1.0000004f;  // 1 + 2*gamma(3): pbrt's conservative slab bound
-    float lx0, ly0, lz0, lx1, ly1, lz1, rx0, ry0, rz0, rx1, ry1, rz1;  // the twelve planes: left min/max, right min/max
     int cl, cr;
+    float ltn, ltf, rtn, rtf;
+    bool hl, hr;
     if (QN) {
         float4 q0, q1;
         ldg8<true>(sc.qnodes + (size_t)t.cur * kQNodeStride, q0, q1);
-        const unsigned w0 = __float_as_uint(q0.x), w1 = __float_as_uint(q0.y), w2 = __float_as_uint(q0.z);
-        const unsigned w3 = __float_as_uint(q0.w), w4 = __float_as_uint(q1.x), w5 = __float_as_uint(q1.y);
+        const unsigned w0 = __float_as_uint(q0.x), w1 = __float_as_uint(q0.y), w2 = __float_as_uint(q0.z);  // left box: x, y, z (min | max << 16)
+        const unsigned w3 = __float_as_uint(q0.w), w4 = __float_as_uint(q1.x), w5 = __float_as_uint(q1.y);  // right box
         const unsigned two23 = 0x4B000000u;  // 8388608.f: a 16-bit q in its low mantissa bits reads 8388608 + q
-        lx0 = __uint_as_float(__byte_perm(w0, two23, 0x7610)); ly0 = __uint_as_float(__byte_perm(w0, two23, 0x7632));
-        lz0 = __uint_as_float(__byte_perm(w1, two23, 0x7610)); lx1 = __uint_as_float(__byte_perm(w1, two23, 0x7632));
-        ly1 = __uint_as_float(__byte_perm(w2, two23, 0x7610)); lz1 = __uint_as_float(__byte_perm(w2, two23, 0x7632));
-        rx0 = __uint_as_float(__byte_perm(w3, two23, 0x7610)); ry0 = __uint_as_float(__byte_perm(w3, two23, 0x7632));
-        rz0 = __uint_as_float(__byte_perm(w4, two23, 0x7610)); rx1 = __uint_as_float(__byte_perm(w4, two23, 0x7632));
-        ry1 = __uint_as_float(__byte_perm(w5, two23, 0x7610)); rz1 = __uint_as_float(__byte_perm(w5, two23, 0x7632));
         cl = __float_as_int(q1.z);
         cr = __float_as_int(q1.w);
+        if (COUNT) {
+            cnt.box += 2;
+            const unsigned same = __match_any_sync(step_mask, t.cur);
+            if ((threadIdx.x & 31) == __ffs(same) - 1) cnt.node_fetch += 1;
+        }
+#if JPB_QN_SELECT
+        // near and far plane of every axis straight out of the node's words: 6 PRMT + 6 FFMA + 4 FMNMX per box
+        // (prmt.b32 spelled in PTX: __byte_perm masks its selector with 0x7777 first -- one LOP3 per axis and step)
+        auto plane = [](unsigned w, unsigned sel) {
+            unsigned r;
+            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "r"(sel));
+            return __uint_as_float(r);
+        };
+        const unsigned fx = t.selx ^ 0x22u, fy = t.sely ^ 0x22u, fz = t.selz ^ 0x22u;
+        ltn = fmaxf(fmaxf(__fmaf_rn(plane(w0, t.selx), t.inv.x, t.oi.x),
+                          __fmaf_rn(plane(w1, t.sely), t.inv.y, t.oi.y)),
+                    fmaxf(__fmaf_rn(plane(w2, t.selz), t.inv.z, t.oi.z), t.tmin));
+        ltf = fminf(fminf(__fmaf_rn(plane(w0, fx), t.inv.x, t.oi.x),
+                          __fmaf_rn(plane(w1, fy), t.inv.y, t.oi.y)),
+                    fminf(__fmaf_rn(plane(w2, fz), t.inv.z, t.oi.z), t.tmax));
+        rtn = fmaxf(fmaxf(__fmaf_rn(plane(w3, t.selx), t.inv.x, t.oi.x),
+                          __fmaf_rn(plane(w4, t.sely), t.inv.y, t.oi.y)),
+                    fmaxf(__fmaf_rn(plane(w5, t.selz), t.inv.z, t.oi.z), t.tmin));
+        rtf = fminf(fminf(__fmaf_rn(plane(w3, fx), t.inv.x, t.oi.x),
+                          __fmaf_rn(plane(w4, fy), t.inv.y, t.oi.y)),
+                    fminf(__fmaf_rn(plane(w5, fz), t.inv.z, t.oi.z), t.tmax));
+        // (no widening of tfar: the quantised boxes are rounded outwards by 2 cells more than the arithmetic can lose)
+        hl = ltn <= ltf;
+        hr = rtn <= rtf;
+#else
+        const float lx0 = __uint_as_float(__byte_perm(w0, two23, 0x7610)), lx1 = __uint_as_float(__byte_perm(w0, two23, 0x7632));
+        const float ly0 = __uint_as_float(__byte_perm(w1, two23, 0x7610)), ly1 = __uint_as_float(__byte_perm(w1, two23, 0x7632));
+        const float lz0 = __uint_as_float(__byte_perm(w2, two23, 0x7610)), lz1 = __uint_as_float(__byte_perm(w2, two23, 0x7632));
+        const float rx0 = __uint_as_float(__byte_perm(w3, two23, 0x7610)), rx1 = __uint_as_float(__byte_perm(w3, two23, 0x7632));
+        const float ry0 = __uint_as_float(__byte_perm(w4, two23, 0x7610)), ry1 = __uint_as_float(__byte_perm(w4, two23, 0x7632));
+        const float rz0 = __uint_as_float(__byte_perm(w5, two23, 0x7610)), rz1 = __uint_as_float(__byte_perm(w5, two23, 0x7632));
+        float a0 = __fmaf_rn(lx0, t.inv.x, t.oi.x), a1 = __fmaf_rn(lx1, t.inv.x, t.oi.x);
+        float b0 = __fmaf_rn(ly0, t.inv.y, t.oi.y), b1 = __fmaf_rn(ly1, t.inv.y, t.oi.y);
+        float c0 = __fmaf_rn(lz0, t.inv.z, t.oi.z), c1 = __fmaf_rn(lz1, t.inv.z, t.oi.z);
+        ltn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), t.tmin));
+        ltf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), t.tmax));
+        a0 = __fmaf_rn(rx0, t.inv.x, t.oi.x); a1 = __fmaf_rn(rx1, t.inv.x, t.oi.x);
+        b0 = __fmaf_rn(ry0, t.inv.y, t.oi.y); b1 = __fmaf_rn(ry1, t.inv.y, t.oi.y);
+        c0 = __fmaf_rn(rz0, t.inv.z, t.oi.z); c1 = __fmaf_rn(rz1, t.inv.z, t.oi.z);
+        rtn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), t.tmin));
+        rtf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), t.tmax));
+        hl = ltn <= ltf * widen;
+        hr = rtn <= rtf * widen;
+#endif
     } else {
         const Float4* np = sc.nodes + (size_t)t.cur * kNodeStride;
         float4 n0, n1, n2, n3;
         ldg8<kWideNodeLoads>(np, n0, n1);
         ldg8<kWideNodeLoads>(np + 2, n2, n3);
-        // left box: min = (n0.x n0.y n0.z), max = (n0.w n1.x n1.y);  right box: min = (n1.z n1.w n2.x), max = (n2.y n2.z n2.w)
-        lx0 = n0.x; ly0 = n0.y; lz0 = n0.z; lx1 = n0.w; ly1 = n1.x; lz1 = n1.y;
-        rx0 = n1.z; ry0 = n1.w; rz0 = n2.x; rx1 = n2.y; ry1 = n2.z; rz1 = n2.w;
         cl = __float_as_int(n3.x);
         cr = __float_as_int(n3.y);
+        if (COUNT) {
+            cnt.box += 2;
+            const unsigned same = __match_any_sync(step_mask, t.cur);  // the lanes of this step that sit on the same node
+            if ((threadIdx.x & 31) == __ffs(same) - 1) cnt.node_fetch += 1;
+        }
+        // left box: min = (n0.x n0.y n0.z), max = (n0.w n1.x n1.y)
+        float a0 = __fmaf_rn(n0.x, t.inv.x, t.oi.x), a1 = __fmaf_rn(n0.w, t.inv.x, t.oi.x);
+        float b0 = __fmaf_rn(n0.y, t.inv.y, t.oi.y), b1 = __fmaf_rn(n1.x, t.inv.y, t.oi.y);
+        float c0 = __fmaf_rn(n0.z, t.inv.z, t.oi.z), c1 = __fmaf_rn(n1.y, t.inv.z, t.oi.z);
+        ltn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), t.tmin));
+        ltf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), t.tmax));
+        // right box: min = (n1.z n1.w n2.x), max = (n2.y n2.z n2.w)
+        a0 = __fmaf_rn(n1.z, t.inv.x, t.oi.x); a1 = __fmaf_rn(n2.y, t.inv.x, t.oi.x);
+        b0 = __fmaf_rn(n1.w, t.inv.y, t.oi.y); b1 = __fmaf_rn(n2.z, t.inv.y, t.oi.y);
+        c0 = __fmaf_rn(n2.x, t.inv.z, t.oi.z); c1 = __fmaf_rn(n2.w, t.inv.z, t.oi.z);
+        rtn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), t.tmin));
+        rtf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), t.tmax));
+        hl = ltn <= ltf * widen;
+        hr = rtn <= rtf * widen;
     }
-    if (COUNT) {
-        cnt.box += 2;
-        const unsigned same = __match_any_sync(step_mask, t.cur);  // the lanes of this step that sit on the same node
-        if ((threadIdx.x & 31) == __ffs(same) - 1) cnt.node_fetch += 1;
-    }
-    float a0 = __fmaf_rn(lx0, t.inv.x, t.oi.x), a1 = __fmaf_rn(lx1, t.inv.x, t.oi.x);
-    float b0 = __fmaf_rn(ly0, t.inv.y, t.oi.y), b1 = __fmaf_rn(ly1, t.inv.y, t.oi.y);
-    float c0 = __fmaf_rn(lz0, t.inv.z, t.oi.z), c1 = __fmaf_rn(lz1, t.inv.z, t.oi.z);
-    const float ltn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), t.tmin));
-    const float ltf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), t.tmax));
-    a0 = __fmaf_rn(rx0, t.inv.x, t.oi.x); a1 = __fmaf_rn(rx1, t.inv.x, t.oi.x);
-    b0 = __fmaf_rn(ry0, t.inv.y, t.oi.y); b1 = __fmaf_rn(ry1, t.inv.y, t.oi.y);
-    c0 = __fmaf_rn(rz0, t.inv.z, t.oi.z); c1 = __fmaf_rn(rz1, t.inv.z, t.oi.z);
-    const float rtn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), t.tmin));
-    const float rtf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), t.tmax));
-    const bool hl = ltn <= ltf * widen;
-    const bool hr = rtn <= rtf * widen;
     const bool both = hl && hr;
     // the nearer child first, left on ties (the reference's order, bvh.h:99-100): right_first = both ? ltn > rtn : hr, spelled
     // as one predicate expression (4 fewer instructions per step than the select chain the ternary compiled to)

@@ -1038,9 +1038,11 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, Bv
                 const unsigned rmn[3] = {q_lo(n[1].z, 0), q_lo(n[1].w, 1), q_lo(n[2].x, 2)};
                 const unsigned rmx[3] = {q_hi(n[2].y, 0), q_hi(n[2].z, 1), q_hi(n[2].w, 2)};
                 Float4* q = &hs.qnodes[i * kQNodeStride];
-                q[0] = Float4{as_float(lmn[0] | (lmn[1] << 16)), as_float(lmn[2] | (lmx[0] << 16)), as_float(lmx[1] | (lmx[2] << 16)),
-                              as_float(rmn[0] | (rmn[1] << 16))};
-                q[1] = Float4{as_float(rmn[2] | (rmx[0] << 16)), as_float(rmx[1] | (rmx[2] << 16)), n[3].x, n[3].y};
+                // one word per (box, axis): min in the low half, max in the high half -- the kernel picks the ray's near and far
+                // plane of an axis out of one word with a per-ray PRMT selector (no min / max of the two distances)
+                q[0] = Float4{as_float(lmn[0] | (lmx[0] << 16)), as_float(lmn[1] | (lmx[1] << 16)), as_float(lmn[2] | (lmx[2] << 16)),
+                              as_float(rmn[0] | (rmx[0] << 16))};
+                q[1] = Float4{as_float(rmn[1] | (rmx[1] << 16)), as_float(rmn[2] | (rmx[2] << 16)), n[3].x, n[3].y};
             }
         });
     }

@@ -41,8 +41,9 @@ __device__ __forceinline__ unsigned hash32(unsigned x) {
     return x;
 }
 
-// Every lane gathers `iters` x 4 independent 64-byte records.  UNIFORM: the index depends on the warp only.
-template <bool UNIFORM>
+// Every lane gathers `iters` x 4 independent records of 64 bytes (two 256-bit loads: the float BVH node, a triangle slot) or,
+// HALF, of 32 bytes (one 256-bit load: the quantised node).  UNIFORM: the index depends on the warp only.
+template <bool UNIFORM, bool HALF = false>
 __global__ void __launch_bounds__(kBlock, 6) k_gather(const float4* __restrict__ recs, unsigned mask, int iters, float* sink) {
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned s = hash32((UNIFORM ? (tid >> 5) : tid) * 2654435761u + 12345u);
@@ -52,9 +53,10 @@ __global__ void __launch_bounds__(kBlock, 6) k_gather(const float4* __restrict__
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             s = s * 1664525u + 1013904223u;
-            const float4* p = recs + (size_t)((s >> 7) & mask) * 4;
+            const float4* p = recs + (size_t)((s >> 7) & mask) * (HALF ? 2 : 4);
             ldg256(p, a[u], b[u]);
-            ldg256(p + 2, c[u], d[u]);
+            if (!HALF) ldg256(p + 2, c[u], d[u]);
+            else c[u] = d[u] = a[u];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) acc += a[u].x + b[u].y + c[u].z + d[u].w;
@@ -140,8 +142,10 @@ int main(int argc, char** argv) {
         const double recs = (double)grid * kBlock * iters * 4;
         const double ms_d = time_ms([&] { k_gather<false><<<grid, kBlock>>>(buf, mask, iters, sink); }, 5);
         const double ms_u = time_ms([&] { k_gather<true><<<grid, kBlock>>>(buf, mask, iters, sink); }, 5);
-        printf("%s{\"working_set_bytes\": %zu, \"divergent_gbs\": %.1f, \"divergent_grecords_s\": %.2f, \"uniform_gbs\": %.1f}", first ? "" : ", ",
-               w, recs * 64 / (ms_d * 1e-3) / 1e9, recs / (ms_d * 1e-3) / 1e9, recs * 64 / (ms_u * 1e-3) / 1e9);
+        // the same working set as 32-byte records (twice as many of them)
+        const double ms_h = time_ms([&] { k_gather<false, true><<<grid, kBlock>>>(buf, (unsigned)(w / 32 - 1), iters, sink); }, 5);
+        printf("%s{\"working_set_bytes\": %zu, \"divergent_gbs\": %.1f, \"divergent_grecords_s\": %.2f, \"uniform_gbs\": %.1f, \"divergent32_gbs\": %.1f, \"divergent32_grecords_s\": %.2f}", first ? "" : ", ",
+               w, recs * 64 / (ms_d * 1e-3) / 1e9, recs / (ms_d * 1e-3) / 1e9, recs * 64 / (ms_u * 1e-3) / 1e9, recs * 32 / (ms_h * 1e-3) / 1e9, recs / (ms_h * 1e-3) / 1e9);
         first = false;
     }
     printf("]");
