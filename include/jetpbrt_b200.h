@@ -256,7 +256,9 @@ int jpbrt_device_count(void);
 
 /* Host-only view of what jpbrt_upload_scene would upload, for validating the BVH and the flattened
  * tables without a GPU.  `what`: 0 nodes, 1 slots, 2 slot_nrm (float4 records); 3 slot_ml (int2),
- * 4 prim_slot (int); 5 materials, 6 lights (float4 records).  Copies up to `capacity` 32-bit words
+ * 4 prim_slot (int); 5 materials, 6 lights (float4 records); 7 the 32-byte quantised nodes (8 words each: six
+ * min | max << 16 plane-index words, two child references; empty for trees of more than 2^20 nodes), 8 their grid
+ * (origin xyz, cell xyz).  Copies up to `capacity` 32-bit words
  * into `out` (may be NULL) and returns the total number of 32-bit words, or a negative status. */
 long long jpbrt_debug_flatten(const jpbrt_scene_desc* desc, int what, void* out, long long capacity);
 

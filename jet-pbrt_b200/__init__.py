@@ -421,7 +421,8 @@ def device_count() -> int:
 
 
 _TABLES = {"nodes": (0, np.float32), "slots": (1, np.float32), "slot_nrm": (2, np.float32), "slot_ml": (3, np.int32),
-           "prim_slot": (4, np.int32), "materials": (5, np.float32), "lights": (6, np.float32)}
+           "prim_slot": (4, np.int32), "materials": (5, np.float32), "lights": (6, np.float32), "qnodes": (7, np.uint32),
+           "qgrid": (8, np.float32)}
 
 
 def debug_flatten(scene: HostScene, table: str) -> np.ndarray:

@@ -512,6 +512,12 @@ long long jpbrt_debug_flatten(const jpbrt_scene_desc* desc, int what, void* out,
     case 4: src = hs.prim_slot.data(); words = (long long)hs.prim_slot.size(); break;
     case 5: src = hs.materials.data(); words = (long long)hs.materials.size() * 4; break;
     case 6: src = hs.lights.data(); words = (long long)hs.lights.size() * 4; break;
+    case 7: src = hs.qnodes.data(); words = (long long)hs.qnodes.size() * 4; break;
+    case 8: {  // the quantised nodes' grid: origin xyz, cell xyz
+        float grid[6] = {hs.q_origin[0], hs.q_origin[1], hs.q_origin[2], hs.q_cell[0], hs.q_cell[1], hs.q_cell[2]};
+        if (out && capacity > 0) memcpy(out, grid, (size_t)std::min(6ll, capacity) * 4);
+        return 6;
+    }
     default: return set_error(nullptr, JPBRT_ERR_INVALID, "unknown table %d", what);
     }
     if (out && capacity > 0) memcpy(out, src, (size_t)std::min(words, capacity) * 4);

@@ -794,7 +794,10 @@ int FlattenScene(const jpbrt_scene_desc* d, HostScene* out, std::string* err, Bv
     // ray origins are the camera position or points on surfaces: include the camera in the magnitude
     for (int a = 0; a < 3; ++a) maxabs = std::max(maxabs, std::fabs(d->camera.pos[a]));
     const float pad = 4e-6f * maxabs + 1e-30f;
-    Builder bld(boxes, nthreads);
+    // (Scenes small enough for the insertion-based optimisation below are built by ONE thread: the pass visits nodes in an order
+    // that depends on their temporary ids, which concurrent subtree tasks hand out in timing order -- the same scene must
+    // flatten to the same tree every time.)
+    Builder bld(boxes, N <= (1 << 18) ? 1 : nthreads);
     phase("builder setup (centroids)");
     int root = -1;
     if (build && N >= 2) {

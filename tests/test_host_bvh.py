@@ -183,3 +183,28 @@ def test_coincident_centroids_build_a_shallow_valid_tree(pkg):
     nodes, refs, slots, nrm = decode(pkg, sc)
     depth = check_tree(nodes, refs, slots, nrm, pkg.debug_flatten(sc, "prim_slot"), sc.d.n_primitives)
     assert depth <= 20, depth
+
+
+@pytest.mark.parametrize("name,scale", [("cornell", 1.0), ("bunny", 1.0), ("glossy", 1.0), ("large", 0.1)])
+def test_quantised_nodes_contain_the_float_nodes(pkg, name, scale):
+    """The 32-byte nodes the production kernels walk mid-size trees through (csrc/intersect.cuh, QN): every plane index, turned
+    back into a coordinate with the grid the kernels use, lies OUTSIDE the float box by at least two cells (the slack the
+    kernels' 2^23-offset arithmetic may consume) and by at most four; child references are the float nodes' own."""
+    sc = pkg.HostScene.builtin(name, 64, 64, scale)
+    nodes = pkg.debug_flatten(sc, "nodes").reshape(-1, 16)
+    q = pkg.debug_flatten(sc, "qnodes").reshape(-1, 8)
+    grid = pkg.debug_flatten(sc, "qgrid").astype(np.float64)
+    origin, cell = grid[:3], grid[3:]
+    assert len(q) == len(nodes) and (cell > 0).all()
+    assert np.array_equal(q[:, 6:8], nodes[:, 12:14].view(np.uint32))
+    planes = q[:, :6].astype(np.int64)
+    lo, hi = planes & 0xffff, planes >> 16                       # per (box, axis): L.x L.y L.z R.x R.y R.z
+    fmin = np.concatenate([nodes[:, 0:3], nodes[:, 6:9]], axis=1).astype(np.float64)     # Lmin.xyz, Rmin.xyz
+    fmax = np.concatenate([nodes[:, 3:6], nodes[:, 9:12]], axis=1).astype(np.float64)    # Lmax.xyz, Rmax.xyz
+    o6, c6 = np.tile(origin, 2), np.tile(cell, 2)
+    finite = np.isfinite(fmin) & np.isfinite(fmax)               # (the wrapped root of a one-leaf scene has an infinite dummy box)
+    below = (fmin - (o6 + lo * c6)) / c6
+    above = ((o6 + hi * c6) - fmax) / c6
+    assert (below[finite] >= 2.0 - 1e-6).all() and (below[finite] <= 4.0 + 1e-6).all(), (below[finite].min(), below[finite].max())
+    assert (above[finite] >= 2.0 - 1e-6).all() and (above[finite] <= 4.0 + 1e-6).all(), (above[finite].min(), above[finite].max())
+    assert lo.min() >= 0 and hi.max() <= 65535 and (lo[finite] < hi[finite]).all()
