@@ -165,6 +165,9 @@ constexpr int kTravBlock = 256;        // threads per block of every kernel that
 // Per-lane traversal state.  The BVH walk is a state machine so that a warp can (a) run the inner-node
 // step and the leaf step in separate, converged phases (while-while traversal) and (b) hand a finished
 // lane a new ray while the other lanes keep walking (ray replacement) -- see traverse_queue() below.
+#ifndef JPB_QN_FAST_RCP
+#define JPB_QN_FAST_RCP 1
+#endif
 #ifndef JPB_QN_SELECT
 #define JPB_QN_SELECT 1  // quantised walk: near / far planes picked by a per-ray PRMT selector (0: both distances + min / max, A/B)
 #endif
@@ -211,8 +214,19 @@ template <bool QN = false>
 __device__ __forceinline__ void trav_init(const DevScene& sc, Trav& t, const f3& o, const f3& d, float tmin, float tmax) {
     t.o = o;
     t.d = d;
-    const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     if (QN) {
+        // (the slab constants of the quantised walk feed box tests with two cells of slack: the hardware's approximate reciprocal
+        //  -- one MUFU instead of the ~12-instruction IEEE division with its slow-path branch, three times per ray -- is exact
+        //  enough by four orders of magnitude; a flushed denormal or zero component gives +-inf and the axis drops out below.
+        //  Measured: k_extend -0.9 %, k_connect -1.0 % on the bunny scene, film unchanged; profiles/ab/r02_ab_qn_fast_rcp_farsel.log)
+#if JPB_QN_FAST_RCP
+        f3 inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(d.x));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(d.y));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv.z) : "f"(d.z));
+#else
+        const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+#endif
         quant_axis(sc.q_origin[0], sc.q_cell[0], o.x, inv.x, t.inv.x, t.oi.x);
         quant_axis(sc.q_origin[1], sc.q_cell[1], o.y, inv.y, t.inv.y, t.oi.y);
         quant_axis(sc.q_origin[2], sc.q_cell[2], o.z, inv.z, t.inv.z, t.oi.z);
@@ -223,6 +237,7 @@ __device__ __forceinline__ void trav_init(const DevScene& sc, Trav& t, const f3&
         t.selz = d.z < 0.f ? 0x7632u : 0x7610u;
 #endif
     } else {
+        const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
         t.inv = inv;
         // slab distances as one explicit FMA each: bound * inv - o * inv.  Its rounding error (about one ulp of
         // |o * inv|) is covered by the padding baked into every stored box (4e-6 * the largest ray-origin
@@ -282,6 +297,7 @@ __device__ __forceinline__ void trav_node_step(const DevScene& sc, Trav& t, cons
             asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "r"(sel));
             return __uint_as_float(r);
         };
+        // (the far planes' selectors: derived here -- keeping them in three more registers measured +-0)
         const unsigned fx = t.selx ^ 0x22u, fy = t.sely ^ 0x22u, fz = t.selz ^ 0x22u;
         ltn = fmaxf(fmaxf(__fmaf_rn(plane(w0, t.selx), t.inv.x, t.oi.x),
                           __fmaf_rn(plane(w1, t.sely), t.inv.y, t.oi.y)),
