@@ -208,3 +208,62 @@ def test_quantised_nodes_contain_the_float_nodes(pkg, name, scale):
     assert (below[finite] >= 2.0 - 1e-6).all() and (below[finite] <= 4.0 + 1e-6).all(), (below[finite].min(), below[finite].max())
     assert (above[finite] >= 2.0 - 1e-6).all() and (above[finite] <= 4.0 + 1e-6).all(), (above[finite].min(), above[finite].max())
     assert lo.min() >= 0 and hi.max() <= 65535 and (lo[finite] < hi[finite]).all()
+
+
+def _fma32(a, b, c):
+    """float32 fused multiply-add: the product of two float32 is exact in float64, one rounding to float32 at the end
+    (the float64 addition's own rounding is 2^29 times finer)."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+@pytest.mark.parametrize("name,scale", [("bunny", 1.0), ("large", 0.1), ("cornell", 1.0)])
+def test_quantised_slab_arithmetic_never_rejects_a_box_the_float_test_enters(pkg, name, scale):
+    """The kernels' quantised slab test, restated in numpy float32 (csrc/intersect.cuh: quant_axis + the QN branch of
+    trav_node_step: t = (2^23 + q) * (cell * inv) + ((origin - o) * inv - 2^23 * cell * inv), near / far plane picked by the
+    sign of the direction, no widening), run on the scene's real nodes with rays aimed at them -- many nearly parallel to
+    an axis, the hard case for the 2^23 cancellation: it must enter every box the exact test on the float box enters."""
+    f32 = np.float32
+    sc = pkg.HostScene.builtin(name, 64, 64, scale)
+    nodes = pkg.debug_flatten(sc, "nodes").reshape(-1, 16)
+    q = pkg.debug_flatten(sc, "qnodes").reshape(-1, 8)
+    grid = pkg.debug_flatten(sc, "qgrid")
+    origin, cell = grid[:3].astype(f32), grid[3:].astype(f32)
+    rng = np.random.default_rng(11)
+    n = 400_000
+    pick = rng.integers(0, len(nodes), n)
+    bmin, bmax = nodes[pick, 0:3].astype(np.float64), nodes[pick, 3:6].astype(np.float64)   # the LEFT child box of a random node
+    ok = np.isfinite(bmin).all(axis=1) & np.isfinite(bmax).all(axis=1)
+    planes = q[pick, 0:3].astype(np.int64)
+    qlo, qhi = (planes & 0xffff).astype(f32), (planes >> 16).astype(f32)
+    wmin, wmax = nodes[:, 0:3][np.isfinite(nodes[:, 0:3]).all(axis=1)].min(axis=0), nodes[:, 3:6][np.isfinite(nodes[:, 3:6]).all(axis=1)].max(axis=0)
+    o = rng.uniform(wmin, wmax, (n, 3))
+    ext = np.maximum(bmax - bmin, 1e-3)
+    tgt = 0.5 * (bmin + bmax) + rng.uniform(-0.7, 0.7, (n, 3)) * ext                       # inside or just outside the box
+    par = rng.random(n) < 0.4                                                              # nearly axis-parallel rays
+    k = rng.integers(0, 3, n)
+    o[par, k[par]] = tgt[par, k[par]] + rng.uniform(-1e-5, 1e-5, par.sum()) * ext[par, k[par]]
+    o = o.astype(f32)
+    d = tgt - o.astype(np.float64)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = d.astype(f32)
+    with np.errstate(divide="ignore", over="ignore", invalid="ignore"):
+        inv = (f32(1) / d).astype(f32)   # (the kernels use the hardware's approximate reciprocal: 1 ulp more, four orders below the slack)
+        cinv = (cell * inv).astype(f32)
+        oiq = _fma32((origin - o).astype(f32), inv, (f32(-8388608.0) * cinv).astype(f32))
+        dead = ~(np.abs(oiq) <= f32(3.4028234664e38))                                      # the axis drops out (NaN constants)
+        t_lo = _fma32((f32(8388608.0) + qlo).astype(f32), cinv, oiq)
+        t_hi = _fma32((f32(8388608.0) + qhi).astype(f32), cinv, oiq)
+        near = np.where(d < 0, t_hi, t_lo)
+        far = np.where(d < 0, t_lo, t_hi)
+        near[dead], far[dead] = -np.inf, np.inf
+        tn = np.maximum(near.max(axis=1), f32(0.001))
+        tf = far.min(axis=1)
+        hit_q = tn <= tf
+        t0 = (bmin - o) / d.astype(np.float64)
+        t1 = (bmax - o) / d.astype(np.float64)
+        degenerate = ~np.isfinite(t0).all(axis=1) | ~np.isfinite(t1).all(axis=1)
+        hit_exact = np.maximum(np.minimum(t0, t1).max(axis=1), 0.001) <= np.maximum(t0, t1).min(axis=1)
+    use = ok & ~degenerate
+    assert hit_exact[use].sum() > 0.2 * n
+    missed = use & hit_exact & ~hit_q
+    assert missed.sum() == 0, f"{missed.sum()} boxes entered by the exact test are rejected by the quantised arithmetic"
