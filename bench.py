@@ -20,10 +20,12 @@ The ONE JSON line rank 0 prints:
   configs (N = 1): every other BASELINE config (cornell, large at 64 spp, glossy at 64 spp) with value / e2e / roofline /
           cpu_baseline / image error, measured by the same code.
   roofline : the closest-hit traversal kernel (k_extend) against ceilings MEASURED in this run on this GPU by
-          jet-pbrt_b200/build/peaks_l2 (scripts/peaks_l2.cu): bytes of the DISTINCT node / primitive records each warp step
-          fetches (+ ray in, hit out) per second, over the gather bandwidth of 64-byte records at the scene's working-set
-          size.  The per-lane SURVEY 8(d) figure, the HBM stream peak (MEASURED_PEAKS.json), the DRAM traffic and the
-          issue-slot utilisation from this build's ncu capture (profiles/r02_ncu_constants.json) are quoted beside it.
+          jet-pbrt_b200/build/peaks_l2 (scripts/peaks_l2.cu): ALGORITHMIC bytes -- the DISTINCT node (two boxes + two child
+          references = 64 B) and primitive records each warp step needs (+ ray in, hit out) -- per second, over the gather
+          bandwidth of 64-byte records at the scene's working-set size.  Where the tree is walked through the 32-byte quantised
+          nodes (stats.node_bytes), `as_fetched` gives the bytes actually requested against the ceiling of that mix of 32- and
+          64-byte records.  The per-lane SURVEY 8(d) figure, the HBM stream peak (MEASURED_PEAKS.json), the DRAM traffic and
+          the issue-slot utilisation from this build's ncu capture (profiles/r02_ncu_constants.json) are quoted beside it.
   cpu_baseline : the UNMODIFIED reference (oracle/_ref) on this host's cores, on a bounded sample of the same workload.
   reduce_check (N > 1): the NCCL-reduced film against all N x spp samples rendered by rank 0 alone.
 """

@@ -5,9 +5,10 @@
 // Primitive tests keep the reference's exact float expressions (compiled with -fmad=false): the
 // set of accepted (ray, primitive) pairs and every accepted t are bit-identical to the CPU code.
 // The BVH only prunes: boxes are padded and tested conservatively (reciprocal-multiply slabs
-// widened by 2*gamma(3)), traversal is front-to-back with early-out, and an any-hit variant
-// serves shadow rays -- none of which can change a hit, only the tie-break between primitives
-// that report EXACTLY equal t.
+// widened by 2*gamma(3); or, for mid-size trees, 32-byte nodes quantised to a 16-bit grid and rounded
+// outwards), traversal is front-to-back with early-out, and an any-hit variant serves shadow rays --
+// none of which can change a hit, only the tie-break between primitives that report EXACTLY equal t
+// (SURVEY.md Appendix A.6).
 #pragma once
 
 #include "dev_scene.h"
