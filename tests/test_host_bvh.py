@@ -267,3 +267,14 @@ def test_quantised_slab_arithmetic_never_rejects_a_box_the_float_test_enters(pkg
     assert hit_exact[use].sum() > 0.2 * n
     missed = use & hit_exact & ~hit_q
     assert missed.sum() == 0, f"{missed.sum()} boxes entered by the exact test are rejected by the quantised arithmetic"
+
+
+def test_the_same_scene_flattens_to_the_same_tables(pkg):
+    """50 k primitives: large enough for concurrent subtree tasks, small enough for the insertion-based optimisation pass, whose
+    visiting order depends on the temporary node ids -- which used to be handed out in thread-timing order (sibling leaves came
+    out swapped from one upload to the next).  Such scenes are now built by one thread; bigger ones skip the pass."""
+    sc = pkg.HostScene.builtin("large", 64, 64, 0.1)
+    first = {t: pkg.debug_flatten(sc, t).tobytes() for t in ("nodes", "qnodes", "slots", "prim_slot")}
+    for _ in range(3):
+        for t, ref in first.items():
+            assert pkg.debug_flatten(sc, t).tobytes() == ref, t
